@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py -- MPHF build / batched lookup throughput on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one complete MPHF construction (Mphf::new_parallel, gamma = 1.7) over the workload's
+synthetic key set, keys resident in HBM when the timed region starts.  The same run also reports
+ * lookup:  batched Mphf::hash of every key against the built structure (Mkeys/s),
+ * e2e:     the same build through the C ABI with HOST (pinned) keys: H2D copy, build, and the D2H
+            export of all level words + ranks inside the timed region,
+ * roofline for the dominant kernel (CUDA events inside the library, on the launching stream),
+ * cpu_baseline: the oracle's restatement of new_parallel on this box's host cores.
+One JSON line on stdout (rank 0).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as ge  # noqa: E402
+
+METRIC = "mphf_build_throughput"
+UNIT = "Mkeys/s"
+GAMMA = 1.7
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        self.idx = device_index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                for line in out.strip().splitlines():
+                    self.rows.append([c.strip() for c in line.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def algorithmic_bytes(stats):
+    """B_l = 16k + 8c + 41W per level (key read in mark and in filter, redo write, zeroing
+    of a and collide, finalize read a/read collide/write a, ranks).  Returns total and per-kernel splits."""
+    ks, bits = stats["keys_in"], stats["bits"]
+    total = 0
+    per_pass = []
+    for l, (k, b) in enumerate(zip(ks, bits)):
+        w = (b + 63) // 64
+        c = ks[l + 1] if l + 1 < len(ks) else 0
+        total += 16 * k + 8 * c + 41 * w
+        # this implementation's pass(l) kernel: reads the keys that entered level l-1 (level 0: the input),
+        # writes level l's list.  pass(0) = 8k; pass(l) = 8 k_{l-1} + 8 k_l
+        per_pass.append(8 * k if l == 0 else 8 * ks[l - 1] + 8 * k)
+    return total, per_pass
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference algorithm (oracle restatement of Mphf::new_parallel; the Rust crate cannot be
+    compiled in this image) on the host cores, same config / metric / unit."""
+    if rank != 0:
+        return
+    orc = ge.load_oracle()
+    orc.build_lib()
+    n = args.ref_keys
+    keys = orc.keygen(n, seed=1, kind=0)
+    threads = orc.max_threads()
+    for _ in range(args.warmup):
+        orc.OracleMphf.new_parallel(GAMMA, keys[: max(n // 10, 1)], None, nthreads=threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        m = orc.OracleMphf.new_parallel(GAMMA, keys, None, nthreads=threads)
+    dt = (time.perf_counter() - t0) / args.steps
+    val = n / dt / 1e6
+    tq = time.perf_counter()
+    m.hash_batch(keys[: min(n, 20_000_000)], nthreads=threads)
+    lookup = min(n, 20_000_000) / (time.perf_counter() - tq) / 1e6
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": "Mphf::new_parallel gamma=1.7 on %d distinct random u64 keys (bounded sample of the 1e8-key config)" % n,
+                   "gamma": GAMMA, "n_keys": n},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": "%d keys per step, OpenMP restatement of new_parallel (rustc absent)" % n},
+        "lookup": {"value": lookup, "unit": UNIT, "cores": threads},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--keys", type=int, default=100_000_000, help="keys per GPU (BASELINE configs[1]: 1e8)")
+    ap.add_argument("--ref-keys", type=int, default=100_000_000, help="keys per step of the CPU reference arm")
+    ap.add_argument("--cpu-baseline-keys", type=int, default=100_000_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    pkg = ge.load_package()
+    pkg.build_native()
+    L = pkg.lib()
+    n = args.keys
+    stream = torch.cuda.current_stream(dev)
+
+    # ---- synthetic input, resident in HBM: distinct-by-construction random u64 keys -------------
+    keys = torch.empty(n, dtype=torch.int64, device=dev)
+    assert L.bphf_keygen_u64(C.c_void_p(keys.data_ptr()), rank * n, n, 1, 0, local_rank, None) == 0
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def build():
+        return pkg.Mphf.new_parallel(GAMMA, keys, None, stream=stream)
+
+    # ---- warm-up ---------------------------------------------------------------------------------------------
+    L.bphf_set_profile(1)
+    m = None
+    for _ in range(max(args.warmup, 3)):
+        m = build()
+    stats = m.build_stats()
+
+    # ---- timed: K builds, device time via CUDA events on the launching stream -----------------------------------
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pass_ms = [0.0, 0.0]
+    launches = 0
+    barrier()
+    with ClockSampler(local_rank) as clocks:
+        e0.record(stream)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            m = build()
+            st = m.build_stats()
+            pass_ms[0] += st["pass_ms"][0]
+            pass_ms[1] += st["pass_ms"][1] if len(st["pass_ms"]) > 1 else 0.0
+            launches += st["kernel_launches"]
+        e1.record(stream)
+        barrier()
+        wall = time.perf_counter() - t0
+    dev_ms = e0.elapsed_time(e1)
+    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / args.steps
+    value = world * n / (ms_per_step * 1e-3) / 1e6
+
+    # ---- lookup: hash every key (device resident), K passes ------------------------------------------------------
+    out = torch.empty(n, dtype=torch.int64, device=dev)
+    for _ in range(3):
+        m.hash_batch(keys, out=out, stream=stream)
+    barrier()
+    q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    q0.record(stream)
+    for _ in range(args.steps):
+        m.hash_batch(keys, out=out, stream=stream)
+    q1.record(stream)
+    barrier()
+    tq = torch.tensor([q0.elapsed_time(q1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tq, op=dist.ReduceOp.MAX)
+    q_ms = float(tq.item()) / args.steps
+    lookup_val = world * n / (q_ms * 1e-3) / 1e6
+    bad = C.c_uint64(1)
+    assert L.bphf_check_permutation(C.c_void_p(out.data_ptr()), n, local_rank, C.byref(bad)) == 0
+    permutation_ok = bad.value == 0
+
+    # ---- end to end through the C ABI with host buffers --------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        hk = torch.empty(n, dtype=torch.int64).pin_memory()
+        hk.copy_(keys)
+        tw, tr, _ = m.total_dims()
+        words = torch.empty(tw, dtype=torch.int64).pin_memory()
+        ranks = torch.empty(tr, dtype=torch.int64).pin_memory()
+        hk_np = hk.numpy().view(np.uint64)
+
+        def e2e_step():
+            mm = pkg.Mphf.new_parallel(GAMMA, hk_np, None, device=local_rank)
+            assert L.bphf_export_all(mm._h, C.c_void_p(words.data_ptr()), C.c_void_p(ranks.data_ptr()), 0) == 0
+            return mm
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        barrier()
+        dt = torch.tensor([(time.perf_counter() - t0) / args.steps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * n / float(dt.item()) / 1e6, "unit": UNIT, "h2d_bytes_per_step": 8 * n,
+               "d2h_bytes_per_step": 8 * (tw + tr), "ms_per_step": float(dt.item()) * 1e3,
+               "what": "bphf_build_u64(host pinned keys) + bphf_export_all(host) per step, wall clock"}
+        del hk, words, ranks
+
+    # ---- roofline of the dominant kernel -----------------------------------------------------------------------
+    peak, peak_src = measured_peaks()
+    total_bytes, per_pass = algorithmic_bytes(stats)
+    dom = 0 if pass_ms[0] >= pass_ms[1] else 1
+    k_ms = pass_ms[dom] / args.steps
+    achieved = per_pass[dom] / (k_ms * 1e-3) / 1e9 if k_ms > 0 else None
+    roofline = {
+        "bound": "hbm", "kernel": "pass0_kernel (level-0 mark)" if dom == 0 else "pass_kernel level 1 (filter+compact+mark)",
+        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+        "traffic": None, "peak_source": peak_src, "kernel_ms": k_ms, "algorithmic_bytes_per_launch": per_pass[dom],
+        "pass0_ms": pass_ms[0] / args.steps, "pass1_ms": pass_ms[1] / args.steps,
+        "whole_build": {"algorithmic_bytes": total_bytes, "bytes_per_key": total_bytes / n,
+                        "achieved": total_bytes / (ms_per_step * 1e-3) / 1e9, "frac": total_bytes / (ms_per_step * 1e-3) / 1e9 / peak},
+        "lookup": {"algorithmic_bytes_per_key": 16.0 + 8.0 * (m.total_dims()[0] + m.total_dims()[1]) / n,
+                   "achieved": (16.0 * n + 8.0 * (m.total_dims()[0] + m.total_dims()[1])) / (q_ms * 1e-3) / 1e9},
+    }
+    roofline["lookup"]["frac"] = roofline["lookup"]["achieved"] / peak
+
+    # ---- CPU baseline (oracle port of new_parallel on the host cores), rank 0 at N=1 only ------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        orc = ge.load_oracle()
+        nc = args.cpu_baseline_keys
+        ck = orc.keygen(nc, seed=1, kind=0)
+        threads = orc.max_threads()
+        t0 = time.perf_counter()
+        ref = orc.OracleMphf.new_parallel(GAMMA, ck, None, nthreads=threads)
+        dt = time.perf_counter() - t0
+        cpu = {"value": nc / dt / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": "one new_parallel(1.7) over %d keys of the same generator (%.1f s); C/OpenMP restatement, rustc absent" % (nc, dt)}
+        if nc == n:
+            same = orc.fingerprint(ref.levels()) == orc.fingerprint(m.levels())
+            cpu["bit_exact_vs_gpu"] = bool(same)
+        del ref, ck
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64", "data": "synthetic",
+            "config": {"workload": "Mphf::new_parallel gamma=1.7 on 1e8 distinct random u64 keys per GPU (BASELINE configs[1])"
+                       if n == 100_000_000 else "Mphf::new_parallel gamma=1.7 on %d keys per GPU" % n,
+                       "gamma": GAMMA, "n_keys_per_gpu": n, "levels": stats["n_levels"], "tail_level": stats["tail_level"],
+                       "l2": "inputs (%.0f MB of keys per step) are larger than the 126 MB L2" % (8 * n / 1e6),
+                       "multi_gpu": "independent replicas per GPU" if world > 1 else "single GPU"},
+            "lookup": {"value": lookup_val, "unit": UNIT, "ms_per_pass": q_ms, "permutation_ok": permutation_ok},
+            "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,
+            "gpu_launches": launches + args.steps, "wall_ms_per_step": wall / args.steps * 1e3,
+            "clocks": clocks.summary(),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

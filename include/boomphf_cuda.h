@@ -1,0 +1,156 @@
+/*
+ * boomphf_cuda.h -- C ABI of the B200-native (sm_100a) MPHF build / batched lookup path.
+ *
+ * This is the drop-in boundary for the hot path of 10XGenomics/rust-boomphf (crate boomphf
+ * 0.6.0).  The reference has no FFI of its own; the boundary is its Rust public API
+ * (citations are file:line into the reference tree):
+ *
+ *   Mphf::new(gamma, &[T])                       src/lib.rs:235   -> bphf_build_u64
+ *   Mphf::new_parallel(gamma, &[T], Option<u64>) src/lib.rs:363   -> bphf_build_u64
+ *   Mphf::hash / Mphf::try_hash                  src/lib.rs:324,340 -> bphf_hash_batch_u64
+ *   Mphf { bitvecs: Box<[(BitVector, Box<[u64]>)]> } (serde data model)
+ *                                                src/lib.rs:90-96, src/bitvector.rs:41-54
+ *                                                -> bphf_num_levels / bphf_level_dims /
+ *                                                   bphf_level_export / bphf_from_levels
+ *   BoomHashMap::create_map / get                src/hashmap.rs:27-40,49-66
+ *                                                -> bphf_map_permute_u64 / bphf_map_get_batch_u64
+ *
+ * A thin Rust shim binds exactly these symbols; all functions are plain C,
+ * take plain pointers and sizes, return 0 on success and a negative status on error, and
+ * never unwind across the boundary.  There is NO CPU fallback: every compute entry point
+ * fails with BPHF_ERR_CUDA when no sm_100 device is usable.
+ *
+ * Results are bit-exact with the reference algorithm for T = u64 (same per-level bit
+ * vectors, same rank arrays, same hash value for every key) -- see DESIGN.md for the
+ * parity argument and its one unpinned assumption (the third-party wyhash 8-byte read).
+ */
+#ifndef BOOMPHF_CUDA_H
+#define BOOMPHF_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define BPHF_API __attribute__((visibility("default")))
+#else
+#define BPHF_API
+#endif
+
+typedef struct bphf_mphf bphf_mphf; /* opaque; owns device memory on one GPU */
+
+enum {
+    BPHF_OK = 0,
+    BPHF_ERR_ARG = -1,       /* null / inconsistent argument                                     */
+    BPHF_ERR_GAMMA = -2,     /* reference: assert!(gamma > 1.01)            src/lib.rs:236,364   */
+    BPHF_ERR_MAX_ITERS = -3, /* reference: panic!("counldn't find unique hashes") :267,400       */
+    BPHF_ERR_CUDA = -4,      /* CUDA runtime error or no usable device (no CPU fallback exists)  */
+    BPHF_ERR_NOMEM = -5,     /* device or host allocation failed                                 */
+    BPHF_ERR_INTERNAL = -6   /* invariant violated (would be a bug)                              */
+};
+
+/* bphf_hash_batch_u64 writes this where Mphf::try_hash returns None
+ * (Mphf::hash would hit unreachable!("must find a hash value"), src/lib.rs:334). */
+#define BPHF_NONE UINT64_MAX
+
+#define BPHF_MAX_ITERS 100u /* src/lib.rs:98 */
+#define BPHF_MAX_LEVELS 101u
+
+/* where a pointer argument lives */
+enum { BPHF_MEM_HOST = 0, BPHF_MEM_DEVICE = 1 };
+
+/* ---- library ------------------------------------------------------------------------- */
+BPHF_API int bphf_abi_version(void);
+BPHF_API const char *bphf_last_error(void); /* thread-local text of the last failure */
+BPHF_API int bphf_device_count(int *count);
+/* 1 when the 8-byte wyhash tail is read with swapped 32-bit halves (the primary candidate,
+ * see DESIGN.md "parity unpinned"); must equal the oracle's bo_wy_swap_8byte_tail(). */
+BPHF_API int bphf_wy_swap_8byte_tail(void);
+
+/* ---- build: Mphf::new / Mphf::new_parallel for T = u64 ---------------------------------
+ * keys            n distinct u64 keys (borrowed, never modified), host or device memory
+ * gamma           must be > 1.01
+ * has_seed/seed   Option<u64> starting_seed of new_parallel (None and Mphf::new: has_seed=0).
+ *                 Level l is built with seed index seed+l (src/lib.rs:370,385); lookups always
+ *                 use seed index l (src/lib.rs:327) exactly like the reference.
+ * device          CUDA device ordinal
+ * keys_mem        BPHF_MEM_HOST or BPHF_MEM_DEVICE (device pointer must be on `device`)
+ * stream          cudaStream_t to run on, or NULL for a library-owned stream.  The call is
+ *                 blocking either way (it returns after the structure is complete).
+ * The result does not depend on key order, thread or GPU schedule. */
+BPHF_API int bphf_build_u64(const uint64_t *keys, uint64_t n, double gamma, int has_seed, uint64_t seed,
+                            int device, int keys_mem, void *stream, bphf_mphf **out);
+
+/* ---- data model: (BitVector{bits, vector}, ranks) per level ---------------------------- */
+BPHF_API int bphf_num_levels(const bphf_mphf *m, uint32_t *n_levels);
+BPHF_API int bphf_level_dims(const bphf_mphf *m, uint32_t level, uint64_t *bits, uint64_t *n_words,
+                             uint64_t *n_ranks);
+/* copy one level out: n_words u64 words (BitVector.vector) and n_ranks u64 ranks */
+BPHF_API int bphf_level_export(const bphf_mphf *m, uint32_t level, uint64_t *words_out, uint64_t *ranks_out,
+                               int out_mem);
+/* all levels at once into caller buffers laid out level after level (no padding):
+ * words_out has sum(n_words) entries, ranks_out sum(n_ranks) */
+BPHF_API int bphf_export_all(const bphf_mphf *m, uint64_t *words_out, uint64_t *ranks_out, int out_mem);
+BPHF_API int bphf_total_dims(const bphf_mphf *m, uint64_t *total_words, uint64_t *total_ranks, uint64_t *n_keys);
+/* upload a deserialised Mphf (host arrays) to `device` */
+BPHF_API int bphf_from_levels(uint32_t n_levels, const uint64_t *bits, const uint64_t *const *words,
+                              const uint64_t *const *ranks, int device, bphf_mphf **out);
+BPHF_API void bphf_free(bphf_mphf *m);
+
+/* ---- lookup: Mphf::hash / try_hash over a batch ----------------------------------------
+ * out[i] = rank of keys[i], or BPHF_NONE when no level matched.  keys/out both live in
+ * `mem`.  Re-entrant on a shared handle. */
+BPHF_API int bphf_hash_batch_u64(const bphf_mphf *m, const uint64_t *keys, uint64_t n, uint64_t *out, int mem,
+                                 void *stream);
+
+/* ---- BoomHashMap helpers -------------------------------------------
+ * create_map (src/hashmap.rs:27-40): out-of-place scatter into MPHF order,
+ *   keys_out[hash(k)] = k, values_out[hash(k)] = v  (values may be NULL). */
+BPHF_API int bphf_map_permute_u64(const bphf_mphf *m, const uint64_t *keys, const uint64_t *values, uint64_t n,
+                                  uint64_t *keys_out, uint64_t *values_out, int mem, void *stream);
+/* get (src/hashmap.rs:49-66): pos = try_hash(q); found = pos != None && map_keys[pos] == q;
+ * values_out[i] = map_values[pos] (0 when not found; pos itself when map_values is NULL =
+ * get_key_id, src/hashmap.rs:88-105), found_out[i] = 0/1. */
+BPHF_API int bphf_map_get_batch_u64(const bphf_mphf *m, const uint64_t *map_keys, const uint64_t *map_values,
+                                    uint64_t n_map, const uint64_t *queries, uint64_t n_queries,
+                                    uint64_t *values_out, uint8_t *found_out, int mem, void *stream);
+
+/* ---- build statistics (measurement only) ------------------------------------------------ */
+typedef struct bphf_build_stats {
+    uint32_t n_levels;
+    uint32_t tail_level;                   /* first level finished by the single-CTA tail kernel  */
+    uint64_t keys_in[BPHF_MAX_LEVELS + 1]; /* keys entering each level                             */
+    uint64_t bits[BPHF_MAX_LEVELS + 1];
+    uint32_t kernel_launches;              /* kernels launched by the build                        */
+    uint32_t host_syncs;                   /* host round trips                                     */
+    float pass_ms[BPHF_MAX_LEVELS + 1];    /* per-level mark(+filter) kernel time, profile>=1: level 0 only; 2: all */
+    float fin_ms[BPHF_MAX_LEVELS + 1];     /* per-level finalize kernel time (profile 2)            */
+    float tail_ms, ranks_ms, total_ms;     /* profile 2 (total_ms always)                           */
+    float h2d_ms;                          /* host->device key copy when keys_mem == HOST           */
+} bphf_build_stats;
+BPHF_API int bphf_get_build_stats(const bphf_mphf *m, bphf_build_stats *out);
+/* 0: no events; 1: CUDA events around the level-0 pass only; 2: around every kernel */
+BPHF_API int bphf_set_profile(int level);
+
+/* ---- utilities used by tests and bench (device side) ------------------------------------ */
+/* distinct-by-construction synthetic keys: kind 0 = splitmix64 finaliser of
+ * seed + i*golden (bijection on u64); 1 = 62-bit 2-bit-packed 31-mers (bijection on 2^62);
+ * 2 = 2*i (benches/build.rs:11).  out is a device pointer, i runs over [start, start+n). */
+BPHF_API int bphf_keygen_u64(uint64_t *out_dev, uint64_t start, uint64_t n, uint64_t seed, int kind, int device,
+                             void *stream);
+/* MPHF property at full size: *n_bad = number of values that are >= n or repeat an earlier one */
+BPHF_API int bphf_check_permutation(const uint64_t *vals_dev, uint64_t n, int device, uint64_t *n_bad);
+/* order-independent checksum (sum and xor of splitmix64(v)) of a device u64 array */
+BPHF_API int bphf_checksum_u64(const uint64_t *vals_dev, uint64_t n, int device, uint64_t *sum_out,
+                               uint64_t *xor_out);
+/* pinned host memory for end-to-end runs */
+BPHF_API void *bphf_host_alloc(size_t bytes);
+BPHF_API void bphf_host_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BOOMPHF_CUDA_H */

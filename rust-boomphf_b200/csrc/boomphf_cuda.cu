@@ -1,0 +1,915 @@
+// boomphf_cuda.cu -- C ABI (include/boomphf_cuda.h) over the sm_100a kernels.
+// Host driver of the level cascade: Mphf::new / new_parallel  (/root/reference/src/lib.rs:235-275, 363-408).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "build_kernels.cuh"
+#include "query_kernels.cuh"
+
+using namespace bphf;
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+struct CudaFailure {
+    int code;
+    std::string msg;
+};
+
+static int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e__ = (call);                                                                        \
+        if (e__ != cudaSuccess) {                                                                        \
+            char buf__[512];                                                                             \
+            snprintf(buf__, sizeof buf__, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            throw CudaFailure{e__ == cudaErrorMemoryAllocation ? BPHF_ERR_NOMEM : BPHF_ERR_CUDA, buf__}; \
+        }                                                                                                \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        CK(cudaGetDevice(&prev));
+        if (prev != dev) CK(cudaSetDevice(dev));
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        if (cudaGetDevice(&cur) == cudaSuccess && cur != prev && prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+constexpr int MAX_DEVICES = 64;
+struct DeviceInfo {
+    bool init = false;
+    int sm_count = 0;
+    int cc_major = 0;
+};
+static DeviceInfo g_dev[MAX_DEVICES];
+static std::mutex g_dev_mutex;
+static int g_profile = 0;
+
+static const DeviceInfo& device_info(int dev) {
+    if (dev < 0 || dev >= MAX_DEVICES) throw CudaFailure{BPHF_ERR_ARG, "device ordinal out of range"};
+    std::lock_guard<std::mutex> lock(g_dev_mutex);
+    DeviceInfo& d = g_dev[dev];
+    if (!d.init) {
+        int count = 0;
+        CK(cudaGetDeviceCount(&count));
+        if (dev >= count) throw CudaFailure{BPHF_ERR_CUDA, "no such CUDA device (this library has no CPU fallback)"};
+        int prev = -1;
+        CK(cudaGetDevice(&prev));
+        CK(cudaSetDevice(dev));
+        CK(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev));
+        CK(cudaDeviceGetAttribute(&d.cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+        if (d.cc_major != 10)
+            throw CudaFailure{BPHF_ERR_CUDA, "device is not sm_100 (Blackwell B200); kernels are built for sm_100a only"};
+        // keep freed build scratch in the stream-ordered pool instead of returning it to the OS
+        cudaMemPool_t pool;
+        CK(cudaDeviceGetDefaultMemPool(&pool, dev));
+        uint64_t thresh = UINT64_MAX;
+        CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+        CK(cudaFuncSetAttribute(tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TailSmem)));
+        if (prev != dev) CK(cudaSetDevice(prev));
+        d.init = true;
+    }
+    return d;
+}
+
+// library-owned streams, one set per (thread, device)
+struct ThreadStreams {
+    cudaStream_t main[MAX_DEVICES] = {};
+    cudaStream_t copy[MAX_DEVICES] = {};
+};
+static thread_local ThreadStreams g_streams;
+static cudaStream_t own_stream(int dev, bool copy) {
+    cudaStream_t& s = copy ? g_streams.copy[dev] : g_streams.main[dev];
+    if (!s) CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    return s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the handle
+// ------------------------------------------------------------------------------------------------
+struct bphf_mphf {
+    int device = 0;
+    uint32_t n_levels = 0;
+    uint64_t n_keys = 0;       // popcount of all levels == number of keys
+    uint64_t words_used = 0;   // arena words (multiple of 8)
+    uint64_t* d_words = nullptr;
+    uint64_t* d_ranks = nullptr;
+    QLevel* d_lv = nullptr;
+    std::vector<LevelDesc> lv;
+    bphf_build_stats stats;
+    bphf_mphf() { memset(&stats, 0, sizeof stats); }
+};
+
+static void upload_level_table(bphf_mphf* m, cudaStream_t s) {
+    std::vector<QLevel> q(std::max<uint32_t>(m->n_levels, 1));
+    for (uint32_t l = 0; l < m->n_levels; l++) {
+        q[l].bits = m->lv[l].bits;
+        q[l].bit_off = m->lv[l].word_off * 64;
+        q[l].sp0 = m->lv[l].sp0_query;
+    }
+    CK(cudaMallocAsync((void**)&m->d_lv, q.size() * sizeof(QLevel), s));
+    CK(cudaMemcpyAsync(m->d_lv, q.data(), q.size() * sizeof(QLevel), cudaMemcpyHostToDevice, s));
+    CK(cudaStreamSynchronize(s));  // q is a stack vector
+}
+
+// ------------------------------------------------------------------------------------------------
+// plan: upper-biased simulation of the cascade (expected collision fraction 1 - exp(-k/bits))
+// ------------------------------------------------------------------------------------------------
+struct Plan {
+    uint64_t words_cap = 0;
+    uint64_t list_cap[2] = {0, 0};
+    std::vector<uint64_t> k_up;  // per non-tail level: upper estimate of keys entering
+    bool maybe_big = false;
+};
+
+static Plan make_plan(uint64_t n, double gamma) {
+    Plan p;
+    uint64_t k = n;
+    uint64_t words = 0;
+    for (uint32_t level = 0; level <= BPHF_MAX_LEVELS && k > 0; level++) {
+        const uint64_t bits = level_size(gamma, k);
+        if (level == 0 && (bits >> 32)) p.maybe_big = true;
+        if (k <= TAIL_MAX_KEYS && bits <= TAIL_MAX_BITS) break;
+        words += round_up8((bits + 63) / 64);
+        p.k_up.push_back(k);
+        const double frac = 1.0 - std::exp(-(double)k / (double)bits);
+        const double kn = (double)k * frac;
+        const uint64_t k_next = (uint64_t)(kn + 6.0 * std::sqrt(kn) + 64.0);
+        k = std::min(k, k_next);
+    }
+    p.words_cap = words + 1024;
+    p.list_cap[1] = p.k_up.size() > 1 ? p.k_up[1] : 0;  // level 1's list lives in buf[1]
+    p.list_cap[0] = p.k_up.size() > 2 ? p.k_up[2] : 0;  // level 2's list lives in buf[0]
+    return p;
+}
+
+// ------------------------------------------------------------------------------------------------
+// build
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct EventPair {
+    cudaEvent_t a = nullptr, b = nullptr;
+    int kind = 0;  // 0 pass, 1 finalize, 2 tail, 3 ranks, 4 h2d
+    uint32_t level = 0;
+};
+
+struct Builder {
+    int device;
+    const DeviceInfo& info;
+    cudaStream_t s;
+    int profile;
+    BuildState hst;
+    BuildState* d_state = nullptr;
+    uint64_t* d_keys_owned = nullptr;
+    const uint64_t* d_keys = nullptr;
+    uint64_t* d_words = nullptr;
+    uint64_t* d_coll = nullptr;
+    uint32_t* d_blockpop = nullptr;
+    uint64_t* d_buf[2] = {nullptr, nullptr};
+    uint64_t phys_words = 0;  // words_cap + TAIL_RESERVE_WORDS
+    uint64_t n = 0;
+    bool maybe_big = false;
+    uint32_t launches = 0, syncs = 0;
+    std::vector<EventPair> events;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+
+    Builder(int dev, const DeviceInfo& di, cudaStream_t st, int prof) : device(dev), info(di), s(st), profile(prof) {
+        memset(&hst, 0, sizeof hst);
+    }
+    ~Builder() {
+        // scratch goes back to the pool (stream ordered); the handle took ownership of what it keeps
+        if (d_state) cudaFreeAsync(d_state, s);
+        if (d_keys_owned) cudaFreeAsync(d_keys_owned, s);
+        if (d_words) cudaFreeAsync(d_words, s);
+        if (d_coll) cudaFreeAsync(d_coll, s);
+        if (d_blockpop) cudaFreeAsync(d_blockpop, s);
+        for (int i = 0; i < 2; i++)
+            if (d_buf[i]) cudaFreeAsync(d_buf[i], s);
+        for (auto& e : events) {
+            if (e.a) cudaEventDestroy(e.a);
+            if (e.b) cudaEventDestroy(e.b);
+        }
+        if (ev_begin) cudaEventDestroy(ev_begin);
+        if (ev_end) cudaEventDestroy(ev_end);
+    }
+
+    int max_grid() const { return info.sm_count * 8; }
+
+    size_t begin_event(int kind, uint32_t level) {
+        const bool want = profile >= 2 || (profile == 1 && kind == 0 && level <= 1);
+        if (!want) return (size_t)-1;
+        EventPair e;
+        e.kind = kind;
+        e.level = level;
+        CK(cudaEventCreate(&e.a));
+        CK(cudaEventCreate(&e.b));
+        CK(cudaEventRecord(e.a, s));
+        events.push_back(e);
+        return events.size() - 1;
+    }
+    void end_event(size_t id) {
+        if (id != (size_t)-1) CK(cudaEventRecord(events[id].b, s));
+    }
+
+    void alloc_arena(uint64_t words_cap) {
+        phys_words = words_cap + TAIL_RESERVE_WORDS;
+        CK(cudaMallocAsync((void**)&d_words, phys_words * 8, s));
+        CK(cudaMallocAsync((void**)&d_coll, phys_words * 8, s));
+        CK(cudaMallocAsync((void**)&d_blockpop, (phys_words / 8) * 4, s));
+        CK(cudaMemsetAsync(d_words, 0, phys_words * 8, s));
+        CK(cudaMemsetAsync(d_coll, 0, phys_words * 8, s));
+    }
+    // ST_NEED_WORDS: move to a larger arena, keeping everything built so far
+    void grow_arena(uint64_t need_words) {
+        const uint64_t new_cap = std::max<uint64_t>(need_words + need_words / 2, hst.words_cap * 2);
+        const uint64_t new_phys = new_cap + TAIL_RESERVE_WORDS;
+        uint64_t *nw = nullptr, *nc = nullptr;
+        uint32_t* nb = nullptr;
+        CK(cudaMallocAsync((void**)&nw, new_phys * 8, s));
+        CK(cudaMallocAsync((void**)&nc, new_phys * 8, s));
+        CK(cudaMallocAsync((void**)&nb, (new_phys / 8) * 4, s));
+        CK(cudaMemsetAsync(nw, 0, new_phys * 8, s));
+        CK(cudaMemsetAsync(nc, 0, new_phys * 8, s));
+        const uint64_t used = hst.words_used;
+        CK(cudaMemcpyAsync(nw, d_words, used * 8, cudaMemcpyDeviceToDevice, s));
+        CK(cudaMemcpyAsync(nc, d_coll, used * 8, cudaMemcpyDeviceToDevice, s));
+        CK(cudaMemcpyAsync(nb, d_blockpop, (used / 8) * 4, cudaMemcpyDeviceToDevice, s));
+        CK(cudaFreeAsync(d_words, s));
+        CK(cudaFreeAsync(d_coll, s));
+        CK(cudaFreeAsync(d_blockpop, s));
+        d_words = nw;
+        d_coll = nc;
+        d_blockpop = nb;
+        phys_words = new_phys;
+        hst.words_cap = new_cap;
+    }
+    void grow_list(int which, uint64_t need) {
+        const uint64_t cap = need + need / 8 + 1024;
+        if (d_buf[which]) CK(cudaFreeAsync(d_buf[which], s));
+        d_buf[which] = nullptr;
+        CK(cudaMallocAsync((void**)&d_buf[which], cap * 8, s));
+        hst.list_cap[which] = cap;
+    }
+
+    void launch_pass0(uint64_t begin, uint64_t end) {
+        if (end <= begin) return;
+        const uint64_t tiles = (end - begin + PASS_TILE - 1) / PASS_TILE;
+        const int grid = (int)std::min<uint64_t>(tiles, (uint64_t)max_grid());
+        uint32_t* a32 = reinterpret_cast<uint32_t*>(d_words);
+        uint32_t* c32 = reinterpret_cast<uint32_t*>(d_coll);
+        if (maybe_big)
+            pass0_kernel<true><<<grid, PASS_THREADS, 0, s>>>(d_state, d_keys, begin, end, a32, c32);
+        else
+            pass0_kernel<false><<<grid, PASS_THREADS, 0, s>>>(d_state, d_keys, begin, end, a32, c32);
+        CK(cudaGetLastError());
+        launches++;
+    }
+    void launch_pass(uint32_t level, uint64_t k_src_up) {
+        const uint64_t tiles = std::max<uint64_t>(1, (k_src_up + PASS_TILE - 1) / PASS_TILE);
+        const int grid = (int)std::min<uint64_t>(tiles, (uint64_t)max_grid());
+        uint32_t* a32 = reinterpret_cast<uint32_t*>(d_words);
+        uint32_t* c32 = reinterpret_cast<uint32_t*>(d_coll);
+        const size_t ev = begin_event(0, level);
+        if (maybe_big)
+            pass_kernel<true><<<grid, PASS_THREADS, 0, s>>>(d_state, level, d_keys, d_buf[0], d_buf[1], a32, c32);
+        else
+            pass_kernel<false><<<grid, PASS_THREADS, 0, s>>>(d_state, level, d_keys, d_buf[0], d_buf[1], a32, c32);
+        CK(cudaGetLastError());
+        end_event(ev);
+        launches++;
+    }
+    void launch_finalize(uint32_t level, uint64_t k_up) {
+        const uint64_t bits = level_size(hst.gamma, k_up);
+        const uint64_t pairs = round_up8((bits + 63) / 64) / 2;
+        const int grid = (int)std::min<uint64_t>(std::max<uint64_t>(1, (pairs + FIN_THREADS - 1) / FIN_THREADS),
+                                                 (uint64_t)max_grid());
+        const size_t ev = begin_event(1, level);
+        finalize_kernel<<<grid, FIN_THREADS, 0, s>>>(d_state, level, d_words, d_coll, d_blockpop);
+        CK(cudaGetLastError());
+        end_event(ev);
+        launches++;
+    }
+    void launch_tail() {
+        const size_t ev = begin_event(2, 0);
+        tail_kernel<<<1, TAIL_THREADS, sizeof(TailSmem), s>>>(d_state, d_keys, d_buf[0], d_buf[1],
+                                                             reinterpret_cast<uint32_t*>(d_words),
+                                                             reinterpret_cast<const uint32_t*>(d_coll), d_blockpop);
+        CK(cudaGetLastError());
+        end_event(ev);
+        launches++;
+    }
+    void upload_state() { CK(cudaMemcpyAsync(d_state, &hst, sizeof hst, cudaMemcpyHostToDevice, s)); }
+    void download_state() {
+        CK(cudaMemcpyAsync(&hst, d_state, sizeof hst, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        syncs++;
+    }
+};
+
+}  // namespace
+
+static int build_impl(const uint64_t* keys, uint64_t n, double gamma, int has_seed, uint64_t seed, int device,
+                      int keys_mem, void* stream, bphf_mphf** out) {
+    if (!out) return fail(BPHF_ERR_ARG, "out is null");
+    *out = nullptr;
+    if (n && !keys) return fail(BPHF_ERR_ARG, "keys is null");
+    if (keys_mem != BPHF_MEM_HOST && keys_mem != BPHF_MEM_DEVICE) return fail(BPHF_ERR_ARG, "bad keys_mem");
+    // assert!(gamma > 1.01)  src/lib.rs:236,364  (NaN fails the assertion too)
+    if (!(gamma > 1.01)) return fail(BPHF_ERR_GAMMA, "assertion failed: gamma > 1.01");
+
+    const DeviceInfo& info = device_info(device);
+    DeviceGuard guard(device);
+    cudaStream_t s = stream ? (cudaStream_t)stream : own_stream(device, false);
+    Builder b(device, info, s, g_profile);
+    b.n = n;
+
+    CK(cudaEventCreate(&b.ev_begin));
+    CK(cudaEventCreate(&b.ev_end));
+    CK(cudaEventRecord(b.ev_begin, s));
+
+    const Plan plan = make_plan(n, gamma);
+    b.maybe_big = plan.maybe_big;
+
+    CK(cudaMallocAsync((void**)&b.d_state, sizeof(BuildState), s));
+    b.alloc_arena(plan.words_cap);
+    for (int i = 0; i < 2; i++) {
+        if (plan.list_cap[i]) CK(cudaMallocAsync((void**)&b.d_buf[i], plan.list_cap[i] * 8, s));
+    }
+
+    BuildState& st = b.hst;
+    st.status = ST_RUNNING;
+    st.tail_level = NO_TAIL;
+    st.words_cap = plan.words_cap;
+    st.list_cap[0] = plan.list_cap[0];
+    st.list_cap[1] = plan.list_cap[1];
+    st.seed0 = has_seed ? seed : 0;  // starting_seed.unwrap_or(0)
+    st.gamma = gamma;
+    if (!try_make_level(&st, 0, n)) return fail(BPHF_ERR_INTERNAL, "level 0 does not fit the planned arena");
+    b.upload_state();
+
+    // ---- level 0: keys (H2D in chunks when they live on the host, marking each chunk as it lands)
+    float h2d_ms = 0.f;
+    if (keys_mem == BPHF_MEM_HOST && n) {
+        CK(cudaMallocAsync((void**)&b.d_keys_owned, n * 8, s));
+        b.d_keys = b.d_keys_owned;
+        cudaStream_t cs = own_stream(device, true);
+        const uint64_t chunk = 16ull << 20;  // 16 Mi keys = 128 MiB per copy
+        const uint64_t n_chunks = (n + chunk - 1) / chunk;
+        std::vector<cudaEvent_t> evs(n_chunks);
+        cudaEvent_t ready;
+        CK(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+        CK(cudaEventRecord(ready, s));  // allocation + state upload precede the copies
+        CK(cudaStreamWaitEvent(cs, ready, 0));
+        const size_t pe = b.begin_event(0, 0);
+        for (uint64_t c = 0; c < n_chunks; c++) {
+            const uint64_t lo = c * chunk, hi = std::min(n, lo + chunk);
+            CK(cudaMemcpyAsync(b.d_keys_owned + lo, keys + lo, (hi - lo) * 8, cudaMemcpyHostToDevice, cs));
+            CK(cudaEventCreateWithFlags(&evs[c], cudaEventDisableTiming));
+            CK(cudaEventRecord(evs[c], cs));
+            CK(cudaStreamWaitEvent(s, evs[c], 0));
+            b.launch_pass0(lo, hi);
+        }
+        b.end_event(pe);
+        for (auto e : evs) cudaEventDestroy(e);
+        cudaEventDestroy(ready);
+    } else {
+        b.d_keys = keys;
+        const size_t pe = b.begin_event(0, 0);
+        b.launch_pass0(0, n);
+        b.end_event(pe);
+    }
+    b.launch_finalize(0, n);
+
+    // ---- levels 1.. : everything the plan expects, then the tail, without a host round trip
+    uint32_t next_level = 1;
+    for (; next_level < plan.k_up.size(); next_level++) {
+        b.launch_pass(next_level, plan.k_up[next_level - 1]);
+        b.launch_finalize(next_level, plan.k_up[next_level]);
+    }
+    // one more pass+finalize pair in case the upper-biased plan was one level short, then the tail
+    for (;;) {
+        b.launch_tail();
+        b.download_state();
+        if (st.status == ST_DONE) break;
+        if (st.status == ST_ERR_MAX_ITERS) {
+            char msg[128];
+            snprintf(msg, sizeof msg, "counldn't find unique hashes (ran out of key space, %llu keys left)",
+                     (unsigned long long)st.err_info);
+            return fail(BPHF_ERR_MAX_ITERS, msg);
+        }
+        if (st.status == ST_ERR_INTERNAL) {
+            char msg[128];
+            snprintf(msg, sizeof msg, "internal consistency check failed (info %llx)", (unsigned long long)st.err_info);
+            return fail(BPHF_ERR_INTERNAL, msg);
+        }
+        const uint32_t level = st.n_levels;  // the level that could not be set up / has not run yet
+        if (level == 0 || level > BPHF_MAX_LEVELS) return fail(BPHF_ERR_INTERNAL, "bad resume level");
+        if (st.status == ST_NEED_WORDS || st.status == ST_NEED_LIST) {
+            const uint64_t k = st.lv[level].k_in;
+            // words_used still points at the end of the previous level: grow what is missing and redo
+            // the level set-up on the host until it fits, then hand the state back to the device
+            for (;;) {
+                if (st.status == ST_NEED_WORDS) b.grow_arena(st.need);
+                else b.grow_list(level & 1, st.need);
+                st.status = ST_RUNNING;
+                if (try_make_level(&st, level, k)) break;
+            }
+            b.upload_state();
+        } else if (st.status != ST_RUNNING) {
+            return fail(BPHF_ERR_INTERNAL, "unknown build status");
+        }
+        // enqueue a few more levels from where the device stopped (k only shrinks from here)
+        uint64_t k_up = st.lv[level].k_in;
+        const uint64_t k_prev = st.lv[level - 1].k_in;
+        b.launch_pass(level, k_prev);
+        b.launch_finalize(level, k_up);
+        for (uint32_t l = level + 1; l < level + 4 && l <= BPHF_MAX_LEVELS; l++) {
+            b.launch_pass(l, k_up);
+            b.launch_finalize(l, k_up);
+        }
+    }
+
+    // ---- compute_ranks: exclusive scan of block popcounts over the whole arena
+    std::unique_ptr<bphf_mphf> m(new (std::nothrow) bphf_mphf());
+    if (!m) return fail(BPHF_ERR_NOMEM, "host allocation failed");
+    m->device = device;
+    m->n_levels = st.n_levels;
+    m->words_used = st.words_used;
+    m->lv.assign(st.lv, st.lv + st.n_levels);
+    const uint64_t n_blocks = st.words_used / 8;
+    CK(cudaMallocAsync((void**)&m->d_ranks, std::max<uint64_t>(n_blocks, 1) * 8, s));
+    {
+        const uint64_t n_chunks = (n_blocks + SCAN_CHUNK - 1) / SCAN_CHUNK;
+        uint64_t* d_sums = nullptr;
+        CK(cudaMallocAsync((void**)&d_sums, std::max<uint64_t>(n_chunks, 1) * 8, s));
+        const size_t ev = b.begin_event(3, 0);
+        if (n_chunks) {
+            scan_sums_kernel<<<(unsigned)n_chunks, SCAN_THREADS, 0, s>>>(b.d_blockpop, n_blocks, d_sums);
+            scan_top_kernel<<<1, 1024, 0, s>>>(d_sums, n_chunks);
+            scan_apply_kernel<<<(unsigned)n_chunks, SCAN_THREADS, 0, s>>>(b.d_blockpop, n_blocks, d_sums, m->d_ranks);
+            CK(cudaGetLastError());
+            b.launches += 3;
+        }
+        b.end_event(ev);
+        CK(cudaFreeAsync(d_sums, s));
+    }
+    m->d_words = b.d_words;  // the handle keeps the arena (padded, <= planned capacity)
+    b.d_words = nullptr;
+    CK(cudaEventRecord(b.ev_end, s));
+    upload_level_table(m.get(), s);  // synchronises the stream
+    b.syncs++;
+
+    // ---- statistics
+    bphf_build_stats& bs = m->stats;
+    bs.n_levels = st.n_levels;
+    bs.tail_level = st.tail_level;
+    uint64_t total_keys = 0;
+    for (uint32_t l = 0; l < st.n_levels; l++) {
+        bs.keys_in[l] = st.lv[l].k_in;
+        bs.bits[l] = st.lv[l].bits;
+    }
+    total_keys = n;
+    m->n_keys = total_keys;
+    bs.kernel_launches = b.launches;
+    bs.host_syncs = b.syncs;
+    CK(cudaEventElapsedTime(&bs.total_ms, b.ev_begin, b.ev_end));
+    for (auto& e : b.events) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, e.a, e.b));
+        if (e.kind == 0 && e.level <= BPHF_MAX_LEVELS) bs.pass_ms[e.level] += ms;
+        else if (e.kind == 1 && e.level <= BPHF_MAX_LEVELS) bs.fin_ms[e.level] += ms;
+        else if (e.kind == 2) bs.tail_ms += ms;
+        else if (e.kind == 3) bs.ranks_ms += ms;
+    }
+    bs.h2d_ms = h2d_ms;
+    *out = m.release();
+    return BPHF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// exported functions
+// ------------------------------------------------------------------------------------------------
+#define API_BEGIN try {
+#define API_END                                      \
+    }                                                \
+    catch (const CudaFailure& f) {                   \
+        return fail(f.code, f.msg);                  \
+    }                                                \
+    catch (const std::bad_alloc&) {                  \
+        return fail(BPHF_ERR_NOMEM, "host allocation failed"); \
+    }                                                \
+    catch (...) {                                    \
+        return fail(BPHF_ERR_INTERNAL, "unexpected exception"); \
+    }
+
+// stage host arrays on the device for the map helpers (simple, unpipelined)
+struct Staged {
+    cudaStream_t s;
+    std::vector<void*> ptrs;
+    explicit Staged(cudaStream_t st) : s(st) {}
+    ~Staged() {
+        for (void* p : ptrs) cudaFreeAsync(p, s);
+    }
+    template <typename T>
+    T* in(const T* host, uint64_t count) {
+        if (!host || !count) return nullptr;
+        T* d = nullptr;
+        CK(cudaMallocAsync((void**)&d, count * sizeof(T), s));
+        ptrs.push_back(d);
+        CK(cudaMemcpyAsync(d, host, count * sizeof(T), cudaMemcpyHostToDevice, s));
+        return d;
+    }
+    template <typename T>
+    T* scratch(uint64_t count) {
+        T* d = nullptr;
+        CK(cudaMallocAsync((void**)&d, std::max<uint64_t>(count, 1) * sizeof(T), s));
+        ptrs.push_back(d);
+        return d;
+    }
+};
+
+extern "C" {
+
+BPHF_API int bphf_abi_version(void) { return 1; }
+BPHF_API const char* bphf_last_error(void) { return g_last_error.c_str(); }
+BPHF_API int bphf_wy_swap_8byte_tail(void) { return BPHF_WY_SWAP_8BYTE_TAIL; }
+
+BPHF_API int bphf_device_count(int* count) {
+    API_BEGIN
+    if (!count) return fail(BPHF_ERR_ARG, "count is null");
+    *count = 0;
+    CK(cudaGetDeviceCount(count));
+    return BPHF_OK;
+    API_END
+}
+
+BPHF_API int bphf_set_profile(int level) {
+    g_profile = level < 0 ? 0 : (level > 2 ? 2 : level);
+    return BPHF_OK;
+}
+
+BPHF_API int bphf_build_u64(const uint64_t* keys, uint64_t n, double gamma, int has_seed, uint64_t seed, int device,
+                            int keys_mem, void* stream, bphf_mphf** out) {
+    API_BEGIN
+    return build_impl(keys, n, gamma, has_seed, seed, device, keys_mem, stream, out);
+    API_END
+}
+
+BPHF_API int bphf_num_levels(const bphf_mphf* m, uint32_t* n_levels) {
+    if (!m || !n_levels) return fail(BPHF_ERR_ARG, "null argument");
+    *n_levels = m->n_levels;
+    return BPHF_OK;
+}
+
+BPHF_API int bphf_level_dims(const bphf_mphf* m, uint32_t level, uint64_t* bits, uint64_t* n_words, uint64_t* n_ranks) {
+    if (!m) return fail(BPHF_ERR_ARG, "null handle");
+    if (level >= m->n_levels) return fail(BPHF_ERR_ARG, "that level doesn't exist");
+    if (bits) *bits = m->lv[level].bits;
+    if (n_words) *n_words = m->lv[level].n_words;
+    if (n_ranks) *n_ranks = (m->lv[level].n_words + 7) / 8;
+    return BPHF_OK;
+}
+
+BPHF_API int bphf_total_dims(const bphf_mphf* m, uint64_t* total_words, uint64_t* total_ranks, uint64_t* n_keys) {
+    if (!m) return fail(BPHF_ERR_ARG, "null handle");
+    uint64_t w = 0, r = 0;
+    for (uint32_t l = 0; l < m->n_levels; l++) {
+        w += m->lv[l].n_words;
+        r += (m->lv[l].n_words + 7) / 8;
+    }
+    if (total_words) *total_words = w;
+    if (total_ranks) *total_ranks = r;
+    if (n_keys) *n_keys = m->n_keys;
+    return BPHF_OK;
+}
+
+BPHF_API int bphf_level_export(const bphf_mphf* m, uint32_t level, uint64_t* words_out, uint64_t* ranks_out, int out_mem) {
+    API_BEGIN
+    if (!m) return fail(BPHF_ERR_ARG, "null handle");
+    if (level >= m->n_levels) return fail(BPHF_ERR_ARG, "that level doesn't exist");
+    DeviceGuard guard(m->device);
+    cudaStream_t s = own_stream(m->device, false);
+    const LevelDesc& d = m->lv[level];
+    const cudaMemcpyKind kind = out_mem == BPHF_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    if (words_out && d.n_words) CK(cudaMemcpyAsync(words_out, m->d_words + d.word_off, d.n_words * 8, kind, s));
+    if (ranks_out && d.n_words)
+        CK(cudaMemcpyAsync(ranks_out, m->d_ranks + d.word_off / 8, ((d.n_words + 7) / 8) * 8, kind, s));
+    CK(cudaStreamSynchronize(s));
+    return BPHF_OK;
+    API_END
+}
+
+BPHF_API int bphf_export_all(const bphf_mphf* m, uint64_t* words_out, uint64_t* ranks_out, int out_mem) {
+    API_BEGIN
+    if (!m) return fail(BPHF_ERR_ARG, "null handle");
+    DeviceGuard guard(m->device);
+    cudaStream_t s = own_stream(m->device, false);
+    const cudaMemcpyKind kind = out_mem == BPHF_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    uint64_t wo = 0, ro = 0;
+    for (uint32_t l = 0; l < m->n_levels; l++) {
+        const LevelDesc& d = m->lv[l];
+        const uint64_t nr = (d.n_words + 7) / 8;
+        if (words_out && d.n_words) CK(cudaMemcpyAsync(words_out + wo, m->d_words + d.word_off, d.n_words * 8, kind, s));
+        if (ranks_out && nr) CK(cudaMemcpyAsync(ranks_out + ro, m->d_ranks + d.word_off / 8, nr * 8, kind, s));
+        wo += d.n_words;
+        ro += nr;
+    }
+    CK(cudaStreamSynchronize(s));
+    return BPHF_OK;
+    API_END
+}
+
+BPHF_API int bphf_from_levels(uint32_t n_levels, const uint64_t* bits, const uint64_t* const* words,
+                              const uint64_t* const* ranks, int device, bphf_mphf** out) {
+    API_BEGIN
+    if (!out) return fail(BPHF_ERR_ARG, "out is null");
+    *out = nullptr;
+    if (n_levels > BPHF_MAX_LEVELS || (n_levels && (!bits || !words || !ranks))) return fail(BPHF_ERR_ARG, "bad level arrays");
+    device_info(device);
+    DeviceGuard guard(device);
+    cudaStream_t s = own_stream(device, false);
+    std::unique_ptr<bphf_mphf> m(new bphf_mphf());
+    m->device = device;
+    m->n_levels = n_levels;
+    m->lv.resize(n_levels);
+    uint64_t off = 0;
+    for (uint32_t l = 0; l < n_levels; l++) {
+        LevelDesc& d = m->lv[l];
+        d.bits = bits[l];
+        d.n_words = (bits[l] + 63) / 64;
+        d.word_off = off;
+        d.k_in = 0;
+        d.sp0 = d.sp0_query = seed_xor_p0(l);
+        off += round_up8(d.n_words);
+        if (d.n_words && (!words[l] || !ranks[l])) return fail(BPHF_ERR_ARG, "null level buffer");
+    }
+    m->words_used = off;
+    CK(cudaMallocAsync((void**)&m->d_words, std::max<uint64_t>(off, 8) * 8, s));
+    CK(cudaMallocAsync((void**)&m->d_ranks, std::max<uint64_t>(off / 8, 1) * 8, s));
+    CK(cudaMemsetAsync(m->d_words, 0, std::max<uint64_t>(off, 8) * 8, s));
+    uint64_t n_keys = 0;
+    for (uint32_t l = 0; l < n_levels; l++) {
+        const LevelDesc& d = m->lv[l];
+        if (!d.n_words) continue;
+        CK(cudaMemcpyAsync(m->d_words + d.word_off, words[l], d.n_words * 8, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(m->d_ranks + d.word_off / 8, ranks[l], ((d.n_words + 7) / 8) * 8, cudaMemcpyHostToDevice, s));
+        for (uint64_t i = 0; i < d.n_words; i++) n_keys += (uint64_t)__builtin_popcountll(words[l][i]);
+    }
+    m->n_keys = n_keys;
+    upload_level_table(m.get(), s);
+    m->stats.n_levels = n_levels;
+    *out = m.release();
+    return BPHF_OK;
+    API_END
+}
+
+BPHF_API void bphf_free(bphf_mphf* m) {
+    if (!m) return;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    if (cudaSetDevice(m->device) == cudaSuccess) {
+        cudaStream_t s = nullptr;
+        try {
+            s = own_stream(m->device, false);
+        } catch (...) {
+        }
+        if (m->d_words) cudaFreeAsync(m->d_words, s);
+        if (m->d_ranks) cudaFreeAsync(m->d_ranks, s);
+        if (m->d_lv) cudaFreeAsync(m->d_lv, s);
+    }
+    if (prev >= 0) cudaSetDevice(prev);
+    delete m;
+}
+
+BPHF_API int bphf_get_build_stats(const bphf_mphf* m, bphf_build_stats* out) {
+    if (!m || !out) return fail(BPHF_ERR_ARG, "null argument");
+    *out = m->stats;
+    return BPHF_OK;
+}
+
+// ---- lookups ---------------------------------------------------------------------------------
+static int query_grid(const DeviceInfo& info, uint64_t n) {
+    const uint64_t blocks = (n + QUERY_THREADS - 1) / QUERY_THREADS;
+    return (int)std::max<uint64_t>(1, std::min<uint64_t>(blocks, (uint64_t)info.sm_count * 16));
+}
+
+BPHF_API int bphf_hash_batch_u64(const bphf_mphf* m, const uint64_t* keys, uint64_t n, uint64_t* out, int mem, void* stream) {
+    API_BEGIN
+    if (!m) return fail(BPHF_ERR_ARG, "null handle");
+    if (n == 0) return BPHF_OK;
+    if (!keys || !out) return fail(BPHF_ERR_ARG, "null buffer");
+    const DeviceInfo& info = device_info(m->device);
+    DeviceGuard guard(m->device);
+    cudaStream_t s = stream ? (cudaStream_t)stream : own_stream(m->device, false);
+    if (mem == BPHF_MEM_DEVICE) {
+        query_kernel<<<query_grid(info, n), QUERY_THREADS, 0, s>>>(m->d_lv, m->n_levels, m->d_words, m->d_ranks, keys, n, out);
+        CK(cudaGetLastError());
+        if (!stream) CK(cudaStreamSynchronize(s));
+        return BPHF_OK;
+    }
+    // host buffers: H2D -> kernel -> D2H pipelined in chunks over two streams
+    const uint64_t chunk = 8ull << 20;  // 8 Mi keys = 64 MiB each way
+    const int NBUF = 3;
+    const uint64_t cap = std::min(n, chunk);
+    uint64_t* d_in[NBUF];
+    uint64_t* d_out[NBUF];
+    cudaStream_t cs = own_stream(m->device, true);
+    cudaEvent_t in_ready[NBUF], out_done[NBUF], kernel_done[NBUF];
+    for (int i = 0; i < NBUF; i++) {
+        CK(cudaMallocAsync((void**)&d_in[i], cap * 8, s));
+        CK(cudaMallocAsync((void**)&d_out[i], cap * 8, s));
+        CK(cudaEventCreateWithFlags(&in_ready[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&out_done[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&kernel_done[i], cudaEventDisableTiming));
+    }
+    CK(cudaEventRecord(out_done[0], s));
+    CK(cudaStreamWaitEvent(cs, out_done[0], 0));  // buffers exist before the copy stream touches them
+    uint64_t c = 0;
+    for (uint64_t lo = 0; lo < n; lo += chunk, c++) {
+        const int bi = (int)(c % NBUF);
+        const uint64_t cnt = std::min(chunk, n - lo);
+        if (c >= (uint64_t)NBUF) CK(cudaStreamWaitEvent(cs, out_done[bi], 0));  // buffer free again
+        CK(cudaMemcpyAsync(d_in[bi], keys + lo, cnt * 8, cudaMemcpyHostToDevice, cs));
+        CK(cudaEventRecord(in_ready[bi], cs));
+        CK(cudaStreamWaitEvent(s, in_ready[bi], 0));
+        query_kernel<<<query_grid(info, cnt), QUERY_THREADS, 0, s>>>(m->d_lv, m->n_levels, m->d_words, m->d_ranks, d_in[bi], cnt, d_out[bi]);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(out + lo, d_out[bi], cnt * 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaEventRecord(out_done[bi], s));
+    }
+    CK(cudaStreamSynchronize(s));
+    CK(cudaStreamSynchronize(cs));
+    for (int i = 0; i < NBUF; i++) {
+        CK(cudaFreeAsync(d_in[i], s));
+        CK(cudaFreeAsync(d_out[i], s));
+        cudaEventDestroy(in_ready[i]);
+        cudaEventDestroy(out_done[i]);
+        cudaEventDestroy(kernel_done[i]);
+    }
+    return BPHF_OK;
+    API_END
+}
+
+BPHF_API int bphf_map_permute_u64(const bphf_mphf* m, const uint64_t* keys, const uint64_t* values, uint64_t n,
+                                  uint64_t* keys_out, uint64_t* values_out, int mem, void* stream) {
+    API_BEGIN
+    if (!m) return fail(BPHF_ERR_ARG, "null handle");
+    if (n == 0) return BPHF_OK;
+    if (!keys || !keys_out || (values && !values_out)) return fail(BPHF_ERR_ARG, "null buffer");
+    const DeviceInfo& info = device_info(m->device);
+    DeviceGuard guard(m->device);
+    cudaStream_t s = stream ? (cudaStream_t)stream : own_stream(m->device, false);
+    Staged st(s);
+    const uint64_t *dk = keys, *dv = values;
+    uint64_t *dko = keys_out, *dvo = values_out;
+    if (mem == BPHF_MEM_HOST) {
+        dk = st.in(keys, n);
+        dv = st.in(values, n);
+        dko = st.scratch<uint64_t>(n);
+        dvo = values ? st.scratch<uint64_t>(n) : nullptr;
+    }
+    unsigned long long* d_bad = st.scratch<unsigned long long>(1);
+    CK(cudaMemsetAsync(d_bad, 0, 8, s));
+    map_permute_kernel<<<query_grid(info, n), QUERY_THREADS, 0, s>>>(m->d_lv, m->n_levels, m->d_words, m->d_ranks, dk, dv, n, dko, dvo, d_bad);
+    CK(cudaGetLastError());
+    unsigned long long bad = 0;
+    CK(cudaMemcpyAsync(&bad, d_bad, 8, cudaMemcpyDeviceToHost, s));
+    if (mem == BPHF_MEM_HOST) {
+        CK(cudaMemcpyAsync(keys_out, dko, n * 8, cudaMemcpyDeviceToHost, s));
+        if (values) CK(cudaMemcpyAsync(values_out, dvo, n * 8, cudaMemcpyDeviceToHost, s));
+    }
+    CK(cudaStreamSynchronize(s));
+    if (bad) return fail(BPHF_ERR_ARG, "a key was not in the construction set (hash out of range)");
+    return BPHF_OK;
+    API_END
+}
+
+BPHF_API int bphf_map_get_batch_u64(const bphf_mphf* m, const uint64_t* map_keys, const uint64_t* map_values,
+                                    uint64_t n_map, const uint64_t* queries, uint64_t nq, uint64_t* values_out,
+                                    uint8_t* found_out, int mem, void* stream) {
+    API_BEGIN
+    if (!m) return fail(BPHF_ERR_ARG, "null handle");
+    if (nq == 0) return BPHF_OK;
+    if (!queries || !values_out || !found_out || (n_map && !map_keys)) return fail(BPHF_ERR_ARG, "null buffer");
+    const DeviceInfo& info = device_info(m->device);
+    DeviceGuard guard(m->device);
+    cudaStream_t s = stream ? (cudaStream_t)stream : own_stream(m->device, false);
+    Staged st(s);
+    const uint64_t *dmk = map_keys, *dmv = map_values, *dq = queries;
+    uint64_t* dvo = values_out;
+    uint8_t* dfo = found_out;
+    if (mem == BPHF_MEM_HOST) {
+        dmk = st.in(map_keys, n_map);
+        dmv = st.in(map_values, n_map);
+        dq = st.in(queries, nq);
+        dvo = st.scratch<uint64_t>(nq);
+        dfo = st.scratch<uint8_t>(nq);
+    }
+    map_get_kernel<<<query_grid(info, nq), QUERY_THREADS, 0, s>>>(m->d_lv, m->n_levels, m->d_words, m->d_ranks, dmk, dmv, n_map, dq, nq, dvo, dfo);
+    CK(cudaGetLastError());
+    if (mem == BPHF_MEM_HOST) {
+        CK(cudaMemcpyAsync(values_out, dvo, nq * 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(found_out, dfo, nq, cudaMemcpyDeviceToHost, s));
+    }
+    if (mem == BPHF_MEM_HOST || !stream) CK(cudaStreamSynchronize(s));
+    return BPHF_OK;
+    API_END
+}
+
+// ---- utilities --------------------------------------------------------------------------------
+BPHF_API int bphf_keygen_u64(uint64_t* out_dev, uint64_t start, uint64_t n, uint64_t seed, int kind, int device, void* stream) {
+    API_BEGIN
+    if (n == 0) return BPHF_OK;
+    if (!out_dev) return fail(BPHF_ERR_ARG, "null buffer");
+    const DeviceInfo& info = device_info(device);
+    DeviceGuard guard(device);
+    cudaStream_t s = stream ? (cudaStream_t)stream : own_stream(device, false);
+    const int grid = (int)std::min<uint64_t>((n + 255) / 256, (uint64_t)info.sm_count * 16);
+    keygen_kernel<<<grid, 256, 0, s>>>(out_dev, start, n, seed, kind);
+    CK(cudaGetLastError());
+    if (!stream) CK(cudaStreamSynchronize(s));
+    return BPHF_OK;
+    API_END
+}
+
+BPHF_API int bphf_check_permutation(const uint64_t* vals_dev, uint64_t n, int device, uint64_t* n_bad) {
+    API_BEGIN
+    if (!n_bad) return fail(BPHF_ERR_ARG, "null argument");
+    *n_bad = 0;
+    if (n == 0) return BPHF_OK;
+    if (!vals_dev) return fail(BPHF_ERR_ARG, "null buffer");
+    const DeviceInfo& info = device_info(device);
+    DeviceGuard guard(device);
+    cudaStream_t s = own_stream(device, false);
+    Staged st(s);
+    const uint64_t n32 = (n + 31) / 32;
+    uint32_t* bitmap = st.scratch<uint32_t>(n32);
+    unsigned long long* d_bad = st.scratch<unsigned long long>(1);
+    CK(cudaMemsetAsync(bitmap, 0, n32 * 4, s));
+    CK(cudaMemsetAsync(d_bad, 0, 8, s));
+    const int grid = (int)std::min<uint64_t>((n + 255) / 256, (uint64_t)info.sm_count * 16);
+    check_perm_kernel<<<grid, 256, 0, s>>>(vals_dev, n, bitmap, d_bad);
+    CK(cudaGetLastError());
+    unsigned long long bad = 0;
+    CK(cudaMemcpyAsync(&bad, d_bad, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    *n_bad = bad;
+    return BPHF_OK;
+    API_END
+}
+
+BPHF_API int bphf_checksum_u64(const uint64_t* vals_dev, uint64_t n, int device, uint64_t* sum_out, uint64_t* xor_out) {
+    API_BEGIN
+    if (!sum_out || !xor_out) return fail(BPHF_ERR_ARG, "null argument");
+    *sum_out = *xor_out = 0;
+    if (n == 0) return BPHF_OK;
+    const DeviceInfo& info = device_info(device);
+    DeviceGuard guard(device);
+    cudaStream_t s = own_stream(device, false);
+    Staged st(s);
+    unsigned long long* acc = st.scratch<unsigned long long>(2);
+    CK(cudaMemsetAsync(acc, 0, 16, s));
+    const int grid = (int)std::min<uint64_t>((n + 255) / 256, (uint64_t)info.sm_count * 16);
+    checksum_kernel<<<grid, 256, 0, s>>>(vals_dev, n, acc);
+    CK(cudaGetLastError());
+    unsigned long long h[2];
+    CK(cudaMemcpyAsync(h, acc, 16, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    *sum_out = h[0];
+    *xor_out = h[1];
+    return BPHF_OK;
+    API_END
+}
+
+BPHF_API void* bphf_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+        g_last_error = "cudaMallocHost failed";
+        return nullptr;
+    }
+    return p;
+}
+BPHF_API void bphf_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+}  // extern "C"

@@ -1,0 +1,480 @@
+// build_kernels.cuh -- sm_100a kernels of the MPHF level cascade.
+//
+// Reference functions replaced (file:line into /root/reference):
+//   Context::find_collisions  src/lib.rs:429-434   -> mark()           (pass_kernel, tail_kernel)
+//   Context::filter           src/lib.rs:443-452   -> collide test + stream compaction (pass_kernel)
+//                                                     and a &= ~collide (finalize_kernel)
+//   Mphf::new_parallel loop   src/lib.rs:363-408   -> device-resident BuildState, no host round trip
+//   Mphf::compute_ranks       src/lib.rs:277-297   -> finalize_kernel block popcounts + scan kernels
+//
+// Schedule (differs from the reference on purpose, result identical -- SURVEY.md 3.1):
+//   pass(l)     : stream the keys that entered level l-1, keep those whose level-(l-1) slot collided,
+//                 append them to level l's key list AND mark them into level l's (a, collide) arrays
+//                 in the same kernel.  pass(0) only marks.
+//   finalize(l) : a &= ~collide word-wise (the net effect of every a.remove(idx)), per-512-bit-block
+//                 popcounts, total unique count u_l; the last CTA derives k_{l+1} = k_l - u_l and the
+//                 next level's size/offset/seed on the device.
+//   tail        : once k <= TAIL_MAX_KEYS one CTA finishes every remaining level in shared memory.
+#pragma once
+#include "common.cuh"
+
+namespace bphf {
+
+constexpr int PASS_THREADS = 256;
+constexpr int PASS_KPT = 8;                          // keys per thread per tile
+constexpr int PASS_TILE = PASS_THREADS * PASS_KPT;   // 2048 keys, 16 KB staging
+constexpr int FIN_THREADS = 256;
+constexpr int TAIL_THREADS = 1024;
+constexpr uint32_t NO_TAIL = 0xffffffffu;
+
+// streaming 8-byte load that does not pollute L1 (keys are read once per pass)
+__device__ __forceinline__ uint64_t ld_stream_u64(const uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+
+// level bookkeeping shared by the finalize kernel (last CTA), the tail kernel and the host
+// (resume after growing a buffer).  Level `level` gets k keys; returns false (status set) when a
+// buffer must grow first.
+__host__ __device__ inline bool try_make_level(BuildState* st, uint32_t level, uint64_t k) {
+    make_level(st, level, k);
+    const LevelDesc& d = st->lv[level];
+    const bool tail_ok = (k <= TAIL_MAX_KEYS) && (d.bits <= TAIL_MAX_BITS);
+    if (tail_ok) {
+        if (st->tail_level == NO_TAIL) st->tail_level = level;
+        // arena space for tail levels comes out of the TAIL_RESERVE_WORDS slack; lists live in smem
+        st->words_used = d.word_off + round_up8(d.n_words);
+        return true;
+    }
+    const uint64_t need_words = d.word_off + round_up8(d.n_words);
+    if (need_words > st->words_cap) {
+        st->status = ST_NEED_WORDS;
+        st->need = need_words;
+        return false;
+    }
+    if (level >= 1 && k > st->list_cap[level & 1]) {
+        st->status = ST_NEED_LIST;
+        st->need = k;
+        return false;
+    }
+    st->words_used = need_words;
+    return true;
+}
+
+// called once level `level` is complete (a final, popcounts written) with k_next keys left over
+__host__ __device__ inline void finish_level(BuildState* st, uint32_t level, uint64_t k_next) {
+    st->n_levels = level + 1;
+    st->redo_count = 0;
+    st->uniq_count = 0;
+    st->fin_ticket = 0;
+    // reference: the `iter > MAX_ITERS` check sits inside `while !redo_keys.is_empty()` after
+    // `iter += 1`, i.e. it fires for level index >= 100 even when nothing is left to redo
+    if (level >= 1 && level + 1 > BPHF_MAX_ITERS) {
+        st->status = ST_ERR_MAX_ITERS;
+        st->err_info = k_next;
+        return;
+    }
+    if (k_next == 0) {
+        st->status = ST_DONE;
+        return;
+    }
+    try_make_level(st, level + 1, k_next);
+}
+
+// find_collisions (src/lib.rs:429-434) on the 32-bit view of the little-endian u64 words:
+// bit i of the level = bit (i & 31) of u32 word (i >> 5).  a: fetch_or returning the old word;
+// collide: fire-and-forget OR when the slot was already taken.  The reference's
+// `!collide.contains(idx)` pre-check only skips redundant work; the final (a, collide) is the same.
+__device__ __forceinline__ void mark_bit(uint32_t* __restrict__ a32, uint32_t* __restrict__ c32, uint64_t w,
+                                         uint32_t m) {
+    const uint32_t old = atomicOr(a32 + w, m);
+    if (old & m) atomicOr(c32 + w, m);
+}
+
+template <bool BIG>
+__device__ __forceinline__ uint64_t level_index(uint64_t sp0, uint64_t key, uint64_t bits) {
+    if (BIG) return hashmod_big(sp0, key, bits);
+    return hashmod_small(sp0, key, (uint32_t)bits);
+}
+
+// ---------------------------------------------------------------------------------------------
+// pass_kernel<FIRST = true>: level 0, mark only, over user_keys[key_begin, key_end)
+// ---------------------------------------------------------------------------------------------
+template <bool MAYBE_BIG>
+__global__ void __launch_bounds__(PASS_THREADS)
+    pass0_kernel(const BuildState* __restrict__ st, const uint64_t* __restrict__ keys, uint64_t key_begin,
+                 uint64_t key_end, uint32_t* __restrict__ a32, uint32_t* __restrict__ c32) {
+    if (st->status != ST_RUNNING || st->n_levels != 0 || st->tail_level == 0) return;
+    const uint64_t bits = st->lv[0].bits;
+    const uint64_t sp0 = st->lv[0].sp0;
+    const uint64_t off32 = st->lv[0].word_off * 2;
+    const bool big = MAYBE_BIG && (bits >> 32) != 0;
+    const uint64_t n = key_end - key_begin;
+    const uint64_t n_tiles = (n + PASS_TILE - 1) / PASS_TILE;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint64_t base = key_begin + tile * PASS_TILE + threadIdx.x;
+        uint64_t key[PASS_KPT];
+#pragma unroll
+        for (int j = 0; j < PASS_KPT; j++) {
+            const uint64_t i = base + (uint64_t)j * PASS_THREADS;
+            key[j] = (i < key_end) ? ld_stream_u64(keys + i) : 0;
+        }
+#pragma unroll
+        for (int j = 0; j < PASS_KPT; j++) {
+            const uint64_t i = base + (uint64_t)j * PASS_THREADS;
+            if (i < key_end) {
+                const uint64_t idx = big ? level_index<true>(sp0, key[j], bits) : level_index<false>(sp0, key[j], bits);
+                mark_bit(a32, c32, off32 + (idx >> 5), 1u << (idx & 31));
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pass_kernel: level >= 1.  filter(level-1) + compaction + mark(level) fused.
+// ---------------------------------------------------------------------------------------------
+template <bool MAYBE_BIG>
+__global__ void __launch_bounds__(PASS_THREADS)
+    pass_kernel(BuildState* __restrict__ st, uint32_t level, const uint64_t* __restrict__ user_keys,
+                uint64_t* __restrict__ buf0, uint64_t* __restrict__ buf1, uint32_t* __restrict__ a32,
+                uint32_t* __restrict__ c32) {
+    if (st->status != ST_RUNNING || st->n_levels != level || level >= st->tail_level) return;
+    __shared__ uint64_t stage[PASS_TILE];
+    __shared__ uint32_t warp_tot[PASS_THREADS / 32];
+    __shared__ uint64_t sh_base;
+
+    const LevelDesc* __restrict__ pv = &st->lv[level - 1];
+    const LevelDesc* __restrict__ cu = &st->lv[level];
+    const uint64_t p_bits = pv->bits, p_sp0 = pv->sp0, p_off32 = pv->word_off * 2, k_src = pv->k_in;
+    const uint64_t c_bits = cu->bits, c_sp0 = cu->sp0, c_off32 = cu->word_off * 2;
+    const bool p_big = MAYBE_BIG && (p_bits >> 32) != 0;
+    const bool c_big = MAYBE_BIG && (c_bits >> 32) != 0;
+    const uint64_t* __restrict__ src = (level == 1) ? user_keys : (((level - 1) & 1) ? buf1 : buf0);
+    uint64_t* __restrict__ dst = (level & 1) ? buf1 : buf0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    const uint64_t n_tiles = (k_src + PASS_TILE - 1) / PASS_TILE;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint64_t base = tile * PASS_TILE + threadIdx.x;
+        uint64_t key[PASS_KPT];
+        uint32_t cw[PASS_KPT], sh[PASS_KPT];
+#pragma unroll
+        for (int j = 0; j < PASS_KPT; j++) {
+            const uint64_t i = base + (uint64_t)j * PASS_THREADS;
+            key[j] = (i < k_src) ? ld_stream_u64(src + i) : 0;
+        }
+        // Context::filter (src/lib.rs:443-452): does this key's level-(l-1) slot collide?
+#pragma unroll
+        for (int j = 0; j < PASS_KPT; j++) {
+            const uint64_t idx = p_big ? level_index<true>(p_sp0, key[j], p_bits) : level_index<false>(p_sp0, key[j], p_bits);
+            cw[j] = __ldg(c32 + p_off32 + (idx >> 5));
+            sh[j] = (uint32_t)idx & 31;
+        }
+        uint32_t flags = 0;
+#pragma unroll
+        for (int j = 0; j < PASS_KPT; j++) {
+            const uint64_t i = base + (uint64_t)j * PASS_THREADS;
+            if (i < k_src && ((cw[j] >> sh[j]) & 1u)) flags |= 1u << j;
+        }
+        // block-wide exclusive scan of per-thread counts (warp shuffle scan + 8 warp totals)
+        const uint32_t cnt = __popc(flags);
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        uint32_t warp_off = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < PASS_THREADS / 32; w++) {
+            const uint32_t t = warp_tot[w];
+            if (w < warp) warp_off += t;
+            total += t;
+        }
+        uint32_t pos = warp_off + incl - cnt;
+#pragma unroll
+        for (int j = 0; j < PASS_KPT; j++)
+            if (flags & (1u << j)) stage[pos++] = key[j];
+        if (threadIdx.x == 0)
+            sh_base = (uint64_t)atomicAdd((unsigned long long*)&st->redo_count, (unsigned long long)total);
+        __syncthreads();
+        const uint64_t out = sh_base;
+        // rayon filter_map().collect() (src/lib.rs:374-377): append to level l's list (coalesced), and
+        // find_collisions of level l for the same key while it is still on chip
+        for (uint32_t i = threadIdx.x; i < total; i += PASS_THREADS) {
+            const uint64_t kk = stage[i];
+            dst[out + i] = kk;
+            const uint64_t idx = c_big ? level_index<true>(c_sp0, kk, c_bits) : level_index<false>(c_sp0, kk, c_bits);
+            mark_bit(a32, c32, c_off32 + (idx >> 5), 1u << (idx & 31));
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// finalize_kernel: a &= ~collide; block popcounts; unique count; last CTA sets up level+1
+// 4 consecutive lanes own one 8-word rank block (16 B per lane).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(FIN_THREADS)
+    finalize_kernel(BuildState* __restrict__ st, uint32_t level, uint64_t* __restrict__ words,
+                    const uint64_t* __restrict__ coll, uint32_t* __restrict__ blockpop) {
+    if (st->status != ST_RUNNING || st->n_levels != level || level >= st->tail_level) return;
+    __shared__ bool is_last;
+    const uint64_t word_off = st->lv[level].word_off;
+    const uint64_t n_pairs = round_up8(st->lv[level].n_words) / 2;  // multiple of 4
+    const int lane = threadIdx.x & 31;
+    ulonglong2* __restrict__ a2 = reinterpret_cast<ulonglong2*>(words + word_off);
+    const ulonglong2* __restrict__ c2 = reinterpret_cast<const ulonglong2*>(coll + word_off);
+    uint32_t* __restrict__ bp = blockpop + word_off / 8;
+
+    uint64_t uniq = 0;
+    const uint64_t stride = (uint64_t)gridDim.x * FIN_THREADS;
+    for (uint64_t p0 = (uint64_t)blockIdx.x * FIN_THREADS + (threadIdx.x & ~31u); p0 < n_pairs; p0 += stride) {
+        const uint64_t p = p0 + lane;
+        uint32_t pc = 0;
+        if (p < n_pairs) {
+            ulonglong2 a = a2[p];
+            const ulonglong2 c = c2[p];
+            a.x &= ~c.x;
+            a.y &= ~c.y;
+            a2[p] = a;
+            pc = __popcll(a.x) + __popcll(a.y);
+        }
+        uniq += pc;
+        pc += __shfl_xor_sync(0xffffffffu, pc, 1);
+        pc += __shfl_xor_sync(0xffffffffu, pc, 2);
+        if (p < n_pairs && (lane & 3) == 0) bp[p >> 2] = pc;
+    }
+    // block reduction of the unique count, one atomic per CTA
+    uint64_t u = uniq;
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) u += __shfl_xor_sync(0xffffffffu, u, d);
+    __shared__ uint64_t warp_u[FIN_THREADS / 32];
+    if (lane == 0) warp_u[threadIdx.x >> 5] = u;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint64_t t = 0;
+#pragma unroll
+        for (int w = 0; w < FIN_THREADS / 32; w++) t += warp_u[w];
+        if (t) atomicAdd((unsigned long long*)&st->uniq_count, (unsigned long long)t);
+        __threadfence();
+        const uint32_t ticket = atomicAdd(&st->fin_ticket, 1u);
+        is_last = (ticket == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last && threadIdx.x == 0) {
+        __threadfence();
+        const uint64_t uq = atomicAdd((unsigned long long*)&st->uniq_count, 0ULL);
+        const uint64_t k_in = st->lv[level].k_in;
+        if (uq > k_in || (level >= 1 && atomicAdd((unsigned long long*)&st->redo_count, 0ULL) != k_in)) {
+            st->status = ST_ERR_INTERNAL;
+            st->err_info = ((uint64_t)level << 48) | uq;
+        } else {
+            finish_level(st, level, k_in - uq);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// tail_kernel: one CTA, all remaining levels in shared memory
+// ---------------------------------------------------------------------------------------------
+struct TailSmem {
+    uint64_t keys[2][TAIL_MAX_KEYS];
+    uint32_t a[TAIL_MAX_WORDS * 2 + 16];
+    uint32_t c[TAIL_MAX_WORDS * 2 + 16];
+    uint32_t count;
+    uint32_t uniq;
+    uint32_t status;
+};
+
+__global__ void __launch_bounds__(TAIL_THREADS)
+    tail_kernel(BuildState* __restrict__ st, const uint64_t* __restrict__ user_keys, const uint64_t* __restrict__ buf0,
+                const uint64_t* __restrict__ buf1, uint32_t* __restrict__ words32, const uint32_t* __restrict__ c32,
+                uint32_t* __restrict__ blockpop) {
+    extern __shared__ __align__(16) unsigned char tail_smem_raw[];
+    TailSmem& s = *reinterpret_cast<TailSmem*>(tail_smem_raw);
+    if (st->status != ST_RUNNING || st->tail_level == NO_TAIL || st->n_levels != st->tail_level) return;
+    const uint32_t tid = threadIdx.x;
+    uint32_t level = st->tail_level;
+    uint32_t k = (uint32_t)st->lv[level].k_in;
+    if (tid == 0) s.count = 0;
+    __syncthreads();
+    // gather the keys entering `level`
+    if (level == 0) {
+        for (uint32_t i = tid; i < k; i += TAIL_THREADS) s.keys[0][i] = user_keys[i];
+        if (tid == 0) s.count = k;
+    } else {
+        const LevelDesc* pv = &st->lv[level - 1];
+        const uint64_t p_bits = pv->bits, p_sp0 = pv->sp0, p_off32 = pv->word_off * 2, k_src = pv->k_in;
+        const bool p_big = (p_bits >> 32) != 0;
+        const uint64_t* src = (level == 1) ? user_keys : (((level - 1) & 1) ? buf1 : buf0);
+        for (uint64_t i = tid; i < k_src; i += TAIL_THREADS) {
+            const uint64_t key = src[i];
+            const uint64_t idx = p_big ? hashmod_big(p_sp0, key, p_bits) : (uint64_t)hashmod_small(p_sp0, key, (uint32_t)p_bits);
+            if ((c32[p_off32 + (idx >> 5)] >> (idx & 31)) & 1u) {
+                const uint32_t pos = atomicAdd(&s.count, 1u);
+                if (pos < TAIL_MAX_KEYS) s.keys[0][pos] = key;
+            }
+        }
+    }
+    __syncthreads();
+    if (s.count != k) {
+        if (tid == 0) { st->status = ST_ERR_INTERNAL; st->err_info = ((uint64_t)level << 48) | s.count | (1ULL << 47); }
+        return;
+    }
+    int cur = 0;
+    for (;;) {
+        const uint32_t bits = (uint32_t)st->lv[level].bits;
+        const uint64_t sp0 = st->lv[level].sp0;
+        const uint64_t word_off = st->lv[level].word_off;
+        const uint32_t n32 = (uint32_t)round_up8(st->lv[level].n_words) * 2;
+        for (uint32_t w = tid; w < n32; w += TAIL_THREADS) { s.a[w] = 0; s.c[w] = 0; }
+        if (tid == 0) { s.count = 0; s.uniq = 0; }
+        __syncthreads();
+        const uint64_t* kin = s.keys[cur];
+        uint64_t* kout = s.keys[cur ^ 1];
+        for (uint32_t i = tid; i < k; i += TAIL_THREADS) {
+            const uint32_t idx = hashmod_small(sp0, kin[i], bits);
+            const uint32_t m = 1u << (idx & 31);
+            const uint32_t old = atomicOr(&s.a[idx >> 5], m);
+            if (old & m) atomicOr(&s.c[idx >> 5], m);
+        }
+        __syncthreads();
+        for (uint32_t w = tid; w < n32; w += TAIL_THREADS) {
+            const uint32_t a = s.a[w] & ~s.c[w];
+            s.a[w] = a;
+            words32[word_off * 2 + w] = a;
+        }
+        __syncthreads();
+        for (uint32_t b = tid; b < n32 / 16; b += TAIL_THREADS) {
+            uint32_t pc = 0;
+#pragma unroll
+            for (int j = 0; j < 16; j++) pc += __popc(s.a[b * 16 + j]);
+            blockpop[word_off / 8 + b] = pc;
+            if (pc) atomicAdd(&s.uniq, pc);
+        }
+        for (uint32_t i = tid; i < k; i += TAIL_THREADS) {
+            const uint64_t key = kin[i];
+            const uint32_t idx = hashmod_small(sp0, key, bits);
+            if ((s.c[idx >> 5] >> (idx & 31)) & 1u) kout[atomicAdd(&s.count, 1u)] = key;
+        }
+        __syncthreads();
+        const uint32_t k_next = s.count;
+        if (tid == 0) {
+            if (s.uniq + k_next != k) {
+                st->status = ST_ERR_INTERNAL;
+                st->err_info = ((uint64_t)level << 48) | k_next | (1ULL << 46);
+            } else {
+                finish_level(st, level, k_next);
+            }
+            s.status = st->status;
+        }
+        __syncthreads();
+        if (s.status != ST_RUNNING) return;
+        k = k_next;
+        level += 1;
+        cur ^= 1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// compute_ranks (src/lib.rs:277-297): exclusive prefix sum over the arena's block popcounts
+// ---------------------------------------------------------------------------------------------
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_PER_THREAD = 8;
+constexpr int SCAN_CHUNK = SCAN_THREADS * SCAN_PER_THREAD;
+
+__device__ __forceinline__ uint64_t block_reduce_u64(uint64_t v, uint64_t* sh) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    uint64_t t = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += sh[w];
+    __syncthreads();
+    return t;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+    scan_sums_kernel(const uint32_t* __restrict__ blockpop, uint64_t n, uint64_t* __restrict__ chunk_sums) {
+    __shared__ uint64_t sh[SCAN_THREADS / 32];
+    const uint64_t base = (uint64_t)blockIdx.x * SCAN_CHUNK;
+    uint64_t v = 0;
+#pragma unroll
+    for (int j = 0; j < SCAN_PER_THREAD; j++) {
+        const uint64_t i = base + (uint64_t)j * SCAN_THREADS + threadIdx.x;
+        if (i < n) v += blockpop[i];
+    }
+    const uint64_t t = block_reduce_u64(v, sh);
+    if (threadIdx.x == 0) chunk_sums[blockIdx.x] = t;
+}
+
+// single CTA: in-place exclusive scan of chunk sums
+__global__ void __launch_bounds__(1024) scan_top_kernel(uint64_t* __restrict__ chunk_sums, uint64_t n_chunks) {
+    __shared__ uint64_t sh[32];
+    __shared__ uint64_t carry_sh;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_sh = 0;
+    __syncthreads();
+    for (uint64_t base = 0; base < n_chunks; base += 1024) {
+        const uint64_t i = base + threadIdx.x;
+        const uint64_t v = (i < n_chunks) ? chunk_sums[i] : 0;
+        uint64_t incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint64_t t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        if (lane == 31) sh[warp] = incl;
+        __syncthreads();
+        uint64_t woff = 0, total = 0;
+        for (int w = 0; w < 32; w++) {
+            const uint64_t t = sh[w];
+            if (w < warp) woff += t;
+            total += t;
+        }
+        const uint64_t carry = carry_sh;
+        if (i < n_chunks) chunk_sums[i] = carry + woff + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 0) carry_sh = carry + total;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+    scan_apply_kernel(const uint32_t* __restrict__ blockpop, uint64_t n, const uint64_t* __restrict__ chunk_off,
+                      uint64_t* __restrict__ ranks) {
+    __shared__ uint32_t warp_tot[SCAN_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // thread t owns SCAN_PER_THREAD consecutive entries
+    const uint64_t base = (uint64_t)blockIdx.x * SCAN_CHUNK + (uint64_t)threadIdx.x * SCAN_PER_THREAD;
+    uint32_t v[SCAN_PER_THREAD];
+    uint32_t sum = 0;
+#pragma unroll
+    for (int j = 0; j < SCAN_PER_THREAD; j++) {
+        v[j] = (base + j < n) ? blockpop[base + j] : 0;
+        sum += v[j];
+    }
+    uint32_t incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    uint32_t woff = 0;
+    for (int w = 0; w < warp; w++) woff += warp_tot[w];
+    uint64_t run = chunk_off[blockIdx.x] + woff + incl - sum;
+#pragma unroll
+    for (int j = 0; j < SCAN_PER_THREAD; j++) {
+        if (base + j < n) ranks[base + j] = run;
+        run += v[j];
+    }
+}
+
+}  // namespace bphf

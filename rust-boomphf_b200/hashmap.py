@@ -1,0 +1,119 @@
+"""Host-side mirror of the reference's `hashmap` module for u64 keys and u64 values
+(/root/reference/src/hashmap.rs): BoomHashMap (:16-132) and NoKeyBoomHashMap (:434-523).
+
+`create_map`'s in-place cycle permutation (:27-40) becomes an out-of-place scatter on the GPU
+(keys_out[hash(k)] = k); the resulting arrays are identical because the permutation is unique.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _native as N
+from .mphf import Mphf, _check
+
+
+def _u64(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.uint64))
+
+
+class BoomHashMap:
+    """BoomHashMap<u64, u64>: keys and values stored densely in MPHF order."""
+
+    GAMMA = 1.7  # hard-coded by the reference (src/hashmap.rs:44, :171)
+
+    def __init__(self, mphf, keys, values):
+        self.mphf, self.keys, self.values = mphf, keys, values
+
+    @classmethod
+    def _create_map(cls, keys, values, mphf):
+        keys, values = _u64(keys), _u64(values)
+        if len(keys) != len(values):
+            raise ValueError("keys and values differ in length")
+        ko, vo = np.empty_like(keys), np.empty_like(values)
+        _check(N.lib().bphf_map_permute_u64(mphf._h, C.c_void_p(keys.ctypes.data), C.c_void_p(values.ctypes.data),
+                                            len(keys), C.c_void_p(ko.ctypes.data), C.c_void_p(vo.ctypes.data),
+                                            N.MEM_HOST, None))
+        return cls(mphf, ko, vo)
+
+    @classmethod
+    def new(cls, keys, data, device=0):
+        """BoomHashMap::new (src/hashmap.rs:43-46)"""
+        return cls._create_map(keys, data, Mphf.new(cls.GAMMA, _u64(keys), device=device))
+
+    @classmethod
+    def new_parallel(cls, keys, data, device=0):
+        """BoomHashMap::new_parallel (src/hashmap.rs:170-173)"""
+        return cls._create_map(keys, data, Mphf.new_parallel(cls.GAMMA, _u64(keys), None, device=device))
+
+    @classmethod
+    def new_with_mphf(cls, mphf, keys, data):
+        """the gamma sweep of BASELINE config 5 builds the Mphf directly and wraps it"""
+        return cls._create_map(keys, data, mphf)
+
+    def get_batch(self, queries):
+        """BoomHashMap::get over a batch (src/hashmap.rs:49-66) -> (values, found mask)"""
+        q = _u64(queries)
+        vals = np.empty(len(q), dtype=np.uint64)
+        found = np.empty(len(q), dtype=np.uint8)
+        _check(N.lib().bphf_map_get_batch_u64(self.mphf._h, C.c_void_p(self.keys.ctypes.data),
+                                              C.c_void_p(self.values.ctypes.data), len(self.keys),
+                                              C.c_void_p(q.ctypes.data), len(q), C.c_void_p(vals.ctypes.data),
+                                              C.c_void_p(found.ctypes.data), N.MEM_HOST, None))
+        return vals, found.astype(bool)
+
+    def get(self, key):
+        vals, found = self.get_batch([key])
+        return int(vals[0]) if found[0] else None
+
+    def get_key_id(self, key):
+        """src/hashmap.rs:88-105"""
+        q = _u64([key])
+        vals = np.empty(1, dtype=np.uint64)
+        found = np.empty(1, dtype=np.uint8)
+        _check(N.lib().bphf_map_get_batch_u64(self.mphf._h, C.c_void_p(self.keys.ctypes.data), None, len(self.keys),
+                                              C.c_void_p(q.ctypes.data), 1, C.c_void_p(vals.ctypes.data),
+                                              C.c_void_p(found.ctypes.data), N.MEM_HOST, None))
+        return int(vals[0]) if found[0] else None
+
+    def get_key(self, id):
+        """src/hashmap.rs:117-124 (keeps the reference's `id > len` bound check)"""
+        if id > len(self.keys):
+            return None
+        return int(self.keys[id])  # id == len raises IndexError like the reference panics
+
+    def __len__(self):
+        return len(self.keys)
+
+    def is_empty(self):
+        return len(self.keys) == 0
+
+    def iter(self):
+        return zip(self.keys.tolist(), self.values.tolist())
+
+
+class NoKeyBoomHashMap:
+    """NoKeyBoomHashMap<u64, u64> (src/hashmap.rs:434-523): values only, no key check on get."""
+
+    def __init__(self, mphf, values):
+        self.mphf, self.values = mphf, values
+
+    @classmethod
+    def new_with_mphf(cls, mphf, values):
+        """src/hashmap.rs:495-497 -- values must already be in MPHF order"""
+        return cls(mphf, _u64(values))
+
+    @classmethod
+    def new_parallel(cls, keys, data, device=0):
+        """src/hashmap.rs:489-493"""
+        m = BoomHashMap.new_parallel(keys, data, device=device)
+        return cls(m.mphf, m.values)
+
+    new = new_parallel
+
+    def get_batch(self, queries):
+        """src/hashmap.rs:500-510: Some(values[pos]) whenever try_hash is Some"""
+        pos = self.mphf.hash_batch(_u64(queries))
+        ok = pos < np.uint64(len(self.values))
+        out = np.zeros(len(pos), dtype=np.uint64)
+        out[ok] = self.values[pos[ok].astype(np.int64)]
+        return out, ok

@@ -1,0 +1,200 @@
+"""Host-side mirror of `boomphf::Mphf<u64>` over the C ABI (include/boomphf_cuda.h).
+
+Same names, argument meaning and failure behaviour as the reference
+(/root/reference/src/lib.rs): `Mphf.new` (:235), `Mphf.new_parallel` (:363), `hash` (:324),
+`try_hash` (:340).  Where the reference panics, this raises `MphfPanic` with the same text.
+Key sets are numpy uint64 arrays (host) or CUDA torch tensors of dtype int64/uint64 (device).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _native as N
+
+
+class MphfPanic(RuntimeError):
+    """What a Rust panic of the reference turns into on this side of the boundary."""
+
+    def __init__(self, code, text):
+        super().__init__(text)
+        self.code = code
+
+
+def _check(rc):
+    if rc != N.BPHF_OK:
+        raise MphfPanic(rc, N.last_error() or "boomphf_cuda error %d" % rc)
+
+
+def _is_torch_cuda(x):
+    return hasattr(x, "is_cuda") and hasattr(x, "data_ptr") and bool(x.is_cuda)
+
+
+def _as_keys(keys):
+    """-> (pointer, n, mem, device_or_None, keepalive)"""
+    if _is_torch_cuda(keys):
+        import torch
+        if keys.dtype not in (torch.int64, torch.uint64):
+            raise TypeError("device keys must be int64/uint64")
+        k = keys.contiguous()
+        return C.c_void_p(k.data_ptr()), k.numel(), N.MEM_DEVICE, k.device.index or 0, k
+    if hasattr(keys, "is_cuda") and hasattr(keys, "numpy"):  # CPU torch tensor
+        import torch
+        if keys.dtype not in (torch.int64, torch.uint64):
+            raise TypeError("keys must be int64/uint64")
+        keys = keys.contiguous().view(torch.int64).numpy().view(np.uint64)
+    a = np.ascontiguousarray(np.asarray(keys, dtype=np.uint64))
+    return C.c_void_p(a.ctypes.data), a.size, N.MEM_HOST, None, a
+
+
+def _stream_ptr(stream):
+    if stream is None:
+        return None
+    if hasattr(stream, "cuda_stream"):
+        return C.c_void_p(stream.cuda_stream)
+    return C.c_void_p(int(stream))
+
+
+class Mphf:
+    """A minimal perfect hash function over a set of u64 keys, resident on one B200."""
+
+    def __init__(self, handle, device):
+        self._h = C.c_void_p(handle)
+        self.device = device
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def close(self):
+        if getattr(self, "_h", None):
+            N.lib().bphf_free(self._h)
+            self._h = None
+
+    # ---- constructors ---------------------------------------------------------------------
+    @classmethod
+    def _build(cls, gamma, objects, starting_seed, device, stream):
+        ptr, n, mem, dev, keep = _as_keys(objects)
+        if dev is not None:
+            device = dev
+        out = C.c_void_p()
+        rc = N.lib().bphf_build_u64(ptr, n, float(gamma), 0 if starting_seed is None else 1,
+                                    0 if starting_seed is None else int(starting_seed), int(device), mem,
+                                    _stream_ptr(stream), C.byref(out))
+        del keep
+        _check(rc)
+        return cls(out.value, int(device))
+
+    @classmethod
+    def new(cls, gamma, objects, device=0, stream=None):
+        """Mphf::new(gamma, objects)  (src/lib.rs:235).  Same result as new_parallel."""
+        return cls._build(gamma, objects, None, device, stream)
+
+    @classmethod
+    def new_parallel(cls, gamma, objects, starting_seed=None, device=0, stream=None):
+        """Mphf::new_parallel(gamma, objects, starting_seed)  (src/lib.rs:363)."""
+        return cls._build(gamma, objects, starting_seed, device, stream)
+
+    @classmethod
+    def from_levels(cls, levels, device=0):
+        """Upload a deserialised Mphf: levels = [(bits, words u64[], ranks u64[]), ...]."""
+        n = len(levels)
+        bits = np.array([l[0] for l in levels], dtype=np.uint64)
+        words = [np.ascontiguousarray(l[1], dtype=np.uint64) for l in levels]
+        ranks = [np.ascontiguousarray(l[2], dtype=np.uint64) for l in levels]
+        for b, w, r in zip(bits, words, ranks):
+            if len(w) != (int(b) + 63) // 64 or len(r) != (len(w) + 7) // 8:
+                raise ValueError("level arrays do not match bits")
+        wp = (C.c_void_p * max(n, 1))(*[w.ctypes.data for w in words])
+        rp = (C.c_void_p * max(n, 1))(*[r.ctypes.data for r in ranks])
+        out = C.c_void_p()
+        _check(N.lib().bphf_from_levels(n, C.c_void_p(bits.ctypes.data), wp, rp, int(device), C.byref(out)))
+        return cls(out.value, int(device))
+
+    # ---- data model -------------------------------------------------------------------------
+    @property
+    def num_levels(self):
+        v = C.c_uint32()
+        _check(N.lib().bphf_num_levels(self._h, C.byref(v)))
+        return int(v.value)
+
+    def level_dims(self, level):
+        b, w, r = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        rc = N.lib().bphf_level_dims(self._h, level, C.byref(b), C.byref(w), C.byref(r))
+        if rc != N.BPHF_OK:
+            raise MphfPanic(rc, "that level doesn't exist")  # src/lib.rs:302
+        return int(b.value), int(w.value), int(r.value)
+
+    def level(self, level):
+        """(bits, words, ranks) of one level == (BitVector{bits, vector}, Box<[u64]>)"""
+        bits, nw, nr = self.level_dims(level)
+        words = np.empty(nw, dtype=np.uint64)
+        ranks = np.empty(nr, dtype=np.uint64)
+        _check(N.lib().bphf_level_export(self._h, level, C.c_void_p(words.ctypes.data),
+                                         C.c_void_p(ranks.ctypes.data), N.MEM_HOST))
+        return bits, words, ranks
+
+    def levels(self):
+        """All levels with two bulk copies (bphf_export_all)."""
+        tw, tr, _ = self.total_dims()
+        words = np.empty(tw, dtype=np.uint64)
+        ranks = np.empty(tr, dtype=np.uint64)
+        _check(N.lib().bphf_export_all(self._h, C.c_void_p(words.ctypes.data), C.c_void_p(ranks.ctypes.data),
+                                       N.MEM_HOST))
+        out, wo, ro = [], 0, 0
+        for l in range(self.num_levels):
+            bits, nw, nr = self.level_dims(l)
+            out.append((bits, words[wo:wo + nw], ranks[ro:ro + nr]))
+            wo += nw
+            ro += nr
+        return out
+
+    def total_dims(self):
+        w, r, k = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        _check(N.lib().bphf_total_dims(self._h, C.byref(w), C.byref(r), C.byref(k)))
+        return int(w.value), int(r.value), int(k.value)
+
+    def build_stats(self):
+        st = N.BuildStats()
+        _check(N.lib().bphf_get_build_stats(self._h, C.byref(st)))
+        nl = int(st.n_levels)
+        return {
+            "n_levels": nl, "tail_level": int(st.tail_level),
+            "keys_in": [int(st.keys_in[i]) for i in range(nl)], "bits": [int(st.bits[i]) for i in range(nl)],
+            "kernel_launches": int(st.kernel_launches), "host_syncs": int(st.host_syncs),
+            "pass_ms": [float(st.pass_ms[i]) for i in range(nl)], "fin_ms": [float(st.fin_ms[i]) for i in range(nl)],
+            "tail_ms": float(st.tail_ms), "ranks_ms": float(st.ranks_ms), "total_ms": float(st.total_ms),
+        }
+
+    # ---- lookups ----------------------------------------------------------------------------
+    def hash_batch(self, keys, out=None, stream=None):
+        """try_hash over a batch; entries equal to NONE (u64::MAX) are `None`.
+        numpy in -> numpy out; CUDA tensor in -> CUDA tensor out (int64 view of the u64 values)."""
+        ptr, n, mem, dev, keep = _as_keys(keys)
+        if mem == N.MEM_DEVICE:
+            import torch
+            if dev != self.device:
+                raise ValueError("keys live on another device than the Mphf")
+            if out is None:
+                out = torch.empty(n, dtype=keep.dtype, device=keep.device)
+            if stream is None:
+                stream = torch.cuda.current_stream(keep.device)
+            _check(N.lib().bphf_hash_batch_u64(self._h, ptr, n, C.c_void_p(out.data_ptr()), mem, _stream_ptr(stream)))
+            return out
+        if out is None:
+            out = np.empty(n, dtype=np.uint64)
+        _check(N.lib().bphf_hash_batch_u64(self._h, ptr, n, C.c_void_p(out.ctypes.data), mem, _stream_ptr(stream)))
+        return out
+
+    def try_hash(self, item):
+        """Mphf::try_hash (src/lib.rs:340): Some(rank) or None"""
+        v = int(self.hash_batch(np.array([item], dtype=np.uint64))[0])
+        return None if v == N.NONE else v
+
+    def hash(self, item):
+        """Mphf::hash (src/lib.rs:324); an item outside the construction set may panic"""
+        v = self.try_hash(item)
+        if v is None:
+            raise MphfPanic(N.BPHF_ERR_ARG, "internal error: entered unreachable code: must find a hash value")
+        return v

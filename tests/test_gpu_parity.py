@@ -1,0 +1,273 @@
+"""Parity tests proper (run on a B200 with -m gpu): the CUDA path, called through the C ABI, against the CPU
+oracle on the same seeded inputs -- bit-exact per-level words, ranks and hash values -- plus the committed
+golden fingerprints and size-independent properties at the BASELINE sizes."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "vectors.json")))
+from test_oracle import _keys_for  # noqa: E402
+
+
+def assert_same_levels(got, exp):
+    assert len(got) == len(exp), ("level count", len(got), len(exp))
+    for l, ((b0, w0, r0), (b1, w1, r1)) in enumerate(zip(got, exp)):
+        assert b0 == b1, ("bits", l, b0, b1)
+        assert np.array_equal(w0, w1), ("words differ at level", l)
+        assert np.array_equal(r0, r1), ("ranks differ at level", l)
+
+
+@pytest.mark.parametrize("entry", GOLDEN["mphf"], ids=[e["name"] for e in GOLDEN["mphf"]])
+def test_golden_fingerprints(pkg, oracle, entry):
+    keys = _keys_for(entry["name"], oracle)
+    seed = entry["starting_seed"]
+    m = pkg.Mphf.new_parallel(entry["gamma"], keys, seed)
+    lv = m.levels()
+    assert [l[0] for l in lv] == entry["bits"]
+    assert oracle.fingerprint(lv) == entry["sha256"]
+    if seed is None:
+        m2 = pkg.Mphf.new(entry["gamma"], keys)
+        assert oracle.fingerprint(m2.levels()) == entry["sha256"]
+        if len(keys):
+            assert [int(v) for v in m.hash_batch(keys[:6])] == entry["hash_first"]
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 31, 32, 33, 149, 150, 151, 1000, 4095, 4096, 4097, 8191, 8192, 8193,
+                               20000, 65537, 300001, 1 << 20, 3_000_000])
+def test_build_and_hash_parity_sizes(pkg, oracle, n):
+    keys = oracle.keygen(n, seed=n + 1, kind=0)
+    m = pkg.Mphf.new_parallel(1.7, keys, None)
+    ref = oracle.OracleMphf.new_parallel(1.7, keys)
+    assert_same_levels(m.levels(), ref.levels())
+    if n:
+        h = m.hash_batch(keys)
+        assert np.array_equal(h, ref.hash_batch(keys, nthreads=0))
+        assert np.array_equal(np.sort(h), np.arange(n, dtype=np.uint64))
+    st = m.build_stats()
+    assert st["n_levels"] == ref.num_levels and sum(st["keys_in"][:1]) == n
+
+
+@pytest.mark.parametrize("gamma", [1.0100001, 1.02, 1.3, 1.7, 2.0, 3.0, 5.0, 17.5, 100.0])
+def test_gamma_sweep_parity(pkg, oracle, gamma):
+    keys = oracle.keygen(200_000, seed=11, kind=1)
+    m = pkg.Mphf.new_parallel(gamma, keys, None)
+    ref = oracle.OracleMphf.new_parallel(gamma, keys)
+    assert_same_levels(m.levels(), ref.levels())
+    assert np.array_equal(m.hash_batch(keys), ref.hash_batch(keys, nthreads=0))
+
+
+@pytest.mark.parametrize("seed", [0, 1, 5, 30, 31, 32, 40, 2**63, 2**64 - 3])
+def test_starting_seed_parity(pkg, oracle, seed):
+    # build seed index = starting_seed + level (src/lib.rs:370,385); crosses the 1<<(2*iter) wrap at 32
+    keys = oracle.keygen(100_000, seed=1, kind=0)
+    m = pkg.Mphf.new_parallel(1.7, keys, seed)
+    ref = oracle.OracleMphf.new_parallel(1.7, keys, seed)
+    assert_same_levels(m.levels(), ref.levels())
+    # lookups use seed index = level index on both sides, so even the inconsistent answers agree
+    assert np.array_equal(m.hash_batch(keys), ref.hash_batch(keys, nthreads=0))
+
+
+def test_many_levels_crosses_seed_wrap(pkg, oracle):
+    # gamma just above the floor on a larger set needs > 32 levels: level 32 reuses level 0's seed
+    keys = oracle.keygen(3_000_000, seed=3, kind=0)
+    m = pkg.Mphf.new_parallel(1.0100001, keys, None)
+    ref = oracle.OracleMphf.new_parallel(1.0100001, keys)
+    assert_same_levels(m.levels(), ref.levels())
+    assert np.array_equal(m.hash_batch(keys), ref.hash_batch(keys, nthreads=0))
+
+
+def test_level_size_at_and_above_2_pow_32_uses_modulo(pkg, oracle):
+    # gamma * n >= 2^32 switches level 0 from fast-range to `%` (src/lib.rs:81); later levels switch back
+    n = 4_200_000
+    gamma = 1024.0
+    assert oracle.level_size(gamma, n) >= 2**32
+    keys = oracle.keygen(n, seed=21, kind=0)
+    m = pkg.Mphf.new_parallel(gamma, keys, None)
+    ref = oracle.OracleMphf.new_parallel(gamma, keys)
+    got, exp = m.levels(), ref.levels()
+    assert got[0][0] >= 2**32 and got[-1][0] < 2**32
+    assert_same_levels(got, exp)
+    assert np.array_equal(m.hash_batch(keys), ref.hash_batch(keys, nthreads=0))
+
+
+def test_key_order_does_not_matter(pkg, oracle):
+    keys = oracle.keygen(500_000, seed=2, kind=0)
+    a = pkg.Mphf.new(1.7, keys)
+    rng = np.random.default_rng(0)
+    shuffled = keys.copy()
+    rng.shuffle(shuffled)
+    b = pkg.Mphf.new(1.7, shuffled)
+    assert oracle.fingerprint(a.levels()) == oracle.fingerprint(b.levels())
+
+
+def test_literal_bench_input(pkg, oracle):
+    # benches/build.rs:11-12 -- keys 0,2,4,...,1999998, gamma 2.0; scan1_ser hashes them in order
+    keys = oracle.keygen(1_000_000, 0, kind=2)
+    m = pkg.Mphf.new(2.0, keys)
+    ref = oracle.OracleMphf.new(2.0, keys)
+    assert_same_levels(m.levels(), ref.levels())
+    assert np.array_equal(m.hash_batch(keys), ref.hash_batch(keys, nthreads=0))
+
+
+def test_absent_keys_match_oracle_including_none(pkg, oracle):
+    keys = oracle.keygen(100_000, 1, 0)
+    other = oracle.keygen(100_000, 99, 0)
+    m = pkg.Mphf.new(1.7, keys)
+    ref = oracle.OracleMphf.new(1.7, keys)
+    out = m.hash_batch(other)
+    assert np.array_equal(out, ref.hash_batch(other))
+    assert (out == np.uint64(pkg.NONE)).any()
+    assert m.try_hash(int(keys[5])) == ref.try_hash(int(keys[5]))
+    missing = int(other[np.flatnonzero(out == np.uint64(pkg.NONE))[0]])
+    assert m.try_hash(missing) is None
+    with pytest.raises(pkg.MphfPanic):
+        m.hash(missing)
+
+
+def test_duplicate_keys_report_max_iters(pkg):
+    for n in (10, 100_000):
+        keys = np.arange(n, dtype=np.uint64) * 7 + 1
+        keys[-1] = keys[0]
+        with pytest.raises(pkg.MphfPanic) as e:
+            pkg.Mphf.new_parallel(1.7, keys, None)
+        assert e.value.code == -3 and "counldn't find unique hashes" in str(e.value)
+
+
+def test_heavily_duplicated_input_grows_buffers_then_reports_max_iters(pkg):
+    # every key twice: no level shrinks, so the planned arena and redo lists overflow and must be grown
+    base = np.arange(50_000, dtype=np.uint64) * 3 + 5
+    keys = np.concatenate([base, base])
+    with pytest.raises(pkg.MphfPanic) as e:
+        pkg.Mphf.new_parallel(1.7, keys, None)
+    assert e.value.code == -3
+
+
+def test_device_resident_keys_and_outputs(pkg, oracle):
+    import torch
+    n = 2_000_000
+    keys = oracle.keygen(n, seed=8, kind=0)
+    dk = torch.from_numpy(keys.view(np.int64)).cuda()
+    m = pkg.Mphf.new_parallel(1.7, dk, None)
+    ref = oracle.OracleMphf.new_parallel(1.7, keys)
+    assert_same_levels(m.levels(), ref.levels())
+    out = m.hash_batch(dk)
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy().view(np.uint64), ref.hash_batch(keys, nthreads=0))
+    # the same on a caller-provided stream
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        m2 = pkg.Mphf.new_parallel(1.7, dk, None, stream=s)
+        out2 = m2.hash_batch(dk, stream=s)
+    s.synchronize()
+    assert torch.equal(out, out2)
+
+
+def test_device_keygen_matches_oracle_keygen(pkg, oracle):
+    import ctypes as C
+    import torch
+    for kind in (0, 1, 2):
+        d = torch.empty(100_003, dtype=torch.int64, device="cuda")
+        rc = pkg.lib().bphf_keygen_u64(C.c_void_p(d.data_ptr()), 17, d.numel(), 5, kind, 0, None)
+        assert rc == 0
+        assert np.array_equal(d.cpu().numpy().view(np.uint64), oracle.keygen(d.numel(), 5, kind, start=17))
+
+
+def test_from_levels_upload_round_trip(pkg, oracle):
+    keys = oracle.keygen(300_000, 4, 0)
+    ref = oracle.OracleMphf.new(1.7, keys)
+    blob = oracle.serialize_bincode(ref.levels())          # an Mphf serialised by the reference side
+    m = pkg.Mphf.from_levels(oracle.deserialize_bincode(blob))
+    assert np.array_equal(m.hash_batch(keys), ref.hash_batch(keys, nthreads=0))
+    assert oracle.serialize_bincode(m.levels()) == blob
+    # and the other direction: built on the GPU, serialised, read by the reference side
+    g = pkg.Mphf.new(1.7, keys)
+    assert oracle.serialize_bincode(g.levels()) == blob
+    for l in range(g.num_levels):
+        b, w, r = g.level(l)
+        assert b == ref.level(l)[0] and np.array_equal(w, ref.level(l)[1]) and np.array_equal(r, ref.level(l)[2])
+    with pytest.raises(pkg.MphfPanic):
+        g.level_dims(g.num_levels)
+
+
+def test_boomhashmap_parity(pkg, oracle):
+    keys = oracle.keygen(400_000, 6, 1)
+    vals = keys * np.uint64(3) + np.uint64(1)
+    hm = pkg.BoomHashMap.new_parallel(keys, vals)
+    ref = oracle.OracleMphf.new_parallel(1.7, keys)
+    mk, mv = ref.create_map(keys, vals)
+    assert np.array_equal(hm.keys, mk) and np.array_equal(hm.values, mv)
+    q = np.concatenate([keys[:1000], oracle.keygen(1000, 77, 0)])
+    v, found = hm.get_batch(q)
+    rv, rfound = ref.map_get_batch(mk, mv, q)
+    assert np.array_equal(found, rfound) and np.array_equal(v, rv)
+    assert hm.get(int(keys[3])) == int(vals[3]) and hm.get(12345) is None
+    assert hm.get_key_id(int(keys[3])) == ref.try_hash(int(keys[3]))
+    assert len(hm) == len(keys) and hm.get_key(7) == int(mk[7])
+    nk = pkg.NoKeyBoomHashMap.new_parallel(keys, vals)
+    out, ok = nk.get_batch(keys[:500])
+    assert ok.all() and np.array_equal(out, vals[:500])
+
+
+def test_boomhashmap_gamma_sweep_with_prebuilt_mphf(pkg, oracle):
+    # BASELINE config 5 at a size the oracle finishes in seconds; gamma = 1.0 must be rejected
+    keys = oracle.keygen(1_000_000, 5, 1)
+    vals = np.arange(len(keys), dtype=np.uint64)
+    with pytest.raises(pkg.MphfPanic) as e:
+        pkg.Mphf.new_parallel(1.0, keys, None)
+    assert e.value.code == -2
+    for gamma in (1.7, 2.0, 5.0):
+        m = pkg.Mphf.new_parallel(gamma, keys, None)
+        ref = oracle.OracleMphf.new_parallel(gamma, keys)
+        assert_same_levels(m.levels(), ref.levels())
+        hm = pkg.BoomHashMap.new_with_mphf(m, keys, vals)
+        v, found = hm.get_batch(keys[::97])
+        assert found.all() and np.array_equal(v, vals[::97])
+
+
+def test_ten_million_full_oracle_comparison(pkg, oracle):
+    n = 10_000_000
+    keys = oracle.keygen(n, seed=1, kind=0)
+    m = pkg.Mphf.new_parallel(1.7, keys, None)
+    ref = oracle.OracleMphf.new_parallel(1.7, keys)
+    assert_same_levels(m.levels(), ref.levels())
+    assert np.array_equal(m.hash_batch(keys), ref.hash_batch(keys, nthreads=0))
+
+
+def test_baseline_size_100m_properties(pkg, oracle):
+    """BASELINE configs[1]: 1e8 random u64 keys, gamma 1.7, one B200.  Size-independent checks:
+    the outputs are a permutation of 0..n (the reference's own property), total popcount == n,
+    ranks == cumulative popcounts, rebuilding gives the same structure (checksum of checksums),
+    and a 1e6 sample of keys agrees with an oracle that was fed the exported levels."""
+    import ctypes as C
+    import torch
+    n = 100_000_000
+    dk = torch.empty(n, dtype=torch.int64, device="cuda")
+    assert pkg.lib().bphf_keygen_u64(C.c_void_p(dk.data_ptr()), 0, n, 1, 0, 0, None) == 0
+    m = pkg.Mphf.new_parallel(1.7, dk, None)
+    out = m.hash_batch(dk)
+    torch.cuda.synchronize()
+    bad = C.c_uint64(123)
+    assert pkg.lib().bphf_check_permutation(C.c_void_p(out.data_ptr()), n, 0, C.byref(bad)) == 0
+    assert bad.value == 0
+    lv = m.levels()
+    pop = 0
+    for bits, words, ranks in lv:
+        pc = np.bitwise_count(words).astype(np.uint64)
+        blocks = np.add.reduceat(pc, np.arange(0, len(pc), 8))
+        excl = np.concatenate([[0], np.cumsum(blocks)[:-1]]).astype(np.uint64) + np.uint64(pop)
+        assert np.array_equal(ranks, excl)
+        pop += int(pc.sum())
+    assert pop == n and m.total_dims()[2] == n
+    fp = oracle.fingerprint(lv)
+    m2 = pkg.Mphf.new_parallel(1.7, dk, None)
+    assert oracle.fingerprint(m2.levels()) == fp
+    sample = oracle.keygen(1_000_000, 1, 0, start=54_321_000)
+    ref = oracle.OracleMphf.from_levels(lv)
+    assert np.array_equal(m.hash_batch(sample), ref.hash_batch(sample, nthreads=0))
+    # level sizes follow max(255, floor(gamma * k)) with k = keys left (src/lib.rs:369,384)
+    st = m.build_stats()
+    assert st["keys_in"][0] == n and [oracle.level_size(1.7, k) for k in st["keys_in"]] == st["bits"]

@@ -1,0 +1,226 @@
+"""CPU tests of the oracle (the C restatement of the reference) against the committed golden vectors,
+the reference's own property tests (src/lib.rs:702-885: outputs are a permutation of 0..n), and the
+edge cases SURVEY.md section 4 lists.  No GPU needed."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+GOLDEN = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "vectors.json")))
+
+
+def test_switch_matches_golden(oracle):
+    assert oracle.lib().bo_wy_swap_8byte_tail() == GOLDEN["wy_swap_8byte_tail"]
+
+
+def test_wyhash_readme_known_answers(oracle):
+    # the two literals of the `wyhash` crate README -- the only externally sourced vectors
+    assert "%016x" % oracle.wyhash_bytes([0, 1, 2], 3) == GOLDEN["readme_kat"]["wyhash_bytes_012_seed3"]
+    assert "%016x" % oracle.wyrng(3)[0] == GOLDEN["readme_kat"]["wyrng_seed3"]
+
+
+def test_hash_with_seed_vectors(oracle):
+    for v in GOLDEN["hash_with_seed"]:
+        assert "%016x" % oracle.hash_with_seed(v["iter"], int(v["key"], 16)) == v["h"], v
+
+
+def test_seed_shift_wraps_like_release_builds(oracle):
+    # 1 << (iter + iter) wraps modulo 64 (src/lib.rs:62): iter 32 == iter 0, 33 == 1, 64 == 0
+    for k in (1, 2, 0x0123456789ABCDEF):
+        assert oracle.hash_with_seed(32, k) == oracle.hash_with_seed(0, k)
+        assert oracle.hash_with_seed(33, k) == oracle.hash_with_seed(1, k)
+        assert oracle.hash_with_seed(64, k) == oracle.hash_with_seed(0, k)
+
+
+def test_hashmod_vectors_both_sides_of_2_pow_32(oracle):
+    for v in GOLDEN["hashmod"]:
+        assert oracle.hashmod(v["iter"], int(v["key"], 16), v["n"]) == v["idx"], v
+
+
+def test_hashmod_definition(oracle):
+    # fastmod on the folded hash below 2^32, plain modulo from 2^32 on (src/lib.rs:77-88)
+    rng = np.random.default_rng(5)
+    for k in rng.integers(0, 2**63, size=50, dtype=np.uint64):
+        k = int(k)
+        h = oracle.hash_with_seed(3, k)
+        fold = (h & 0xFFFFFFFF) ^ (h >> 32)
+        for n in (255, 1000003, 2**32 - 1):
+            assert oracle.hashmod(3, k, n) == (fold * n) >> 32
+        for n in (2**32, 2**32 + 1, 5_000_000_000):
+            assert oracle.hashmod(3, k, n) == h % n
+
+
+def test_level_size(oracle):
+    for v in GOLDEN["level_size"]:
+        assert oracle.level_size(v["gamma"], v["k"]) == v["size"]
+    assert oracle.level_size(1.7, 149) == 255 and oracle.level_size(1.7, 150) == 255
+    assert oracle.level_size(1.7, 151) == 256  # 256.7 truncates
+
+
+def _keys_for(name, oracle):
+    table = {
+        "even_1000_g1.7": lambda: np.arange(1000, dtype=np.uint64) * 2,
+        "even_1000_g2.0": lambda: np.arange(1000, dtype=np.uint64) * 2,
+        "doctest_9": lambda: np.array([1, 10, 1000, 23, 457, 856, 845, 124, 912], dtype=np.uint64),
+        "empty": lambda: np.zeros(0, dtype=np.uint64),
+        "one": lambda: np.array([42], dtype=np.uint64),
+        "two": lambda: np.array([42, 43], dtype=np.uint64),
+        "n149": lambda: oracle.keygen(149, 3, 0),
+        "n150": lambda: oracle.keygen(150, 3, 0),
+        "rand_5000_g1.7": lambda: oracle.keygen(5000, 1, 0),
+        "rand_100k_g1.7": lambda: oracle.keygen(100000, 1, 0),
+        "rand_100k_g2.0": lambda: oracle.keygen(100000, 2, 0),
+        "rand_100k_g5.0": lambda: oracle.keygen(100000, 3, 0),
+        "rand_20k_g1.02": lambda: oracle.keygen(20000, 4, 0),
+        "kmer31_100k_g1.7": lambda: oracle.keygen(100000, 5, 1),
+        "bench_even_1M_g2.0": lambda: oracle.keygen(1000000, 0, 2),
+        "rand_1M_g1.7": lambda: oracle.keygen(1000000, 1, 0),
+        "rand_100k_g1.7_seed5": lambda: oracle.keygen(100000, 1, 0),
+        "rand_100k_g1.7_seed30": lambda: oracle.keygen(100000, 1, 0),
+    }
+    return table[name]()
+
+
+@pytest.mark.parametrize("entry", GOLDEN["mphf"], ids=[e["name"] for e in GOLDEN["mphf"]])
+def test_mphf_golden_fingerprints(oracle, entry):
+    keys = _keys_for(entry["name"], oracle)
+    seed = entry["starting_seed"]
+    builds = [oracle.OracleMphf.new_parallel(entry["gamma"], keys, seed, nthreads=4)]
+    if seed is None:
+        builds.append(oracle.OracleMphf.new(entry["gamma"], keys))
+    for m in builds:
+        lv = m.levels()
+        assert [l[0] for l in lv] == entry["bits"]
+        assert oracle.fingerprint(lv) == entry["sha256"]
+    if seed is None:
+        assert [builds[0].hash(int(k)) for k in keys[:6]] == entry["hash_first"]
+        h = builds[0].hash_batch(keys)
+        assert np.array_equal(np.sort(h), np.arange(len(keys), dtype=np.uint64))
+
+
+def test_serial_equals_parallel_bit_for_bit(oracle):
+    # the reference never compares new vs new_parallel; order-independence says they agree
+    rng = np.random.default_rng(11)
+    for n in (3, 77, 1000, 31337, 200000):
+        keys = np.unique(rng.integers(0, 2**64, size=n, dtype=np.uint64))
+        a = oracle.OracleMphf.new(1.7, keys)
+        for threads in (1, 2, 7):
+            b = oracle.OracleMphf.new_parallel(1.7, keys, None, nthreads=threads)
+            assert oracle.fingerprint(a.levels()) == oracle.fingerprint(b.levels())
+        shuffled = keys.copy()
+        rng.shuffle(shuffled)
+        c = oracle.OracleMphf.new(1.7, shuffled)
+        assert oracle.fingerprint(a.levels()) == oracle.fingerprint(c.levels())
+
+
+def test_mphf_property_quickcheck_style(oracle):
+    # check_mphf (src/lib.rs:713-747) over random u64 sets
+    rng = np.random.default_rng(1)
+    for trial in range(60):
+        n = int(rng.integers(0, 400))
+        keys = np.unique(rng.integers(0, 2**64, size=n, dtype=np.uint64))
+        for m in (oracle.OracleMphf.new(1.7, keys), oracle.OracleMphf.new_parallel(1.7, keys, None, nthreads=2)):
+            h = m.hash_batch(keys)
+            assert np.array_equal(np.sort(h), np.arange(len(keys), dtype=np.uint64))
+
+
+def test_ranks_are_cumulative_popcounts(oracle):
+    keys = oracle.keygen(50000, 9, 0)
+    lv = oracle.OracleMphf.new(1.7, keys).levels()
+    pop = 0
+    for bits, words, ranks in lv:
+        assert len(words) == (bits + 63) // 64 and len(ranks) == (len(words) + 7) // 8
+        for i, w in enumerate(words):
+            if i % 8 == 0:
+                assert int(ranks[i // 8]) == pop
+            pop += bin(int(w)).count("1")
+    assert pop == len(keys)
+
+
+def test_gamma_assertion(oracle):
+    keys = np.arange(10, dtype=np.uint64)
+    for g in (1.0, 1.01, 0.5, float("nan")):
+        with pytest.raises(oracle.OracleError) as e:
+            oracle.OracleMphf.new(g, keys)
+        assert e.value.code == oracle.BO_ERR_GAMMA
+        with pytest.raises(oracle.OracleError):
+            oracle.OracleMphf.new_parallel(g, keys)
+    oracle.OracleMphf.new(1.0100001, keys)
+
+
+def test_duplicates_exhaust_max_iters(oracle):
+    keys = np.array([5, 6, 7, 7, 8], dtype=np.uint64)
+    for build in (lambda: oracle.OracleMphf.new(1.7, keys), lambda: oracle.OracleMphf.new_parallel(1.7, keys)):
+        with pytest.raises(oracle.OracleError) as e:
+            build()
+        assert e.value.code == oracle.BO_ERR_MAX_ITERS
+
+
+def test_try_hash_of_absent_keys(oracle):
+    keys = oracle.keygen(10000, 1, 0)
+    m = oracle.OracleMphf.new(1.7, keys)
+    other = oracle.keygen(10000, 2, 0)
+    out = m.hash_batch(other)
+    none = out == np.uint64(oracle.NONE)
+    assert none.any() and (~none).any()          # some None, some arbitrary Some(x)
+    assert (out[~none] < len(keys)).all()
+
+
+def test_empty_set_builds_one_empty_level(oracle):
+    m = oracle.OracleMphf.new(1.7, np.zeros(0, dtype=np.uint64))
+    lv = m.levels()
+    assert len(lv) == 1 and lv[0][0] == 255 and not lv[0][1].any() and list(lv[0][2]) == [0]
+    assert m.try_hash(1) is None
+    with pytest.raises(RuntimeError):
+        m.hash(1)
+
+
+def test_serde_layout_round_trip(oracle):
+    keys = oracle.keygen(30000, 4, 0)
+    m = oracle.OracleMphf.new(1.7, keys)
+    blob = oracle.serialize_bincode(m.levels())
+    lv = oracle.deserialize_bincode(blob)
+    m2 = oracle.OracleMphf.from_levels(lv)
+    assert np.array_equal(m2.hash_batch(keys), m.hash_batch(keys))
+    assert oracle.serialize_bincode(m2.levels()) == blob
+    # u64 L, then per level u64 bits, u64 W, W words, u64 R, R ranks
+    L = int(np.frombuffer(blob[:8], dtype="<u8")[0])
+    assert L == m.num_levels
+    assert len(blob) == 8 + sum(24 + 8 * len(w) + 8 * len(r) for _, w, r in m.levels())
+
+
+def test_starting_seed_changes_build_but_not_lookup_seed(oracle):
+    keys = oracle.keygen(5000, 1, 0)
+    a = oracle.OracleMphf.new_parallel(1.7, keys, None)
+    z = oracle.OracleMphf.new_parallel(1.7, keys, 0)
+    b = oracle.OracleMphf.new_parallel(1.7, keys, 3)
+    assert oracle.fingerprint(a.levels()) == oracle.fingerprint(z.levels())
+    assert oracle.fingerprint(a.levels()) != oracle.fingerprint(b.levels())
+    # hash() uses seed index = level index (src/lib.rs:327), so a Some(3) build is not self-consistent
+    h = b.hash_batch(keys)
+    assert not np.array_equal(np.sort(h), np.arange(len(keys), dtype=np.uint64))
+
+
+def test_create_map_and_get(oracle):
+    keys = oracle.keygen(20000, 6, 1)
+    vals = keys * np.uint64(3) + np.uint64(1)
+    m = oracle.OracleMphf.new(1.7, keys)
+    mk, mv = m.create_map(keys, vals)
+    assert np.array_equal(m.hash_batch(mk), np.arange(len(keys), dtype=np.uint64))
+    assert np.array_equal(mv, mk * np.uint64(3) + np.uint64(1))
+    q = np.concatenate([keys[:100], oracle.keygen(100, 77, 0)])
+    v, found = m.map_get_batch(mk, mv, q)
+    assert found[:100].all() and not found[100:].any()
+    assert np.array_equal(v[:100], vals[:100])
+
+
+def test_keygen_is_distinct_and_matches_golden(oracle):
+    assert ["%016x" % int(v) for v in oracle.keygen(4, 1, 0)] == GOLDEN["keygen"]["kind0_seed1_first4"]
+    assert ["%016x" % int(v) for v in oracle.keygen(4, 5, 1)] == GOLDEN["keygen"]["kind1_seed5_first4"]
+    for kind in (0, 1, 2):
+        k = oracle.keygen(300000, 3, kind)
+        assert len(np.unique(k)) == len(k)
+    assert (oracle.keygen(100000, 3, 1) < np.uint64(1 << 62)).all()
+    # chunked generation is consistent
+    assert np.array_equal(oracle.keygen(1000, 3, 0, start=500), oracle.keygen(1500, 3, 0)[500:])
