@@ -16,7 +16,6 @@ import argparse
 import ctypes as C
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -41,53 +40,85 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region, in-process through NVML (an nvidia-smi
+    subprocess per sample stalls the driver for tens of ms and would perturb a 3 ms step)."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
-
-    def __init__(self, device_index):
-        self.idx = device_index
-        self.rows = []
+    def __init__(self, torch_index):
+        self.samples = []
         self._stop = threading.Event()
         self._t = None
+        self._h = None
+        self._nv = None
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            self._nv = nv
+            h = None
+            try:
+                import torch
+                uuid = str(torch.cuda.get_device_properties(torch_index).uuid)
+                uuid = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
+                h = nv.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except Exception:
+                h = None
+            if h is None:
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+                idx = torch_index
+                if vis:
+                    try:
+                        idx = int(vis.split(",")[torch_index])
+                    except Exception:
+                        idx = torch_index
+                h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self._h = h
+            self._max = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        except Exception:
+            self._nv = None
+
+    def _sample(self):
+        nv, h = self._nv, self._h
+        try:
+            sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            try:
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+            except Exception:
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            self.samples.append((sm, int(r)))
+        except Exception:
+            pass
 
     def _run(self):
         while not self._stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                for line in out.strip().splitlines():
-                    self.rows.append([c.strip() for c in line.split(",")])
-            except Exception:
-                pass
-            self._stop.wait(0.2)
+            self._sample()
+            self._stop.wait(0.1)
 
     def __enter__(self):
-        self._t = threading.Thread(target=self._run, daemon=True)
-        self._t.start()
+        if self._nv is not None:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
         return self
 
     def __exit__(self, *a):
         self._stop.set()
-        self._t.join(timeout=6)
+        if self._t is not None:
+            self._t.join(timeout=2)
+            self._sample()
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[1]))
-                mx.append(float(r[2]))
-                for nm, v in zip(names, r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nm)
-            except Exception:
-                continue
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        if self._nv is None or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "note": "NVML unavailable"}
+        nv = self._nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        sm = sorted(s for s, _ in self.samples)
+        seen = set()
+        for _, r in self.samples:
+            for nm, bit in names.items():
+                if r & bit:
+                    seen.add(nm)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self._max, "reasons": sorted(seen), "samples": len(sm)}
 
 
 def algorithmic_bytes(stats):
@@ -144,7 +175,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--keys", type=int, default=100_000_000, help="keys per GPU (BASELINE configs[1]: 1e8)")
@@ -191,8 +222,12 @@ def main():
         return pkg.Mphf.new_parallel(GAMMA, keys, None, stream=stream)
 
     # ---- warm-up ---------------------------------------------------------------------------------------------
+    # clocks ramp from idle for a few hundred ms: spin untimed builds for ~1 s first, then the W warm-up steps
     L.bphf_set_profile(1)
     m = None
+    t_spin = time.perf_counter()
+    while time.perf_counter() - t_spin < 1.0:
+        m = build()
     for _ in range(max(args.warmup, 3)):
         m = build()
     stats = m.build_stats()

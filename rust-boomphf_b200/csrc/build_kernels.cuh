@@ -114,20 +114,37 @@ __global__ void __launch_bounds__(PASS_THREADS)
     const uint64_t n_tiles = (n + PASS_TILE - 1) / PASS_TILE;
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const uint64_t base = key_begin + tile * PASS_TILE + threadIdx.x;
+        const bool full = key_begin + (tile + 1) * PASS_TILE <= key_end;
         uint64_t key[PASS_KPT];
 #pragma unroll
         for (int j = 0; j < PASS_KPT; j++) {
             const uint64_t i = base + (uint64_t)j * PASS_THREADS;
-            key[j] = (i < key_end) ? ld_stream_u64(keys + i) : 0;
+            key[j] = (full || i < key_end) ? ld_stream_u64(keys + i) : 0;
         }
+        // all PASS_KPT fetch_or's are issued back to back (independent), the collide updates follow:
+        // the a-word round trips overlap instead of serialising on `if (old & m)`
+        uint64_t w[PASS_KPT];
+        uint32_t m[PASS_KPT], old[PASS_KPT];
 #pragma unroll
         for (int j = 0; j < PASS_KPT; j++) {
-            const uint64_t i = base + (uint64_t)j * PASS_THREADS;
-            if (i < key_end) {
-                const uint64_t idx = big ? level_index<true>(sp0, key[j], bits) : level_index<false>(sp0, key[j], bits);
-                mark_bit(a32, c32, off32 + (idx >> 5), 1u << (idx & 31));
+            const uint64_t idx = big ? level_index<true>(sp0, key[j], bits) : level_index<false>(sp0, key[j], bits);
+            w[j] = off32 + (idx >> 5);
+            m[j] = 1u << (idx & 31);
+        }
+        if (full) {
+#pragma unroll
+            for (int j = 0; j < PASS_KPT; j++) old[j] = atomicOr(a32 + w[j], m[j]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < PASS_KPT; j++) {
+                const uint64_t i = base + (uint64_t)j * PASS_THREADS;
+                old[j] = 0;
+                if (i < key_end) old[j] = atomicOr(a32 + w[j], m[j]);
             }
         }
+#pragma unroll
+        for (int j = 0; j < PASS_KPT; j++)
+            if (old[j] & m[j]) atomicOr(c32 + w[j], m[j]);
     }
 }
 
@@ -204,11 +221,30 @@ __global__ void __launch_bounds__(PASS_THREADS)
         const uint64_t out = sh_base;
         // rayon filter_map().collect() (src/lib.rs:374-377): append to level l's list (coalesced), and
         // find_collisions of level l for the same key while it is still on chip
-        for (uint32_t i = threadIdx.x; i < total; i += PASS_THREADS) {
-            const uint64_t kk = stage[i];
-            dst[out + i] = kk;
-            const uint64_t idx = c_big ? level_index<true>(c_sp0, kk, c_bits) : level_index<false>(c_sp0, kk, c_bits);
-            mark_bit(a32, c32, c_off32 + (idx >> 5), 1u << (idx & 31));
+        {
+            uint64_t w[PASS_KPT];
+            uint32_t m[PASS_KPT], old[PASS_KPT];
+#pragma unroll
+            for (int j = 0; j < PASS_KPT; j++) {
+                const uint32_t i = threadIdx.x + j * PASS_THREADS;
+                m[j] = 0;
+                w[j] = c_off32;
+                if (i < total) {
+                    const uint64_t kk = stage[i];
+                    dst[out + i] = kk;
+                    const uint64_t idx = c_big ? level_index<true>(c_sp0, kk, c_bits) : level_index<false>(c_sp0, kk, c_bits);
+                    w[j] = c_off32 + (idx >> 5);
+                    m[j] = 1u << (idx & 31);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < PASS_KPT; j++) {
+                old[j] = 0;
+                if (m[j]) old[j] = atomicOr(a32 + w[j], m[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < PASS_KPT; j++)
+                if (old[j] & m[j]) atomicOr(c32 + w[j], m[j]);
         }
         __syncthreads();
     }
