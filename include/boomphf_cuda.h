@@ -129,11 +129,18 @@ typedef struct bphf_build_stats {
     float pass_ms[BPHF_MAX_LEVELS + 1];    /* per-level mark(+filter) kernel time, profile>=1: level 0 only; 2: all */
     float fin_ms[BPHF_MAX_LEVELS + 1];     /* per-level finalize kernel time (profile 2)            */
     float tail_ms, ranks_ms, total_ms;     /* profile 2 (total_ms always)                           */
-    float h2d_ms;                          /* host->device key copy when keys_mem == HOST           */
+    float h2d_ms;                          /* reserved                                              */
+    uint32_t bucketed_levels;              /* levels built by the shared-memory (bucketed) kernels  */
+    uint32_t rebuilds;                     /* 1 when a bucket overflow forced an unbucketed rebuild */
 } bphf_build_stats;
 BPHF_API int bphf_get_build_stats(const bphf_mphf *m, bphf_build_stats *out);
-/* 0: no events; 1: CUDA events around the level-0 pass only; 2: around every kernel */
+/* 0: no events; 1: CUDA events around the kernels of levels 0 and 1; 2: around every kernel.
+ * pass_ms[l] = entry step of level l (scatter / filter+mark), fin_ms[l] = completion step (bucket mark / finalize) */
 BPHF_API int bphf_set_profile(int level);
+/* construction strategy: mode 0 (default) = large levels are built in shared memory after grouping the keys
+ * by bit range ("bucketed"), levels with fewer than bucket_min_keys keys (0 = default 2^20) by L2 atomics;
+ * mode 1 = L2-atomic kernels only.  Both produce identical structures. */
+BPHF_API int bphf_set_build_mode(int mode, uint64_t bucket_min_keys);
 
 /* ---- utilities used by tests and bench (device side) ------------------------------------ */
 /* distinct-by-construction synthetic keys: kind 0 = splitmix64 finaliser of

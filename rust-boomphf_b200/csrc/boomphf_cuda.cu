@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "build_kernels.cuh"
+#include "bucket_kernels.cuh"
 #include "query_kernels.cuh"
 
 using namespace bphf;
@@ -84,6 +85,9 @@ static const DeviceInfo& device_info(int dev) {
         uint64_t thresh = UINT64_MAX;
         CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
         CK(cudaFuncSetAttribute(tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TailSmem)));
+        CK(cudaFuncSetAttribute(scatter0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CK(cudaFuncSetAttribute(scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CK(cudaFuncSetAttribute(bucket_mark_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         if (prev != dev) CK(cudaSetDevice(prev));
         d.init = true;
     }
@@ -131,33 +135,73 @@ static void upload_level_table(bphf_mphf* m, cudaStream_t s) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// plan: upper-biased simulation of the cascade (expected collision fraction 1 - exp(-k/bits))
+// plan: simulation of the cascade with upper- and lower-biased key counts (expected colliding
+// fraction 1 - exp(-k/bits), +-6 sigma).  It only sizes buffers, grids and shared memory and decides
+// which kernel variants get enqueued; the kernels read the real sizes from the device state.
 // ------------------------------------------------------------------------------------------------
+struct LevelPlan {
+    uint64_t k_up = 0, k_lo = 0;
+    bool maybe_bucket = false, surely_bucket = false;
+    uint32_t range_max = 0, count_max = 1;  // bucket geometry upper bounds (for shared-memory sizing)
+    uint64_t need_keys = 0;                 // capacity needed in buf[level & 1]
+};
 struct Plan {
     uint64_t words_cap = 0;
     uint64_t list_cap[2] = {0, 0};
-    std::vector<uint64_t> k_up;  // per non-tail level: upper estimate of keys entering
+    std::vector<LevelPlan> lv;  // non-tail levels
     bool maybe_big = false;
 };
 
-static Plan make_plan(uint64_t n, double gamma) {
+static int g_build_mode = 0;                      // 0 auto (bucketed prefix), 1 plain L2-atomic kernels only
+static uint64_t g_bucket_min_keys = 1ull << 20;   // levels below this are built by the plain kernels
+
+static Plan make_plan(uint64_t n, double gamma, uint32_t slots, bool bucket_enable, uint64_t min_keys) {
     Plan p;
-    uint64_t k = n;
+    uint64_t k_up = n, k_lo = n;
     uint64_t words = 0;
-    for (uint32_t level = 0; level <= BPHF_MAX_LEVELS && k > 0; level++) {
-        const uint64_t bits = level_size(gamma, k);
-        if (level == 0 && (bits >> 32)) p.maybe_big = true;
-        if (k <= TAIL_MAX_KEYS && bits <= TAIL_MAX_BITS) break;
-        words += round_up8((bits + 63) / 64);
-        p.k_up.push_back(k);
-        const double frac = 1.0 - std::exp(-(double)k / (double)bits);
-        const double kn = (double)k * frac;
-        const uint64_t k_next = (uint64_t)(kn + 6.0 * std::sqrt(kn) + 64.0);
-        k = std::min(k, k_next);
+    for (uint32_t level = 0; level <= BPHF_MAX_LEVELS && k_up > 0; level++) {
+        const uint64_t bits_up = level_size(gamma, k_up), bits_lo = level_size(gamma, k_lo);
+        if (level == 0 && (bits_up >> 32)) p.maybe_big = true;
+        if (k_up <= TAIL_MAX_KEYS && bits_up <= TAIL_MAX_BITS) break;
+        words += round_up8((bits_up + 63) / 64);
+        LevelPlan lp;
+        lp.k_up = k_up;
+        lp.k_lo = k_lo;
+        const bool prev_maybe = level == 0 || p.lv[level - 1].maybe_bucket;
+        const bool prev_surely = level == 0 || p.lv[level - 1].surely_bucket;
+        BucketGeom gu, gl;
+        const bool bu = bucket_enable && bucket_geometry(bits_up, k_up, slots, min_keys, &gu);
+        const bool bl = bucket_enable && bucket_geometry(bits_lo, k_lo, slots, min_keys, &gl);
+        lp.maybe_bucket = prev_maybe && (bu || bl);
+        lp.surely_bucket = prev_surely && bu && bl;
+        lp.need_keys = level >= 1 ? k_up : 0;
+        if (lp.maybe_bucket) {
+            // the real geometry is derived from the real k; size for the worst of both estimates
+            if (bu && bl && gu.range == gl.range) {
+                lp.range_max = gu.range;
+                lp.count_max = std::max(gu.count, gl.count);
+            } else {
+                lp.range_max = BUCKET_R_MAX;
+                lp.count_max = std::max(bu ? gu.count : 1u, bl ? gl.count : 1u) + slots;
+                if (lp.count_max > BUCKET_MAX_COUNT) lp.count_max = BUCKET_MAX_COUNT;
+            }
+            const uint64_t cap_max = (uint64_t)std::max(bu ? gu.cap : 0u, bl ? gl.cap : 0u) + 64;
+            lp.need_keys = std::max<uint64_t>(lp.need_keys, (uint64_t)lp.count_max * cap_max);
+        }
+        p.lv.push_back(lp);
+        auto next = [](uint64_t k, uint64_t bits, double sign) {
+            const double frac = 1.0 - std::exp(-(double)k / (double)bits);
+            const double kn = (double)k * frac;
+            const double v = kn + sign * (6.0 * std::sqrt(kn) + 64.0);
+            return v <= 0.0 ? (uint64_t)0 : (uint64_t)v;
+        };
+        k_up = std::min(k_up, next(k_up, bits_up, +1.0));
+        k_lo = std::min(k_lo, next(k_lo, bits_lo, -1.0));
     }
     p.words_cap = words + 1024;
-    p.list_cap[1] = p.k_up.size() > 1 ? p.k_up[1] : 0;  // level 1's list lives in buf[1]
-    p.list_cap[0] = p.k_up.size() > 2 ? p.k_up[2] : 0;  // level 2's list lives in buf[0]
+    for (size_t l = 0; l < p.lv.size(); l++) p.list_cap[l & 1] = std::max(p.list_cap[l & 1], p.lv[l].need_keys);
+    if (bucket_enable && !p.lv.empty() && p.lv.back().maybe_bucket)  // first tail level right after a bucketed one
+        p.list_cap[p.lv.size() & 1] = std::max<uint64_t>(p.list_cap[p.lv.size() & 1], TAIL_MAX_KEYS);
     return p;
 }
 
@@ -168,9 +212,11 @@ namespace {
 
 struct EventPair {
     cudaEvent_t a = nullptr, b = nullptr;
-    int kind = 0;  // 0 pass, 1 finalize, 2 tail, 3 ranks, 4 h2d
+    int kind = 0;  // 0 entry step of a level (scatter / pass / mark_list), 1 completion step (bucket_mark / finalize), 2 tail, 3 ranks
     uint32_t level = 0;
 };
+
+constexpr size_t MAX_DYN_SMEM = 200 * 1024;
 
 struct Builder {
     int device;
@@ -184,7 +230,9 @@ struct Builder {
     uint64_t* d_words = nullptr;
     uint64_t* d_coll = nullptr;
     uint32_t* d_blockpop = nullptr;
-    uint64_t* d_buf[2] = {nullptr, nullptr};
+    uint32_t* d_cursors = nullptr;  // [2][MAX_BUCKETS_ALLOC]
+    uint64_t* d_buf[2] = {nullptr, nullptr};   // key lists / bucket key regions, level l in d_buf[l & 1]
+    uint32_t* d_ibuf[2] = {nullptr, nullptr};  // slot index within the bucket, same offsets (bucketed levels)
     uint64_t phys_words = 0;  // words_cap + TAIL_RESERVE_WORDS
     uint64_t n = 0;
     bool maybe_big = false;
@@ -202,8 +250,11 @@ struct Builder {
         if (d_words) cudaFreeAsync(d_words, s);
         if (d_coll) cudaFreeAsync(d_coll, s);
         if (d_blockpop) cudaFreeAsync(d_blockpop, s);
-        for (int i = 0; i < 2; i++)
+        if (d_cursors) cudaFreeAsync(d_cursors, s);
+        for (int i = 0; i < 2; i++) {
             if (d_buf[i]) cudaFreeAsync(d_buf[i], s);
+            if (d_ibuf[i]) cudaFreeAsync(d_ibuf[i], s);
+        }
         for (auto& e : events) {
             if (e.a) cudaEventDestroy(e.a);
             if (e.b) cudaEventDestroy(e.b);
@@ -213,9 +264,10 @@ struct Builder {
     }
 
     int max_grid() const { return info.sm_count * 8; }
+    uint32_t slots() const { return (uint32_t)info.sm_count * 2; }
 
     size_t begin_event(int kind, uint32_t level) {
-        const bool want = profile >= 2 || (profile == 1 && kind == 0 && level <= 1);
+        const bool want = profile >= 2 || (profile == 1 && kind <= 1 && level <= 1);
         if (!want) return (size_t)-1;
         EventPair e;
         e.kind = kind;
@@ -235,8 +287,10 @@ struct Builder {
         CK(cudaMallocAsync((void**)&d_words, phys_words * 8, s));
         CK(cudaMallocAsync((void**)&d_coll, phys_words * 8, s));
         CK(cudaMallocAsync((void**)&d_blockpop, (phys_words / 8) * 4, s));
+        CK(cudaMallocAsync((void**)&d_cursors, (size_t)2 * MAX_BUCKETS_ALLOC * CURSOR_STRIDE * 4, s));
         CK(cudaMemsetAsync(d_words, 0, phys_words * 8, s));
         CK(cudaMemsetAsync(d_coll, 0, phys_words * 8, s));
+        CK(cudaMemsetAsync(d_cursors, 0, (size_t)2 * MAX_BUCKETS_ALLOC * CURSOR_STRIDE * 4, s));
     }
     // ST_NEED_WORDS: move to a larger arena, keeping everything built so far
     void grow_arena(uint64_t need_words) {
@@ -262,39 +316,43 @@ struct Builder {
         phys_words = new_phys;
         hst.words_cap = new_cap;
     }
+    // ST_NEED_LIST for level `level`: its key list / bucket regions (buf[level & 1]) are too small.  The buffer
+    // holds nothing live at that point (level-2's keys are dead), so it is simply replaced.
     void grow_list(int which, uint64_t need) {
         const uint64_t cap = need + need / 8 + 1024;
         if (d_buf[which]) CK(cudaFreeAsync(d_buf[which], s));
+        if (d_ibuf[which]) CK(cudaFreeAsync(d_ibuf[which], s));
         d_buf[which] = nullptr;
+        d_ibuf[which] = nullptr;
         CK(cudaMallocAsync((void**)&d_buf[which], cap * 8, s));
+        if (hst.bucket_enable) CK(cudaMallocAsync((void**)&d_ibuf[which], cap * 4, s));
         hst.list_cap[which] = cap;
     }
 
-    void launch_pass0(uint64_t begin, uint64_t end) {
-        if (end <= begin) return;
-        const uint64_t tiles = (end - begin + PASS_TILE - 1) / PASS_TILE;
+    uint32_t* a32() const { return reinterpret_cast<uint32_t*>(d_words); }
+    uint32_t* c32() const { return reinterpret_cast<uint32_t*>(d_coll); }
+
+    // ---- plain (L2-atomic) kernels ----------------------------------------------------------------
+    void launch_mark_list(uint32_t level, uint64_t begin, uint64_t end, uint64_t k_up) {
+        const uint64_t cnt = level == 0 ? end - begin : k_up;
+        if (cnt == 0) return;
+        const uint64_t tiles = (cnt + PASS_TILE - 1) / PASS_TILE;
         const int grid = (int)std::min<uint64_t>(tiles, (uint64_t)max_grid());
-        uint32_t* a32 = reinterpret_cast<uint32_t*>(d_words);
-        uint32_t* c32 = reinterpret_cast<uint32_t*>(d_coll);
         if (maybe_big)
-            pass0_kernel<true><<<grid, PASS_THREADS, 0, s>>>(d_state, d_keys, begin, end, a32, c32);
+            mark_list_kernel<true><<<grid, PASS_THREADS, 0, s>>>(d_state, level, d_keys, begin, end, d_buf[0], d_buf[1], a32(), c32());
         else
-            pass0_kernel<false><<<grid, PASS_THREADS, 0, s>>>(d_state, d_keys, begin, end, a32, c32);
+            mark_list_kernel<false><<<grid, PASS_THREADS, 0, s>>>(d_state, level, d_keys, begin, end, d_buf[0], d_buf[1], a32(), c32());
         CK(cudaGetLastError());
         launches++;
     }
     void launch_pass(uint32_t level, uint64_t k_src_up) {
         const uint64_t tiles = std::max<uint64_t>(1, (k_src_up + PASS_TILE - 1) / PASS_TILE);
         const int grid = (int)std::min<uint64_t>(tiles, (uint64_t)max_grid());
-        uint32_t* a32 = reinterpret_cast<uint32_t*>(d_words);
-        uint32_t* c32 = reinterpret_cast<uint32_t*>(d_coll);
-        const size_t ev = begin_event(0, level);
         if (maybe_big)
-            pass_kernel<true><<<grid, PASS_THREADS, 0, s>>>(d_state, level, d_keys, d_buf[0], d_buf[1], a32, c32);
+            pass_kernel<true><<<grid, PASS_THREADS, 0, s>>>(d_state, level, d_keys, d_buf[0], d_buf[1], a32(), c32());
         else
-            pass_kernel<false><<<grid, PASS_THREADS, 0, s>>>(d_state, level, d_keys, d_buf[0], d_buf[1], a32, c32);
+            pass_kernel<false><<<grid, PASS_THREADS, 0, s>>>(d_state, level, d_keys, d_buf[0], d_buf[1], a32(), c32());
         CK(cudaGetLastError());
-        end_event(ev);
         launches++;
     }
     void launch_finalize(uint32_t level, uint64_t k_up) {
@@ -302,21 +360,63 @@ struct Builder {
         const uint64_t pairs = round_up8((bits + 63) / 64) / 2;
         const int grid = (int)std::min<uint64_t>(std::max<uint64_t>(1, (pairs + FIN_THREADS - 1) / FIN_THREADS),
                                                  (uint64_t)max_grid());
-        const size_t ev = begin_event(1, level);
         finalize_kernel<<<grid, FIN_THREADS, 0, s>>>(d_state, level, d_words, d_coll, d_blockpop);
         CK(cudaGetLastError());
-        end_event(ev);
         launches++;
     }
     void launch_tail() {
         const size_t ev = begin_event(2, 0);
-        tail_kernel<<<1, TAIL_THREADS, sizeof(TailSmem), s>>>(d_state, d_keys, d_buf[0], d_buf[1],
-                                                             reinterpret_cast<uint32_t*>(d_words),
-                                                             reinterpret_cast<const uint32_t*>(d_coll), d_blockpop);
+        tail_kernel<<<1, TAIL_THREADS, sizeof(TailSmem), s>>>(d_state, d_keys, d_buf[0], d_buf[1], a32(), c32(), d_blockpop);
         CK(cudaGetLastError());
         end_event(ev);
         launches++;
     }
+    // ---- bucketed (shared-memory) kernels -----------------------------------------------------------
+    void launch_scatter0(uint64_t begin, uint64_t end, uint32_t count_max) {
+        if (end <= begin) return;
+        const size_t smem = std::min(MAX_DYN_SMEM, scatter_smem_bytes(count_max));
+        const uint64_t tiles = (end - begin + BK_TILE - 1) / BK_TILE;
+        const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (220 * 1024) / (smem + 1024)));
+        const int grid = (int)std::min<uint64_t>(tiles, (uint64_t)info.sm_count * per_sm);
+        scatter0_kernel<<<grid, BK_THREADS, smem, s>>>(d_state, d_keys, begin, end, d_buf[0], d_ibuf[0], d_cursors, (uint32_t)smem);
+        CK(cudaGetLastError());
+        launches++;
+    }
+    void launch_scatter(uint32_t level, uint32_t src_range_max, uint32_t src_count_max, uint32_t dst_count_max) {
+        const size_t smem = std::min(MAX_DYN_SMEM, (size_t)src_range_max / 8 + scatter_smem_bytes(dst_count_max));
+        const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (220 * 1024) / (smem + 1024)));
+        const int grid = (int)std::max<uint32_t>(1, std::min<uint32_t>(src_count_max, (uint32_t)(info.sm_count * per_sm)));
+        scatter_kernel<<<grid, BK_THREADS, smem, s>>>(d_state, level, d_buf[0], d_buf[1], d_ibuf[0], d_ibuf[1], c32(), d_cursors, (uint32_t)smem);
+        CK(cudaGetLastError());
+        launches++;
+    }
+    void launch_bucket_mark(uint32_t level, uint32_t range_max, uint32_t count_max) {
+        const size_t smem = std::min(MAX_DYN_SMEM, (size_t)range_max / 4);
+        const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (220 * 1024) / (smem + 1024)));
+        const int grid = (int)std::max<uint32_t>(1, std::min<uint32_t>(count_max, (uint32_t)(info.sm_count * per_sm)));
+        bucket_mark_kernel<<<grid, BK_THREADS, smem, s>>>(d_state, level, d_ibuf[0], d_ibuf[1], a32(), c32(), d_blockpop,
+                                                         d_cursors, (uint32_t)smem);
+        CK(cudaGetLastError());
+        launches++;
+    }
+
+    // Everything level `level` might need, in dependency order; each kernel checks the device state and returns
+    // at once when it is not the variant that applies.  level 0's entry step is issued by the caller (chunks).
+    void launch_level(uint32_t level, const LevelPlan* prev, const LevelPlan& cur) {
+        const bool prev_maybe_b = level >= 1 && prev->maybe_bucket, prev_surely_b = level >= 1 && prev->surely_bucket;
+        if (level >= 1) {
+            const size_t e0 = begin_event(0, level);
+            if (prev_maybe_b) launch_scatter(level, prev->range_max, prev->count_max, cur.maybe_bucket ? cur.count_max : 1);
+            if (!cur.surely_bucket && prev_maybe_b) launch_mark_list(level, 0, 0, cur.k_up);
+            if (!prev_surely_b) launch_pass(level, prev->k_up);
+            end_event(e0);
+        }
+        const size_t e1 = begin_event(1, level);
+        if (cur.maybe_bucket) launch_bucket_mark(level, cur.range_max, cur.count_max);
+        if (!cur.surely_bucket) launch_finalize(level, cur.k_up);
+        end_event(e1);
+    }
+
     void upload_state() { CK(cudaMemcpyAsync(d_state, &hst, sizeof hst, cudaMemcpyHostToDevice, s)); }
     void download_state() {
         CK(cudaMemcpyAsync(&hst, d_state, sizeof hst, cudaMemcpyDeviceToHost, s));
@@ -327,15 +427,10 @@ struct Builder {
 
 }  // namespace
 
-static int build_impl(const uint64_t* keys, uint64_t n, double gamma, int has_seed, uint64_t seed, int device,
-                      int keys_mem, void* stream, bphf_mphf** out) {
-    if (!out) return fail(BPHF_ERR_ARG, "out is null");
-    *out = nullptr;
-    if (n && !keys) return fail(BPHF_ERR_ARG, "keys is null");
-    if (keys_mem != BPHF_MEM_HOST && keys_mem != BPHF_MEM_DEVICE) return fail(BPHF_ERR_ARG, "bad keys_mem");
-    // assert!(gamma > 1.01)  src/lib.rs:236,364  (NaN fails the assertion too)
-    if (!(gamma > 1.01)) return fail(BPHF_ERR_GAMMA, "assertion failed: gamma > 1.01");
+enum { BUILD_RETRY_PLAIN = 1000 };
 
+static int build_once(const uint64_t* keys, uint64_t n, double gamma, int has_seed, uint64_t seed, int device,
+                      int keys_mem, void* stream, bool bucket_enable, uint32_t rebuilds, bphf_mphf** out) {
     const DeviceInfo& info = device_info(device);
     DeviceGuard guard(device);
     cudaStream_t s = stream ? (cudaStream_t)stream : own_stream(device, false);
@@ -346,13 +441,15 @@ static int build_impl(const uint64_t* keys, uint64_t n, double gamma, int has_se
     CK(cudaEventCreate(&b.ev_end));
     CK(cudaEventRecord(b.ev_begin, s));
 
-    const Plan plan = make_plan(n, gamma);
+    const uint64_t min_keys = g_bucket_min_keys;
+    const Plan plan = make_plan(n, gamma, b.slots(), bucket_enable, min_keys);
     b.maybe_big = plan.maybe_big;
 
     CK(cudaMallocAsync((void**)&b.d_state, sizeof(BuildState), s));
     b.alloc_arena(plan.words_cap);
     for (int i = 0; i < 2; i++) {
         if (plan.list_cap[i]) CK(cudaMallocAsync((void**)&b.d_buf[i], plan.list_cap[i] * 8, s));
+        if (plan.list_cap[i] && bucket_enable) CK(cudaMallocAsync((void**)&b.d_ibuf[i], plan.list_cap[i] * 4, s));
     }
 
     BuildState& st = b.hst;
@@ -363,11 +460,19 @@ static int build_impl(const uint64_t* keys, uint64_t n, double gamma, int has_se
     st.list_cap[1] = plan.list_cap[1];
     st.seed0 = has_seed ? seed : 0;  // starting_seed.unwrap_or(0)
     st.gamma = gamma;
-    if (!try_make_level(&st, 0, n)) return fail(BPHF_ERR_INTERNAL, "level 0 does not fit the planned arena");
+    st.bucket_enable = bucket_enable ? 1 : 0;
+    st.bucket_slots = b.slots();
+    st.bucket_min_keys = min_keys;
+    if (!try_make_level(&st, 0, n)) return fail(BPHF_ERR_INTERNAL, "level 0 does not fit the planned buffers");
     b.upload_state();
+    const bool level0_bucketed = st.lv[0].b_range != 0;
+    const uint32_t count0 = st.lv[0].b_count;
 
-    // ---- level 0: keys (H2D in chunks when they live on the host, marking each chunk as it lands)
-    float h2d_ms = 0.f;
+    // ---- level 0 entry step: keys (H2D in chunks when they live on the host, each chunk is consumed as it lands)
+    auto level0_entry = [&](uint64_t lo, uint64_t hi) {
+        if (level0_bucketed) b.launch_scatter0(lo, hi, count0);
+        else b.launch_mark_list(0, lo, hi, 0);
+    };
     if (keys_mem == BPHF_MEM_HOST && n) {
         CK(cudaMallocAsync((void**)&b.d_keys_owned, n * 8, s));
         b.d_keys = b.d_keys_owned;
@@ -386,7 +491,7 @@ static int build_impl(const uint64_t* keys, uint64_t n, double gamma, int has_se
             CK(cudaEventCreateWithFlags(&evs[c], cudaEventDisableTiming));
             CK(cudaEventRecord(evs[c], cs));
             CK(cudaStreamWaitEvent(s, evs[c], 0));
-            b.launch_pass0(lo, hi);
+            level0_entry(lo, hi);
         }
         b.end_event(pe);
         for (auto e : evs) cudaEventDestroy(e);
@@ -394,22 +499,30 @@ static int build_impl(const uint64_t* keys, uint64_t n, double gamma, int has_se
     } else {
         b.d_keys = keys;
         const size_t pe = b.begin_event(0, 0);
-        b.launch_pass0(0, n);
+        level0_entry(0, n);
         b.end_event(pe);
     }
-    b.launch_finalize(0, n);
 
-    // ---- levels 1.. : everything the plan expects, then the tail, without a host round trip
-    uint32_t next_level = 1;
-    for (; next_level < plan.k_up.size(); next_level++) {
-        b.launch_pass(next_level, plan.k_up[next_level - 1]);
-        b.launch_finalize(next_level, plan.k_up[next_level]);
-    }
-    // one more pass+finalize pair in case the upper-biased plan was one level short, then the tail
+    // ---- all planned levels, then the tail, without a host round trip
+    LevelPlan lp0;
+    lp0.k_up = lp0.k_lo = n;
+    lp0.maybe_bucket = lp0.surely_bucket = level0_bucketed;
+    lp0.range_max = st.lv[0].b_range;
+    lp0.count_max = level0_bucketed ? count0 : 1;
+    std::vector<LevelPlan> lps = plan.lv;
+    if (lps.empty()) lps.push_back(lp0);
+    else lps[0] = lp0;
+    b.launch_level(0, nullptr, lps[0]);
+    for (uint32_t l = 1; l < lps.size(); l++) b.launch_level(l, &lps[l - 1], lps[l]);
+    // the first tail-owned level right after a bucketed one gets its keys from the scatter step as a plain list
+    if (lps.back().maybe_bucket)
+        b.launch_scatter((uint32_t)lps.size(), lps.back().range_max, lps.back().count_max, 1);
+
     for (;;) {
         b.launch_tail();
         b.download_state();
         if (st.status == ST_DONE) break;
+        if (st.status == ST_BUCKET_OVERFLOW) return BUILD_RETRY_PLAIN;
         if (st.status == ST_ERR_MAX_ITERS) {
             char msg[128];
             snprintf(msg, sizeof msg, "counldn't find unique hashes (ran out of key space, %llu keys left)",
@@ -437,14 +550,29 @@ static int build_impl(const uint64_t* keys, uint64_t n, double gamma, int has_se
         } else if (st.status != ST_RUNNING) {
             return fail(BPHF_ERR_INTERNAL, "unknown build status");
         }
-        // enqueue a few more levels from where the device stopped (k only shrinks from here)
-        uint64_t k_up = st.lv[level].k_in;
-        const uint64_t k_prev = st.lv[level - 1].k_in;
-        b.launch_pass(level, k_prev);
-        b.launch_finalize(level, k_up);
+        // enqueue a few more levels from where the device stopped (k only shrinks from here); both kernel
+        // families are enqueued because the modes of the coming levels are decided on the device
+        const bool prev_b = st.lv[level - 1].b_range != 0, cur_b = st.lv[level].b_range != 0;
+        LevelPlan pv, cu;
+        pv.k_up = pv.k_lo = st.lv[level - 1].k_in;
+        pv.maybe_bucket = pv.surely_bucket = prev_b;
+        pv.range_max = prev_b ? st.lv[level - 1].b_range : 0;
+        pv.count_max = prev_b ? st.lv[level - 1].b_count : 1;
+        cu.k_up = cu.k_lo = st.lv[level].k_in;
+        cu.maybe_bucket = cu.surely_bucket = cur_b;
+        cu.range_max = cur_b ? st.lv[level].b_range : 0;
+        cu.count_max = cur_b ? st.lv[level].b_count : 1;
+        b.launch_level(level, &pv, cu);
         for (uint32_t l = level + 1; l < level + 4 && l <= BPHF_MAX_LEVELS; l++) {
-            b.launch_pass(l, k_up);
-            b.launch_finalize(l, k_up);
+            LevelPlan nx;
+            nx.k_up = cu.k_up;
+            nx.k_lo = 0;
+            nx.maybe_bucket = cu.maybe_bucket;
+            nx.surely_bucket = false;
+            nx.range_max = BUCKET_R_MAX;
+            nx.count_max = std::min<uint32_t>(BUCKET_MAX_COUNT, cu.count_max + b.slots());
+            b.launch_level(l, &cu, nx);
+            cu = nx;
         }
     }
 
@@ -500,9 +628,31 @@ static int build_impl(const uint64_t* keys, uint64_t n, double gamma, int has_se
         else if (e.kind == 2) bs.tail_ms += ms;
         else if (e.kind == 3) bs.ranks_ms += ms;
     }
-    bs.h2d_ms = h2d_ms;
+    bs.h2d_ms = 0.f;
+    uint32_t nb = 0;
+    for (uint32_t l = 0; l < st.n_levels; l++) nb += st.lv[l].b_range != 0;
+    bs.bucketed_levels = nb;
+    bs.rebuilds = rebuilds;
     *out = m.release();
     return BPHF_OK;
+}
+
+static int build_impl(const uint64_t* keys, uint64_t n, double gamma, int has_seed, uint64_t seed, int device,
+                      int keys_mem, void* stream, bphf_mphf** out) {
+    if (!out) return fail(BPHF_ERR_ARG, "out is null");
+    *out = nullptr;
+    if (n && !keys) return fail(BPHF_ERR_ARG, "keys is null");
+    if (keys_mem != BPHF_MEM_HOST && keys_mem != BPHF_MEM_DEVICE) return fail(BPHF_ERR_ARG, "bad keys_mem");
+    // assert!(gamma > 1.01)  src/lib.rs:236,364  (NaN fails the assertion too)
+    if (!(gamma > 1.01)) return fail(BPHF_ERR_GAMMA, "assertion failed: gamma > 1.01");
+    int rc = build_once(keys, n, gamma, has_seed, seed, device, keys_mem, stream, g_build_mode == 0, 0, out);
+    if (rc == BUILD_RETRY_PLAIN) {
+        // a bucket region overflowed (heavily duplicated or otherwise non-random input): the plain L2-atomic
+        // kernels have no such limit.  Still the GPU path -- there is no CPU fallback anywhere.
+        rc = build_once(keys, n, gamma, has_seed, seed, device, keys_mem, stream, false, 1, out);
+        if (rc == BUILD_RETRY_PLAIN) return fail(BPHF_ERR_INTERNAL, "bucket overflow reported by an unbucketed build");
+    }
+    return rc;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -560,6 +710,12 @@ BPHF_API int bphf_device_count(int* count) {
     CK(cudaGetDeviceCount(count));
     return BPHF_OK;
     API_END
+}
+
+BPHF_API int bphf_set_build_mode(int mode, uint64_t bucket_min_keys) {
+    g_build_mode = mode == 1 ? 1 : 0;
+    g_bucket_min_keys = bucket_min_keys ? bucket_min_keys : (1ull << 20);
+    return BPHF_OK;
 }
 
 BPHF_API int bphf_set_profile(int level) {

@@ -39,9 +39,15 @@ __device__ __forceinline__ uint64_t ld_stream_u64(const uint64_t* p) {
 // buffer must grow first.
 __host__ __device__ inline bool try_make_level(BuildState* st, uint32_t level, uint64_t k) {
     make_level(st, level, k);
-    const LevelDesc& d = st->lv[level];
+    LevelDesc& d = st->lv[level];
     const bool tail_ok = (k <= TAIL_MAX_KEYS) && (d.bits <= TAIL_MAX_BITS);
     if (tail_ok) {
+        // after a bucketed level the scatter kernel hands the tail its keys as a plain list in buf[level & 1]
+        if (level >= 1 && st->lv[level - 1].b_range != 0 && k > st->list_cap[level & 1]) {
+            st->status = ST_NEED_LIST;
+            st->need = k;
+            return false;
+        }
         if (st->tail_level == NO_TAIL) st->tail_level = level;
         // arena space for tail levels comes out of the TAIL_RESERVE_WORDS slack; lists live in smem
         st->words_used = d.word_off + round_up8(d.n_words);
@@ -53,7 +59,21 @@ __host__ __device__ inline bool try_make_level(BuildState* st, uint32_t level, u
         st->need = need_words;
         return false;
     }
-    if (level >= 1 && k > st->list_cap[level & 1]) {
+    // bucketed (shared-memory) construction for a prefix of large levels, plain L2-atomic kernels after that
+    BucketGeom g;
+    const bool may_bucket = st->bucket_enable && (level == 0 || st->lv[level - 1].b_range != 0);
+    if (may_bucket && bucket_geometry(d.bits, k, st->bucket_slots, st->bucket_min_keys, &g)) {
+        const uint64_t need_keys = (uint64_t)g.count * g.cap;
+        if (need_keys > st->list_cap[level & 1]) {
+            st->status = ST_NEED_LIST;
+            st->need = need_keys;
+            return false;
+        }
+        d.b_div = g.div;
+        d.b_range = g.range;
+        d.b_count = g.count;
+        d.b_cap = g.cap;
+    } else if (level >= 1 && k > st->list_cap[level & 1]) {
         st->status = ST_NEED_LIST;
         st->need = k;
         return false;
@@ -99,16 +119,26 @@ __device__ __forceinline__ uint64_t level_index(uint64_t sp0, uint64_t key, uint
 }
 
 // ---------------------------------------------------------------------------------------------
-// pass_kernel<FIRST = true>: level 0, mark only, over user_keys[key_begin, key_end)
+// mark_list_kernel: find_collisions only, over a contiguous key list.  level 0: the input keys
+// [key_begin, key_end); level >= 1 (first plain level after the bucketed prefix): the list in buf[level & 1]
 // ---------------------------------------------------------------------------------------------
 template <bool MAYBE_BIG>
 __global__ void __launch_bounds__(PASS_THREADS)
-    pass0_kernel(const BuildState* __restrict__ st, const uint64_t* __restrict__ keys, uint64_t key_begin,
-                 uint64_t key_end, uint32_t* __restrict__ a32, uint32_t* __restrict__ c32) {
-    if (st->status != ST_RUNNING || st->n_levels != 0 || st->tail_level == 0) return;
-    const uint64_t bits = st->lv[0].bits;
-    const uint64_t sp0 = st->lv[0].sp0;
-    const uint64_t off32 = st->lv[0].word_off * 2;
+    mark_list_kernel(const BuildState* __restrict__ st, uint32_t level, const uint64_t* __restrict__ user_keys,
+                     uint64_t key_begin, uint64_t key_end, const uint64_t* __restrict__ buf0,
+                     const uint64_t* __restrict__ buf1, uint32_t* __restrict__ a32, uint32_t* __restrict__ c32) {
+    if (st->status != ST_RUNNING || st->n_levels != level || level >= st->tail_level) return;
+    if (st->lv[level].b_range != 0) return;                         // bucketed level: bucket_mark_kernel
+    if (level >= 1 && st->lv[level - 1].b_range == 0) return;       // plain predecessor: pass_kernel marks
+    const uint64_t* __restrict__ keys = user_keys;
+    if (level >= 1) {
+        keys = (level & 1) ? buf1 : buf0;
+        key_begin = 0;
+        key_end = st->lv[level].k_in;
+    }
+    const uint64_t bits = st->lv[level].bits;
+    const uint64_t sp0 = st->lv[level].sp0;
+    const uint64_t off32 = st->lv[level].word_off * 2;
     const bool big = MAYBE_BIG && (bits >> 32) != 0;
     const uint64_t n = key_end - key_begin;
     const uint64_t n_tiles = (n + PASS_TILE - 1) / PASS_TILE;
@@ -157,6 +187,7 @@ __global__ void __launch_bounds__(PASS_THREADS)
                 uint64_t* __restrict__ buf0, uint64_t* __restrict__ buf1, uint32_t* __restrict__ a32,
                 uint32_t* __restrict__ c32) {
     if (st->status != ST_RUNNING || st->n_levels != level || level >= st->tail_level) return;
+    if (st->lv[level - 1].b_range != 0) return;  // bucketed predecessor: scatter_kernel filtered it already
     __shared__ uint64_t stage[PASS_TILE];
     __shared__ uint32_t warp_tot[PASS_THREADS / 32];
     __shared__ uint64_t sh_base;
@@ -258,6 +289,7 @@ __global__ void __launch_bounds__(FIN_THREADS)
     finalize_kernel(BuildState* __restrict__ st, uint32_t level, uint64_t* __restrict__ words,
                     const uint64_t* __restrict__ coll, uint32_t* __restrict__ blockpop) {
     if (st->status != ST_RUNNING || st->n_levels != level || level >= st->tail_level) return;
+    if (st->lv[level].b_range != 0) return;  // bucketed levels are finalized by bucket_mark_kernel
     __shared__ bool is_last;
     const uint64_t word_off = st->lv[level].word_off;
     const uint64_t n_pairs = round_up8(st->lv[level].n_words) / 2;  // multiple of 4
@@ -305,7 +337,10 @@ __global__ void __launch_bounds__(FIN_THREADS)
         __threadfence();
         const uint64_t uq = atomicAdd((unsigned long long*)&st->uniq_count, 0ULL);
         const uint64_t k_in = st->lv[level].k_in;
-        if (uq > k_in || (level >= 1 && atomicAdd((unsigned long long*)&st->redo_count, 0ULL) != k_in)) {
+        // plain predecessor: pass_kernel appended this level's list through redo_count, which must match k_in
+        // (a bucketed predecessor is checked through the bucket cursors instead)
+        const bool check_list = level >= 1 && st->lv[level - 1].b_range == 0;
+        if (uq > k_in || (check_list && atomicAdd((unsigned long long*)&st->redo_count, 0ULL) != k_in)) {
             st->status = ST_ERR_INTERNAL;
             st->err_info = ((uint64_t)level << 48) | uq;
         } else {
@@ -341,6 +376,11 @@ __global__ void __launch_bounds__(TAIL_THREADS)
     // gather the keys entering `level`
     if (level == 0) {
         for (uint32_t i = tid; i < k; i += TAIL_THREADS) s.keys[0][i] = user_keys[i];
+        if (tid == 0) s.count = k;
+    } else if (st->lv[level - 1].b_range != 0) {
+        // bucketed predecessor: scatter_kernel already wrote this level's (filtered) key list to buf[level & 1]
+        const uint64_t* src = (level & 1) ? buf1 : buf0;
+        for (uint32_t i = tid; i < k; i += TAIL_THREADS) s.keys[0][i] = src[i];
         if (tid == 0) s.count = k;
     } else {
         const LevelDesc* pv = &st->lv[level - 1];

@@ -25,6 +25,14 @@ struct LevelDesc {
     uint64_t k_in;      // keys entering this level (build only)
     uint64_t sp0;       // seed_xor_p0(seed index) used to BUILD this level
     uint64_t sp0_query; // seed_xor_p0(level index): what Mphf::hash uses (src/lib.rs:327)
+    // bucketed construction (build only): the level's bit range is cut into b_count buckets of b_range bits
+    // (multiple of 512); the keys entering the level are stored grouped by bucket, bucket b at
+    // buf[level & 1] + b * b_cap, so one CTA owns a bucket's slice of (a, collide) in shared memory
+    uint64_t b_div;     // ceil(2^32 / b_range): bucket ~ umulhi(idx, b_div), exact or one too high
+    uint32_t b_range;   // 0 = plain level (one contiguous key list, L2-atomic kernels)
+    uint32_t b_count;
+    uint32_t b_cap;     // key capacity of each bucket region
+    uint32_t pad_;
 };
 
 enum BuildStatus : uint32_t {
@@ -34,6 +42,7 @@ enum BuildStatus : uint32_t {
     ST_NEED_WORDS = 3,     // arena too small for the next level: host grows it and resumes
     ST_NEED_LIST = 4,      // redo list buffer too small for the next level: host grows it and resumes
     ST_ERR_INTERNAL = 5,
+    ST_BUCKET_OVERFLOW = 6,  // a bucket region or a kernel's shared memory was too small: host rebuilds unbucketed
 };
 
 // device-resident build state; the level loop runs without host round trips (kernels for all
@@ -52,6 +61,10 @@ struct BuildState {
     double gamma;
     uint64_t need;        // how much ST_NEED_* asks for
     uint64_t err_info;
+    uint64_t bucket_min_keys;  // levels with fewer keys are built by the plain (L2-atomic) kernels
+    uint32_t bucket_slots;     // CTAs that run concurrently (SM count x 2): bucket counts are multiples of it
+    uint32_t bucket_enable;
+    uint64_t bucket_keys_seen; // sum of bucket fills seen by the mark kernel (consistency check)
     LevelDesc lv[BPHF_MAX_LEVELS + 1];
 };
 
@@ -65,6 +78,50 @@ constexpr uint64_t TAIL_RESERVE_WORDS = (uint64_t)(BPHF_MAX_LEVELS + 1) * (TAIL_
 
 __host__ __device__ __forceinline__ uint64_t round_up8(uint64_t w) { return (w + 7) & ~7ULL; }
 
+// ---- bucket geometry --------------------------------------------------------------------------------
+constexpr uint32_t BUCKET_R_MAX = 442368;    // bits per bucket: a + collide = 110,592 B of shared memory -> 2 CTAs / SM
+constexpr uint32_t BUCKET_MAX_COUNT = 4096;  // per-tile histogram / base tables live in shared memory
+constexpr uint32_t MAX_BUCKETS_ALLOC = 4096; // buckets per parity in the cursor array
+// every bucket cursor sits in its own 128-byte line: the per-tile reservations (one atomicAdd per bucket per
+// tile) would otherwise pile onto a handful of L2 slices
+constexpr uint32_t CURSOR_STRIDE = 32;
+
+struct BucketGeom {
+    uint64_t div;
+    uint32_t range, count, cap;
+};
+
+// range = multiple of 512 bits so buckets own whole rank blocks; count ~ multiple of the concurrent CTA slots
+__host__ __device__ inline bool bucket_geometry(uint64_t bits, uint64_t k, uint32_t slots, uint64_t min_keys,
+                                               BucketGeom* g) {
+    if (slots == 0 || k < min_keys || (bits >> 32) != 0) return false;
+    if (bits > (uint64_t)BUCKET_R_MAX * BUCKET_MAX_COUNT) return false;
+    uint64_t per_wave = (uint64_t)slots * BUCKET_R_MAX;
+    uint64_t m = (bits + per_wave - 1) / per_wave;
+    uint64_t target = (uint64_t)slots * m;
+    uint64_t range = (bits + target - 1) / target;
+    range = (range + 511) & ~511ULL;
+    if (range < 512) range = 512;
+    if (range > BUCKET_R_MAX) range = BUCKET_R_MAX;
+    uint64_t count = (bits + range - 1) / range;
+    if (count > BUCKET_MAX_COUNT) return false;
+    // expected fill k * range / bits, + 6 sigma + slack
+    double mean = (double)k * (double)range / (double)bits;
+#ifdef __CUDA_ARCH__
+    double sd = sqrt(mean);
+#else
+    double sd = __builtin_sqrt(mean);
+#endif
+    uint64_t cap = (uint64_t)(mean + 6.0 * sd + 96.0);
+    cap = (cap + 31) & ~31ULL;
+    if (cap > 0xffffffffULL) return false;
+    g->range = (uint32_t)range;
+    g->count = (uint32_t)count;
+    g->cap = (uint32_t)cap;
+    g->div = (0xffffffffULL / range) + 1ULL;
+    return true;
+}
+
 // fill in lv[level] for k keys; returns false when the arena cannot hold it (need -> words required)
 __host__ __device__ inline void make_level(BuildState* st, uint32_t level, uint64_t k) {
     LevelDesc& d = st->lv[level];
@@ -74,6 +131,9 @@ __host__ __device__ inline void make_level(BuildState* st, uint32_t level, uint6
     d.k_in = k;
     d.sp0 = seed_xor_p0(st->seed0 + level);
     d.sp0_query = seed_xor_p0(level);
+    d.b_div = 0;
+    d.b_range = d.b_count = d.b_cap = 0;
+    d.pad_ = 0;
 }
 
 }  // namespace bphf

@@ -271,3 +271,84 @@ def test_baseline_size_100m_properties(pkg, oracle):
     # level sizes follow max(255, floor(gamma * k)) with k = keys left (src/lib.rs:369,384)
     st = m.build_stats()
     assert st["keys_in"][0] == n and [oracle.level_size(1.7, k) for k in st["keys_in"]] == st["bits"]
+
+
+# ---- construction strategies: bucketed shared-memory kernels vs plain L2-atomic kernels -----------------------
+@pytest.fixture
+def small_buckets(pkg):
+    """force the bucketed kernels onto small levels so the unit-test sizes exercise them (and every transition)"""
+    pkg.lib().bphf_set_build_mode(0, 3000)
+    yield
+    pkg.lib().bphf_set_build_mode(0, 0)
+
+
+@pytest.fixture
+def plain_only(pkg):
+    pkg.lib().bphf_set_build_mode(1, 0)
+    yield
+    pkg.lib().bphf_set_build_mode(0, 0)
+
+
+@pytest.mark.parametrize("n", [2999, 3000, 3001, 5000, 9000, 20_000, 65_537, 300_001, 1 << 20, 3_000_000])
+def test_bucketed_build_parity_sizes(pkg, oracle, small_buckets, n):
+    keys = oracle.keygen(n, seed=n + 3, kind=0)
+    m = pkg.Mphf.new_parallel(1.7, keys, None)
+    ref = oracle.OracleMphf.new_parallel(1.7, keys)
+    assert_same_levels(m.levels(), ref.levels())
+    st = m.build_stats()
+    assert st["rebuilds"] == 0
+    assert (st["bucketed_levels"] > 0) == (n > 4096)  # <= 4096 keys: the tail kernel owns every level
+    assert np.array_equal(m.hash_batch(keys), ref.hash_batch(keys, nthreads=0))
+
+
+@pytest.mark.parametrize("gamma", [1.0100001, 1.3, 1.7, 2.0, 5.0, 17.5, 100.0, 1000.0])
+def test_bucketed_build_parity_gammas(pkg, oracle, small_buckets, gamma):
+    # large gamma: the level after a bucketed one is already tail sized (scatter -> plain list -> tail kernel)
+    keys = oracle.keygen(150_000, seed=12, kind=1)
+    m = pkg.Mphf.new_parallel(gamma, keys, None)
+    ref = oracle.OracleMphf.new_parallel(gamma, keys)
+    assert_same_levels(m.levels(), ref.levels())
+    assert m.build_stats()["bucketed_levels"] > 0
+    assert np.array_equal(m.hash_batch(keys), ref.hash_batch(keys, nthreads=0))
+
+
+@pytest.mark.parametrize("seed", [5, 31, 2**64 - 3])
+def test_bucketed_build_parity_seeds(pkg, oracle, small_buckets, seed):
+    keys = oracle.keygen(100_000, seed=1, kind=0)
+    m = pkg.Mphf.new_parallel(1.7, keys, seed)
+    assert_same_levels(m.levels(), oracle.OracleMphf.new_parallel(1.7, keys, seed).levels())
+
+
+def test_bucketed_host_keys_in_chunks(pkg, oracle):
+    # 40 M host keys = 3 H2D chunks, each scattered into the level-0 buckets as it lands
+    n = 40_000_000
+    keys = oracle.keygen(n, seed=2, kind=0)
+    m = pkg.Mphf.new_parallel(1.7, keys, None)
+    ref = oracle.OracleMphf.new_parallel(1.7, keys)
+    assert m.build_stats()["bucketed_levels"] >= 4
+    assert_same_levels(m.levels(), ref.levels())
+
+
+def test_plain_and_bucketed_strategies_agree(pkg, oracle, plain_only):
+    keys = oracle.keygen(3_000_000, seed=5, kind=0)
+    a = pkg.Mphf.new_parallel(1.7, keys, None)
+    assert a.build_stats()["bucketed_levels"] == 0
+    pkg.lib().bphf_set_build_mode(0, 0)
+    b = pkg.Mphf.new_parallel(1.7, keys, None)
+    assert b.build_stats()["bucketed_levels"] > 0
+    assert oracle.fingerprint(a.levels()) == oracle.fingerprint(b.levels())
+    assert_same_levels(a.levels(), oracle.OracleMphf.new_parallel(1.7, keys).levels())
+
+
+def test_bucket_overflow_falls_back_to_plain_kernels(pkg, small_buckets):
+    # every key 40 times: all copies of a key land in one bucket, the region overflows, the build is redone
+    # with the L2-atomic kernels and reports the reference's MAX_ITERS failure
+    base = np.arange(5_000, dtype=np.uint64) * 3 + 5
+    keys = np.tile(base, 40)
+    with pytest.raises(pkg.MphfPanic) as e:
+        pkg.Mphf.new_parallel(1.7, keys, None)
+    assert e.value.code == -3
+    # a skewed but valid case: distinct keys plus one key repeated would be invalid input, so instead check that
+    # a valid build right after the failed one is unaffected
+    ok = pkg.Mphf.new_parallel(1.7, base, None)
+    assert ok.total_dims()[2] == len(base)

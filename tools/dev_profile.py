@@ -12,8 +12,11 @@ import torch
 n = int(float(sys.argv[1])) if len(sys.argv) > 1 else 100_000_000
 gamma = float(sys.argv[2]) if len(sys.argv) > 2 else 1.7
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+mode = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+min_keys = int(float(sys.argv[5])) if len(sys.argv) > 5 else 0
 pkg = ge.load_package()
 L = pkg.lib()
+L.bphf_set_build_mode(mode, min_keys)
 keys = torch.empty(n, dtype=torch.int64, device="cuda")
 L.bphf_keygen_u64(C.c_void_p(keys.data_ptr()), 0, n, 1, 0, 0, None)
 torch.cuda.synchronize()
@@ -24,8 +27,8 @@ for prof in (0, 2):
         m = pkg.Mphf.new_parallel(gamma, keys, None)
         dt = time.perf_counter() - t0
         st = m.build_stats()
-        print("profile", prof, "rep", r, "wall_ms %.3f total_ms %.3f launches %d syncs %d levels %d tail_level %d" % (
-            dt * 1e3, st["total_ms"], st["kernel_launches"], st["host_syncs"], st["n_levels"], st["tail_level"]))
+        print("profile", prof, "rep", r, "wall_ms %.3f total_ms %.3f launches %d syncs %d levels %d tail_level %d bucketed %d rebuilds %d" % (
+            dt * 1e3, st["total_ms"], st["kernel_launches"], st["host_syncs"], st["n_levels"], st["tail_level"], st["bucketed_levels"], st["rebuilds"]))
 st = m.build_stats()
 print("pass_ms", ["%.3f" % x for x in st["pass_ms"]])
 print("fin_ms ", ["%.3f" % x for x in st["fin_ms"]])
