@@ -121,10 +121,11 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self._max, "reasons": sorted(seen), "samples": len(sm)}
 
 
-def algorithmic_bytes(stats):
+def algorithmic_bytes(stats, world=1):
     """B_l = 16k + 8c + 41W per level (key read in mark and in filter, redo write, zeroing
-    of a and collide, finalize read a/read collide/write a, ranks).  Returns total and per-kernel splits."""
-    ks, bits = stats["keys_in"], stats["bits"]
+    of a and collide, finalize read a/read collide/write a, ranks).  Returns total and per-kernel splits, PER GPU:
+    a shard of a sharded build streams 1/world of every level's keys but full-width bit vectors."""
+    ks, bits = [k // world for k in stats["keys_in"]], stats["bits"]
     total = 0
     per_pass = []
     for l, (k, b) in enumerate(zip(ks, bits)):
@@ -218,7 +219,19 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # N > 1: ONE MPHF over all world * n keys, keys sharded across the GPUs (they never move); per level the
+    # shards' (a, collide) pairs are merged by the OR-collide peer-memory kernel.  Every rank ends
+    # with a complete replica.  N == 1: the plain single-GPU build.
+    comm = None
+    n_global = world * n
+    if world > 1:
+        import importlib
+        sharded = importlib.import_module(pkg.__name__ + ".sharded")
+        comm = sharded.ShardComm.from_process_group(local_rank, n_global, GAMMA)
+
     def build():
+        if comm is not None:
+            return comm.build(GAMMA, keys, n_global)
         return pkg.Mphf.new_parallel(GAMMA, keys, None, stream=stream)
 
     # ---- warm-up ---------------------------------------------------------------------------------------------
@@ -272,9 +285,26 @@ def main():
         dist.all_reduce(tq, op=dist.ReduceOp.MAX)
     q_ms = float(tq.item()) / args.steps
     lookup_val = world * n / (q_ms * 1e-3) / 1e6
-    bad = C.c_uint64(1)
-    assert L.bphf_check_permutation(C.c_void_p(out.data_ptr()), n, local_rank, C.byref(bad)) == 0
-    permutation_ok = bad.value == 0
+    if world == 1:
+        bad = C.c_uint64(1)
+        assert L.bphf_check_permutation(C.c_void_p(out.data_ptr()), n, local_rank, C.byref(bad)) == 0
+        permutation_ok = bad.value == 0
+    else:
+        # the shards' outputs together must be exactly 0..n_global-1: compare the order-free checksum (sum of
+        # splitmix64 of every value, mod 2^64) of all outputs with that of the range itself
+        def csum(t):
+            sm, xr = C.c_uint64(), C.c_uint64()
+            assert L.bphf_checksum_u64(C.c_void_p(t.data_ptr()), t.numel(), local_rank, C.byref(sm), C.byref(xr)) == 0
+            return sm.value
+        want = torch.arange(rank * n, (rank + 1) * n, dtype=torch.int64, device=dev)
+        both = torch.tensor([csum(out) - (1 << 64) if csum(out) >= (1 << 63) else csum(out),
+                             csum(want) - (1 << 64) if csum(want) >= (1 << 63) else csum(want)], dtype=torch.int64, device=dev)
+        dist.all_reduce(both)
+        in_range = torch.tensor([int(bool((out.view(torch.int64) >= 0).all() and (out.view(torch.int64) < n_global).all()))],
+                                dtype=torch.int64, device=dev)
+        dist.all_reduce(in_range, op=dist.ReduceOp.MIN)
+        permutation_ok = bool(both[0].item() == both[1].item()) and bool(in_range.item() == 1)
+        del want
 
     # ---- end to end through the C ABI with host buffers --------------------------------------------------------
     e2e = None
@@ -287,7 +317,7 @@ def main():
         hk_np = hk.numpy().view(np.uint64)
 
         def e2e_step():
-            mm = pkg.Mphf.new_parallel(GAMMA, hk_np, None, device=local_rank)
+            mm = comm.build(GAMMA, hk_np, n_global) if comm is not None else pkg.Mphf.new_parallel(GAMMA, hk_np, None, device=local_rank)
             assert L.bphf_export_all(mm._h, C.c_void_p(words.data_ptr()), C.c_void_p(ranks.data_ptr()), 0) == 0
             return mm
 
@@ -308,7 +338,7 @@ def main():
 
     # ---- roofline of the dominant kernel -----------------------------------------------------------------------
     peak, peak_src = measured_peaks()
-    total_bytes, per_pass = algorithmic_bytes(stats)
+    total_bytes, per_pass = algorithmic_bytes(stats, world)
     dom = 0 if pass_ms[0] >= pass_ms[1] else 1
     k_ms = pass_ms[dom] / args.steps
     achieved = per_pass[dom] / (k_ms * 1e-3) / 1e9 if k_ms > 0 else None
@@ -350,13 +380,19 @@ def main():
                        if n == 100_000_000 else "Mphf::new_parallel gamma=1.7 on %d keys per GPU" % n,
                        "gamma": GAMMA, "n_keys_per_gpu": n, "levels": stats["n_levels"], "tail_level": stats["tail_level"],
                        "l2": "inputs (%.0f MB of keys per step) are larger than the 126 MB L2" % (8 * n / 1e6),
-                       "multi_gpu": "independent replicas per GPU" if world > 1 else "single GPU"},
+                       "multi_gpu": ("ONE MPHF over %d keys sharded across %d GPUs; per-level OR-collide merge over NVLink peer memory; "
+                                     "every GPU ends with a replica" % (n_global, world)) if world > 1 else "single GPU"},
             "lookup": {"value": lookup_val, "unit": UNIT, "ms_per_pass": q_ms, "permutation_ok": permutation_ok},
             "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,
             "gpu_launches": launches + args.steps, "wall_ms_per_step": wall / args.steps * 1e3,
             "clocks": clocks.summary(),
         }
         print(json.dumps(line), flush=True)
+    if comm is not None:
+        del m
+        torch.cuda.synchronize()
+        dist.barrier()
+        comm.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -84,6 +84,34 @@ BPHF_API int bphf_wy_swap_8byte_tail(void);
 BPHF_API int bphf_build_u64(const uint64_t *keys, uint64_t n, double gamma, int has_seed, uint64_t seed,
                             int device, int keys_mem, void *stream, bphf_mphf **out);
 
+/* ---- sharded build over several GPUs --------------------------------------
+ * The reference's new_parallel shares one (a, collide) pair per level between all rayon workers
+ * (src/lib.rs:373-377).  Here the key set is split into `world` shards, one per GPU (one process or
+ * thread each); every shard marks its keys into its own full-width pair and the pairs are merged per
+ * level with the OR-collide monoid (a,c)+(a',c') = (a|a', c|c'|(a&a')) by a peer-memory (NVLink)
+ * reduce-scatter / all-gather kernel.  Every shard ends up with the identical, complete structure
+ * (a replica for lookups), bit-exact with an unsharded build of the union of the shards.
+ *
+ * Life cycle: every shard calls bphf_comm_create (allocates its peer-visible arena), publishes its
+ * 64-byte handle (bphf_comm_ipc_handle; any host transport, e.g. torch.distributed all_gather),
+ * connects with the handles of all shards in rank order (bphf_comm_connect_ipc), then all shards
+ * call bphf_build_sharded_u64 collectively (same n_global, gamma, seed; same number of calls).
+ * Shards living in ONE process (threads, one or several devices) connect with
+ * bphf_comm_connect_local instead.  world <= 8.  After an error status the comm must be destroyed. */
+typedef struct bphf_comm bphf_comm;
+#define BPHF_IPC_HANDLE_BYTES 64
+/* the arena is sized for builds of up to max_keys_global keys (all shards together) at gamma <= max_gamma */
+BPHF_API int bphf_comm_create(int device, int rank, int world, uint64_t max_keys_global, double max_gamma,
+                              bphf_comm **out);
+BPHF_API int bphf_comm_ipc_handle(const bphf_comm *c, void *handle_out /* BPHF_IPC_HANDLE_BYTES */);
+BPHF_API int bphf_comm_connect_ipc(bphf_comm *c, const void *handles /* world * BPHF_IPC_HANDLE_BYTES */);
+BPHF_API int bphf_comm_connect_local(bphf_comm *c, bphf_comm *const *all /* world comms, rank order */);
+BPHF_API void bphf_comm_destroy(bphf_comm *c);
+/* keys: this shard's n_local keys (host or device memory on the comm's device); n_global = sum of all shards'
+ * n_local.  Blocking; collective over the comm. */
+BPHF_API int bphf_build_sharded_u64(bphf_comm *c, const uint64_t *keys, uint64_t n_local, uint64_t n_global,
+                                    double gamma, int has_seed, uint64_t seed, int keys_mem, bphf_mphf **out);
+
 /* ---- data model: (BitVector{bits, vector}, ranks) per level ---------------------------- */
 BPHF_API int bphf_num_levels(const bphf_mphf *m, uint32_t *n_levels);
 BPHF_API int bphf_level_dims(const bphf_mphf *m, uint32_t level, uint64_t *bits, uint64_t *n_words,
@@ -132,6 +160,7 @@ typedef struct bphf_build_stats {
     float h2d_ms;                          /* reserved                                              */
     uint32_t bucketed_levels;              /* levels built by the shared-memory (bucketed) kernels  */
     uint32_t rebuilds;                     /* 1 when a bucket overflow forced an unbucketed rebuild */
+    float merge_ms[BPHF_MAX_LEVELS + 1];   /* sharded build: barrier + OR-collide merge + barrier (profile 2) */
 } bphf_build_stats;
 BPHF_API int bphf_get_build_stats(const bphf_mphf *m, bphf_build_stats *out);
 /* 0: no events; 1: CUDA events around the kernels of levels 0 and 1; 2: around every kernel.

@@ -504,6 +504,34 @@ BO_API void bo_map_get_batch(const bo_mphf *m, const uint64_t *map_keys, const u
 }
 
 /* ------------------------------------------------------------------------------------------
+ * Level-granular entry points on plain word arrays, used by the tests that model the sharded
+ * (multi-GPU) schedule of SURVEY.md 8e on the CPU: every shard marks into its own (a, collide),
+ * the pairs are folded with the OR-collide monoid, each shard filters its own keys.
+ * ---------------------------------------------------------------------------------------- */
+/* Context::find_collisions_sync (src/lib.rs:436-441) for n keys into caller-owned word arrays */
+BO_API void bo_mark_level(const uint64_t *keys, uint64_t n, uint64_t seed_index, uint64_t bits, uint64_t *a,
+                          uint64_t *collide) {
+    bo_ctx cx;
+    cx.size = bits;
+    cx.seed = seed_index;
+    cx.a.bits = cx.collide.bits = bits;
+    cx.a.nwords = cx.collide.nwords = (bits + 63) / 64;
+    cx.a.v = a;
+    cx.collide.v = collide;
+    for (uint64_t i = 0; i < n; i++) find_collisions_sync(&cx, keys[i]);
+}
+/* the redo half of Context::filter (src/lib.rs:443-452): keys whose slot is set in `collide`, in order */
+BO_API uint64_t bo_filter_level(const uint64_t *keys, uint64_t n, uint64_t seed_index, uint64_t bits,
+                                const uint64_t *collide, uint64_t *redo_out) {
+    uint64_t m = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        uint64_t idx = bo_hashmod(seed_index, keys[i], bits);
+        if ((collide[idx >> 6] >> (idx & 63)) & 1ULL) redo_out[m++] = keys[i];
+    }
+    return m;
+}
+
+/* ------------------------------------------------------------------------------------------
  * Synthetic key generators: bijections of the counter, so keys are
  * distinct by construction.  The CUDA library has the same generators (bphf_keygen_u64).
  * ---------------------------------------------------------------------------------------- */

@@ -67,6 +67,10 @@ def lib():
     L.bo_create_map.argtypes = [vp, vp, vp, u64]
     L.bo_map_get_batch.restype = None
     L.bo_map_get_batch.argtypes = [vp, vp, vp, u64, vp, u64, vp, vp]
+    L.bo_mark_level.restype = None
+    L.bo_mark_level.argtypes = [vp, u64, u64, u64, vp, vp]
+    L.bo_filter_level.restype = u64
+    L.bo_filter_level.argtypes = [vp, u64, u64, u64, vp, vp]
     L.bo_keygen.restype = None
     L.bo_keygen.argtypes = [vp, u64, u64, u64, i32]
     L.bo_free.restype = None
@@ -280,3 +284,34 @@ def level_size(gamma, k):
 
 def max_threads():
     return int(lib().bo_max_threads())
+
+
+def mark_level(keys, seed_index, bits, a, collide):
+    """find_collisions of `keys` into the caller's word arrays (numpy uint64, modified in place)"""
+    k = _as_u64(keys)
+    lib().bo_mark_level(_ptr(k), k.size, int(seed_index), int(bits), _ptr(a), _ptr(collide))
+
+
+def filter_level(keys, seed_index, bits, collide):
+    """keys whose slot collided (the redo list of Context::filter), order preserved"""
+    k = _as_u64(keys)
+    out = np.empty(k.size, dtype=np.uint64)
+    m = lib().bo_filter_level(_ptr(k), k.size, int(seed_index), int(bits), _ptr(collide), _ptr(out))
+    return out[:m].copy()
+
+
+def or_collide(a, c, a2, c2):
+    """the merge monoid of SURVEY.md 8e: (a,c) (+) (a',c') = (a|a', c|c'|(a&a'))"""
+    return a | a2, c | c2 | (a & a2)
+
+
+def ranks_from_levels(level_words):
+    """Mphf::compute_ranks (src/lib.rs:277-297): one running popcount over all levels, one entry per 8 words"""
+    out, pop = [], 0
+    for w in level_words:
+        pc = np.array([bin(int(x)).count("1") for x in w], dtype=np.uint64) if len(w) < 4096 else \
+            np.unpackbits(w.view(np.uint8)).reshape(len(w), 64).sum(axis=1).astype(np.uint64)
+        cum = np.concatenate(([0], np.cumsum(pc)))[:-1] + pop
+        out.append(cum[::8].astype(np.uint64))
+        pop += int(pc.sum())
+    return out

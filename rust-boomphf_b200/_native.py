@@ -32,6 +32,8 @@ SYMBOLS = [
     "bphf_total_dims", "bphf_from_levels", "bphf_free", "bphf_hash_batch_u64", "bphf_map_permute_u64",
     "bphf_map_get_batch_u64", "bphf_get_build_stats", "bphf_set_profile", "bphf_set_build_mode", "bphf_keygen_u64",
     "bphf_check_permutation", "bphf_checksum_u64", "bphf_host_alloc", "bphf_host_free",
+    "bphf_comm_create", "bphf_comm_ipc_handle", "bphf_comm_connect_ipc", "bphf_comm_connect_local",
+    "bphf_comm_destroy", "bphf_build_sharded_u64",
 ]
 
 
@@ -51,6 +53,7 @@ class BuildStats(C.Structure):
         ("h2d_ms", C.c_float),
         ("bucketed_levels", C.c_uint32),
         ("rebuilds", C.c_uint32),
+        ("merge_ms", C.c_float * (MAX_LEVELS + 1)),
     ]
 
 
@@ -129,6 +132,18 @@ def lib():
     L.bphf_host_alloc.argtypes = [C.c_size_t]
     L.bphf_host_free.restype = None
     L.bphf_host_free.argtypes = [vp]
+    L.bphf_comm_create.restype = i32
+    L.bphf_comm_create.argtypes = [i32, i32, i32, u64, dbl, C.POINTER(vp)]
+    L.bphf_comm_ipc_handle.restype = i32
+    L.bphf_comm_ipc_handle.argtypes = [vp, vp]
+    L.bphf_comm_connect_ipc.restype = i32
+    L.bphf_comm_connect_ipc.argtypes = [vp, vp]
+    L.bphf_comm_connect_local.restype = i32
+    L.bphf_comm_connect_local.argtypes = [vp, C.POINTER(vp)]
+    L.bphf_comm_destroy.restype = None
+    L.bphf_comm_destroy.argtypes = [vp]
+    L.bphf_build_sharded_u64.restype = i32
+    L.bphf_build_sharded_u64.argtypes = [vp, vp, u64, u64, dbl, i32, u64, i32, C.POINTER(vp)]
     _lib = L
     return L
 

@@ -15,6 +15,7 @@
 #include "build_kernels.cuh"
 #include "bucket_kernels.cuh"
 #include "query_kernels.cuh"
+#include "shard_kernels.cuh"
 
 using namespace bphf;
 
@@ -88,6 +89,20 @@ static const DeviceInfo& device_info(int dev) {
         CK(cudaFuncSetAttribute(scatter0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CK(cudaFuncSetAttribute(scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CK(cudaFuncSetAttribute(bucket_mark_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        // CUDA loads kernels lazily, and loading one may have to wait for running work: a shard spinning at a
+        // barrier would then block the first launch of the very kernel it waits for.  Load everything now.
+        {
+            cudaFuncAttributes fa;
+            const void* all_kernels[] = {
+                (const void*)mark_list_kernel<false>, (const void*)mark_list_kernel<true>, (const void*)pass_kernel<false>,
+                (const void*)pass_kernel<true>, (const void*)finalize_kernel, (const void*)tail_kernel,
+                (const void*)scan_sums_kernel, (const void*)scan_top_kernel, (const void*)scan_apply_kernel,
+                (const void*)scatter0_kernel, (const void*)scatter_kernel, (const void*)bucket_mark_kernel,
+                (const void*)query_kernel, (const void*)map_permute_kernel, (const void*)map_get_kernel,
+                (const void*)keygen_kernel, (const void*)check_perm_kernel, (const void*)checksum_kernel,
+                (const void*)shard_barrier_kernel, (const void*)or_collide_merge_kernel, (const void*)tail_gather_kernel};
+            for (const void* k : all_kernels) CK(cudaFuncGetAttributes(&fa, k));
+        }
         if (prev != dev) CK(cudaSetDevice(prev));
         d.init = true;
     }
@@ -98,8 +113,28 @@ static const DeviceInfo& device_info(int dev) {
 struct ThreadStreams {
     cudaStream_t main[MAX_DEVICES] = {};
     cudaStream_t copy[MAX_DEVICES] = {};
+    ~ThreadStreams() {
+        for (int d = 0; d < MAX_DEVICES; d++) {
+            if (main[d]) cudaStreamDestroy(main[d]);
+            if (copy[d]) cudaStreamDestroy(copy[d]);
+        }
+    }
 };
 static thread_local ThreadStreams g_streams;
+
+// pinned staging for the device -> host read of the build state: a copy into pageable memory is synchronous
+// inside the driver, and a shard blocked there can keep another shard's thread of the same process from launching
+struct PinnedState {
+    void* p = nullptr;
+    ~PinnedState() {
+        if (p) cudaFreeHost(p);
+    }
+};
+static thread_local PinnedState g_pinned_state;
+static void* pinned_state_buffer(size_t bytes) {
+    if (!g_pinned_state.p) CK(cudaHostAlloc(&g_pinned_state.p, bytes, cudaHostAllocDefault));
+    return g_pinned_state.p;
+}
 static cudaStream_t own_stream(int dev, bool copy) {
     cudaStream_t& s = copy ? g_streams.copy[dev] : g_streams.main[dev];
     if (!s) CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
@@ -120,6 +155,35 @@ struct bphf_mphf {
     std::vector<LevelDesc> lv;
     bphf_build_stats stats;
     bphf_mphf() { memset(&stats, 0, sizeof stats); }
+};
+
+// ------------------------------------------------------------------------------------------------
+// sharded build: the peer-visible arena of one shard
+// ------------------------------------------------------------------------------------------------
+struct bphf_comm {
+    int device = 0;
+    int rank = 0, world = 1;
+    uint64_t phys_words = 0;     // words per arena (incl. the tail reserve)
+    unsigned char* base = nullptr;  // [words | coll | xkeys | flags], one cudaMalloc (IPC-exportable)
+    size_t bytes = 0;
+    void* peer_base[SHARD_MAX] = {};  // mapped bases of all shards (own base at [rank])
+    bool peer_is_ipc[SHARD_MAX] = {};
+    bool connected = false;
+    uint64_t epoch = 0;          // barrier counter; advances identically on every shard
+    cudaStream_t stream = nullptr;  // the shard's build stream (owned: one hardware queue per live shard)
+    void* pinned = nullptr;         // pinned staging for the build state read-back
+    CommDev dev;
+    size_t off_coll() const { return (size_t)phys_words * 8; }
+    size_t off_xkeys() const { return (size_t)phys_words * 16; }
+    size_t off_flags() const { return off_xkeys() + XKEYS_WORDS * 8; }
+    void map_peer(int p, void* b) {
+        peer_base[p] = b;
+        unsigned char* u = static_cast<unsigned char*>(b);
+        dev.words[p] = reinterpret_cast<uint64_t*>(u);
+        dev.coll[p] = reinterpret_cast<uint64_t*>(u + off_coll());
+        dev.xkeys[p] = reinterpret_cast<uint64_t*>(u + off_xkeys());
+        dev.flags[p] = reinterpret_cast<uint64_t*>(u + off_flags());
+    }
 };
 
 static void upload_level_table(bphf_mphf* m, cudaStream_t s) {
@@ -237,6 +301,7 @@ struct Builder {
     uint64_t n = 0;
     bool maybe_big = false;
     uint32_t launches = 0, syncs = 0;
+    bphf_comm* comm = nullptr;  // sharded build: the arenas live in the comm's peer-visible allocation
     std::vector<EventPair> events;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
 
@@ -247,8 +312,8 @@ struct Builder {
         // scratch goes back to the pool (stream ordered); the handle took ownership of what it keeps
         if (d_state) cudaFreeAsync(d_state, s);
         if (d_keys_owned) cudaFreeAsync(d_keys_owned, s);
-        if (d_words) cudaFreeAsync(d_words, s);
-        if (d_coll) cudaFreeAsync(d_coll, s);
+        if (d_words && !comm) cudaFreeAsync(d_words, s);
+        if (d_coll && !comm) cudaFreeAsync(d_coll, s);
         if (d_blockpop) cudaFreeAsync(d_blockpop, s);
         if (d_cursors) cudaFreeAsync(d_cursors, s);
         for (int i = 0; i < 2; i++) {
@@ -284,8 +349,15 @@ struct Builder {
 
     void alloc_arena(uint64_t words_cap) {
         phys_words = words_cap + TAIL_RESERVE_WORDS;
-        CK(cudaMallocAsync((void**)&d_words, phys_words * 8, s));
-        CK(cudaMallocAsync((void**)&d_coll, phys_words * 8, s));
+        if (comm) {
+            if (phys_words > comm->phys_words)
+                throw CudaFailure{BPHF_ERR_NOMEM, "sharded build: the comm's arena is too small for this key count / gamma"};
+            d_words = comm->dev.words[comm->rank];
+            d_coll = comm->dev.coll[comm->rank];
+        } else {
+            CK(cudaMallocAsync((void**)&d_words, phys_words * 8, s));
+            CK(cudaMallocAsync((void**)&d_coll, phys_words * 8, s));
+        }
         CK(cudaMallocAsync((void**)&d_blockpop, (phys_words / 8) * 4, s));
         CK(cudaMallocAsync((void**)&d_cursors, (size_t)2 * MAX_BUCKETS_ALLOC * CURSOR_STRIDE * 4, s));
         CK(cudaMemsetAsync(d_words, 0, phys_words * 8, s));
@@ -294,6 +366,7 @@ struct Builder {
     }
     // ST_NEED_WORDS: move to a larger arena, keeping everything built so far
     void grow_arena(uint64_t need_words) {
+        if (comm) throw CudaFailure{BPHF_ERR_NOMEM, "sharded build: level does not fit the comm's arena (duplicate keys?)"};
         const uint64_t new_cap = std::max<uint64_t>(need_words + need_words / 2, hst.words_cap * 2);
         const uint64_t new_phys = new_cap + TAIL_RESERVE_WORDS;
         uint64_t *nw = nullptr, *nc = nullptr;
@@ -366,9 +439,37 @@ struct Builder {
     }
     void launch_tail() {
         const size_t ev = begin_event(2, 0);
-        tail_kernel<<<1, TAIL_THREADS, sizeof(TailSmem), s>>>(d_state, d_keys, d_buf[0], d_buf[1], a32(), c32(), d_blockpop);
+        CommDev cd;
+        memset(&cd, 0, sizeof cd);
+        if (comm) {
+            cd = comm->dev;
+            tail_gather_kernel<<<1, TAIL_THREADS, 0, s>>>(d_state, d_keys, d_buf[0], d_buf[1], c32(), cd.xkeys[cd.rank]);
+            CK(cudaGetLastError());
+            launches++;
+            launch_barrier(BAR_PLAIN, 0);
+        }
+        tail_kernel<<<1, TAIL_THREADS, sizeof(TailSmem), s>>>(d_state, d_keys, d_buf[0], d_buf[1], a32(), c32(), d_blockpop, cd);
         CK(cudaGetLastError());
         end_event(ev);
+        launches++;
+        // nobody may start the next build (and overwrite its exchange slot) before every shard has read it
+        if (comm) launch_barrier(BAR_PLAIN, 0);
+    }
+    // ---- sharded build: device-side barrier and OR-collide merge over peer memory ---------------------
+    void launch_barrier(uint32_t kind, uint32_t level) {
+        comm->epoch += 1;
+        shard_barrier_kernel<<<1, 32, 0, s>>>(d_state, comm->dev, comm->epoch, kind, level);
+        CK(cudaGetLastError());
+        launches++;
+    }
+    void launch_merge(uint32_t level, uint64_t k_up) {
+        const uint64_t bits = level_size(hst.gamma, k_up);
+        const uint64_t pairs = round_up8((bits + 63) / 64) / 2;
+        const uint64_t per = (pairs + comm->world - 1) / comm->world;
+        const int grid = (int)std::min<uint64_t>(std::max<uint64_t>(1, (per + MERGE_THREADS - 1) / MERGE_THREADS),
+                                                 (uint64_t)info.sm_count * 4);
+        or_collide_merge_kernel<<<grid, MERGE_THREADS, 0, s>>>(d_state, level, comm->dev);
+        CK(cudaGetLastError());
         launches++;
     }
     // ---- bucketed (shared-memory) kernels -----------------------------------------------------------
@@ -411,6 +512,15 @@ struct Builder {
             if (!prev_surely_b) launch_pass(level, prev->k_up);
             end_event(e0);
         }
+        if (comm) {
+            // every shard has marked its keys -> fold the (a, collide) pairs of all shards -> everybody holds
+            // the merged level.  The first barrier also checks that the shards' lists add up to k(level).
+            const size_t em = begin_event(4, level);
+            launch_barrier(BAR_LIST_SUM, level);
+            launch_merge(level, cur.k_up);
+            launch_barrier(BAR_PLAIN, level);
+            end_event(em);
+        }
         const size_t e1 = begin_event(1, level);
         if (cur.maybe_bucket) launch_bucket_mark(level, cur.range_max, cur.count_max);
         if (!cur.surely_bucket) launch_finalize(level, cur.k_up);
@@ -419,8 +529,10 @@ struct Builder {
 
     void upload_state() { CK(cudaMemcpyAsync(d_state, &hst, sizeof hst, cudaMemcpyHostToDevice, s)); }
     void download_state() {
-        CK(cudaMemcpyAsync(&hst, d_state, sizeof hst, cudaMemcpyDeviceToHost, s));
+        void* pin = comm ? comm->pinned : pinned_state_buffer(sizeof hst);
+        CK(cudaMemcpyAsync(pin, d_state, sizeof hst, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
+        memcpy(&hst, pin, sizeof hst);
         syncs++;
     }
 };
@@ -429,21 +541,37 @@ struct Builder {
 
 enum { BUILD_RETRY_PLAIN = 1000 };
 
+// n = keys of this shard; comm == nullptr: unsharded (n_global == n)
 static int build_once(const uint64_t* keys, uint64_t n, double gamma, int has_seed, uint64_t seed, int device,
-                      int keys_mem, void* stream, bool bucket_enable, uint32_t rebuilds, bphf_mphf** out) {
+                      int keys_mem, void* stream, bool bucket_enable, uint32_t rebuilds, bphf_mphf** out,
+                      bphf_comm* comm = nullptr, uint64_t n_global_arg = 0) {
     const DeviceInfo& info = device_info(device);
     DeviceGuard guard(device);
     cudaStream_t s = stream ? (cudaStream_t)stream : own_stream(device, false);
     Builder b(device, info, s, g_profile);
     b.n = n;
+    b.comm = comm;
+    const uint64_t n_global = comm ? n_global_arg : n;
+    if (comm) bucket_enable = false;  // shards mark full-width arrays with the L2-atomic kernels
 
     CK(cudaEventCreate(&b.ev_begin));
     CK(cudaEventCreate(&b.ev_end));
     CK(cudaEventRecord(b.ev_begin, s));
 
     const uint64_t min_keys = g_bucket_min_keys;
-    const Plan plan = make_plan(n, gamma, b.slots(), bucket_enable, min_keys);
+    Plan plan = make_plan(n_global, gamma, b.slots(), bucket_enable, min_keys);
     b.maybe_big = plan.maybe_big;
+    if (comm) {
+        // this shard's redo lists: its expected share of every level + 8 sigma (there is no host round trip to
+        // grow a list in the middle of a collective build; overflow ends in BPHF_ERR_NOMEM)
+        plan.list_cap[0] = plan.list_cap[1] = 1;
+        const double frac = n_global ? (double)n / (double)n_global : 0.0;
+        for (size_t l = 1; l <= plan.lv.size(); l++) {
+            const double est = (l < plan.lv.size() ? (double)plan.lv[l].k_up : (double)TAIL_MAX_KEYS / 0.4) * frac * 1.05;
+            const uint64_t cap = std::min<uint64_t>(n, (uint64_t)(est + 8.0 * std::sqrt(est) + 4096.0));
+            plan.list_cap[l & 1] = std::max<uint64_t>(plan.list_cap[l & 1], cap);
+        }
+    }
 
     CK(cudaMallocAsync((void**)&b.d_state, sizeof(BuildState), s));
     b.alloc_arena(plan.words_cap);
@@ -463,7 +591,10 @@ static int build_once(const uint64_t* keys, uint64_t n, double gamma, int has_se
     st.bucket_enable = bucket_enable ? 1 : 0;
     st.bucket_slots = b.slots();
     st.bucket_min_keys = min_keys;
-    if (!try_make_level(&st, 0, n)) return fail(BPHF_ERR_INTERNAL, "level 0 does not fit the planned buffers");
+    st.shard_rank = comm ? (uint32_t)comm->rank : 0;
+    st.shard_world = comm ? (uint32_t)comm->world : 1;
+    if (!try_make_level(&st, 0, n_global)) return fail(BPHF_ERR_INTERNAL, "level 0 does not fit the planned buffers");
+    st.lv[0].k_loc = n;
     b.upload_state();
     const bool level0_bucketed = st.lv[0].b_range != 0;
     const uint32_t count0 = st.lv[0].b_count;
@@ -505,7 +636,7 @@ static int build_once(const uint64_t* keys, uint64_t n, double gamma, int has_se
 
     // ---- all planned levels, then the tail, without a host round trip
     LevelPlan lp0;
-    lp0.k_up = lp0.k_lo = n;
+    lp0.k_up = lp0.k_lo = n_global;
     lp0.maybe_bucket = lp0.surely_bucket = level0_bucketed;
     lp0.range_max = st.lv[0].b_range;
     lp0.count_max = level0_bucketed ? count0 : 1;
@@ -534,6 +665,14 @@ static int build_once(const uint64_t* keys, uint64_t n, double gamma, int has_se
             snprintf(msg, sizeof msg, "internal consistency check failed (info %llx)", (unsigned long long)st.err_info);
             return fail(BPHF_ERR_INTERNAL, msg);
         }
+        if (st.status == ST_ERR_COMM) {
+            char msg[160];
+            snprintf(msg, sizeof msg, "sharded build: a peer shard failed or did not reach a barrier in time (level %llu, peers %llx)",
+                     (unsigned long long)(st.err_info >> 48), (unsigned long long)(st.err_info & 0xffffffffULL));
+            return fail(BPHF_ERR_CUDA, msg);
+        }
+        if (st.status == ST_ERR_LIST_OVERFLOW)
+            return fail(BPHF_ERR_NOMEM, "sharded build: this shard's share of a level outgrew its redo list (unbalanced shards)");
         const uint32_t level = st.n_levels;  // the level that could not be set up / has not run yet
         if (level == 0 || level > BPHF_MAX_LEVELS) return fail(BPHF_ERR_INTERNAL, "bad resume level");
         if (st.status == ST_NEED_WORDS || st.status == ST_NEED_LIST) {
@@ -600,8 +739,14 @@ static int build_once(const uint64_t* keys, uint64_t n, double gamma, int has_se
         b.end_event(ev);
         CK(cudaFreeAsync(d_sums, s));
     }
-    m->d_words = b.d_words;  // the handle keeps the arena (padded, <= planned capacity)
-    b.d_words = nullptr;
+    if (comm) {
+        // the arena belongs to the comm (peers write into it during the next build): the handle gets a copy
+        CK(cudaMallocAsync((void**)&m->d_words, std::max<uint64_t>(st.words_used, 8) * 8, s));
+        CK(cudaMemcpyAsync(m->d_words, b.d_words, st.words_used * 8, cudaMemcpyDeviceToDevice, s));
+    } else {
+        m->d_words = b.d_words;  // the handle keeps the arena (padded, <= planned capacity)
+        b.d_words = nullptr;
+    }
     CK(cudaEventRecord(b.ev_end, s));
     upload_level_table(m.get(), s);  // synchronises the stream
     b.syncs++;
@@ -615,7 +760,7 @@ static int build_once(const uint64_t* keys, uint64_t n, double gamma, int has_se
         bs.keys_in[l] = st.lv[l].k_in;
         bs.bits[l] = st.lv[l].bits;
     }
-    total_keys = n;
+    total_keys = n_global;
     m->n_keys = total_keys;
     bs.kernel_launches = b.launches;
     bs.host_syncs = b.syncs;
@@ -627,6 +772,7 @@ static int build_once(const uint64_t* keys, uint64_t n, double gamma, int has_se
         else if (e.kind == 1 && e.level <= BPHF_MAX_LEVELS) bs.fin_ms[e.level] += ms;
         else if (e.kind == 2) bs.tail_ms += ms;
         else if (e.kind == 3) bs.ranks_ms += ms;
+        else if (e.kind == 4 && e.level <= BPHF_MAX_LEVELS) bs.merge_ms[e.level] += ms;
     }
     bs.h2d_ms = 0.f;
     uint32_t nb = 0;
@@ -727,6 +873,124 @@ BPHF_API int bphf_build_u64(const uint64_t* keys, uint64_t n, double gamma, int 
                             int keys_mem, void* stream, bphf_mphf** out) {
     API_BEGIN
     return build_impl(keys, n, gamma, has_seed, seed, device, keys_mem, stream, out);
+    API_END
+}
+
+// ---- sharded build -------------------------------------------------------------------
+BPHF_API int bphf_comm_create(int device, int rank, int world, uint64_t max_keys_global, double max_gamma, bphf_comm** out) {
+    API_BEGIN
+    if (!out) return fail(BPHF_ERR_ARG, "out is null");
+    *out = nullptr;
+    if (world < 1 || world > SHARD_MAX || rank < 0 || rank >= world) return fail(BPHF_ERR_ARG, "bad rank / world (world <= 8)");
+    if (!(max_gamma > 1.01)) return fail(BPHF_ERR_GAMMA, "assertion failed: gamma > 1.01");
+    const DeviceInfo& info = device_info(device);
+    DeviceGuard guard(device);
+    const Plan plan = make_plan(max_keys_global, max_gamma, (uint32_t)info.sm_count * 2, false, 0);
+    std::unique_ptr<bphf_comm> c(new bphf_comm());
+    c->device = device;
+    c->rank = rank;
+    c->world = world;
+    c->phys_words = round_up8(plan.words_cap + plan.words_cap / 64 + TAIL_RESERVE_WORDS);
+    c->bytes = c->off_flags() + (size_t)SHARD_MAX * FLAG_STRIDE * 8;
+    memset(&c->dev, 0, sizeof c->dev);
+    c->dev.rank = (uint32_t)rank;
+    c->dev.world = (uint32_t)world;
+    // plain cudaMalloc: exportable with cudaIpcGetMemHandle (pool memory is not)
+    CK(cudaMalloc((void**)&c->base, c->bytes));
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaHostAlloc(&c->pinned, sizeof(BuildState), cudaHostAllocDefault));
+    CK(cudaMemset(c->base, 0, c->bytes));
+    CK(cudaDeviceSynchronize());
+    c->map_peer(rank, c->base);
+    if (world == 1) c->connected = true;
+    *out = c.release();
+    return BPHF_OK;
+    API_END
+}
+
+BPHF_API int bphf_comm_ipc_handle(const bphf_comm* c, void* handle_out) {
+    API_BEGIN
+    if (!c || !handle_out) return fail(BPHF_ERR_ARG, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == BPHF_IPC_HANDLE_BYTES, "IPC handle size");
+    DeviceGuard guard(c->device);
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, c->base));
+    memcpy(handle_out, &h, sizeof h);
+    return BPHF_OK;
+    API_END
+}
+
+BPHF_API int bphf_comm_connect_ipc(bphf_comm* c, const void* handles) {
+    API_BEGIN
+    if (!c || !handles) return fail(BPHF_ERR_ARG, "null argument");
+    DeviceGuard guard(c->device);
+    for (int p = 0; p < c->world; p++) {
+        if (p == c->rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, static_cast<const unsigned char*>(handles) + (size_t)p * BPHF_IPC_HANDLE_BYTES, sizeof h);
+        void* b = nullptr;
+        CK(cudaIpcOpenMemHandle(&b, h, cudaIpcMemLazyEnablePeerAccess));
+        c->map_peer(p, b);
+        c->peer_is_ipc[p] = true;
+    }
+    c->connected = true;
+    return BPHF_OK;
+    API_END
+}
+
+BPHF_API int bphf_comm_connect_local(bphf_comm* c, bphf_comm* const* all) {
+    API_BEGIN
+    if (!c || !all) return fail(BPHF_ERR_ARG, "null argument");
+    DeviceGuard guard(c->device);
+    for (int p = 0; p < c->world; p++) {
+        if (p == c->rank) continue;
+        const bphf_comm* o = all[p];
+        if (!o || o->rank != p || o->world != c->world || o->phys_words != c->phys_words)
+            return fail(BPHF_ERR_ARG, "comms do not match (rank order, world, arena size)");
+        if (o->device != c->device) {
+            int can = 0;
+            CK(cudaDeviceCanAccessPeer(&can, c->device, o->device));
+            if (!can) return fail(BPHF_ERR_CUDA, "devices cannot access each other's memory");
+            cudaError_t e = cudaDeviceEnablePeerAccess(o->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e);
+            cudaGetLastError();
+        }
+        c->map_peer(p, o->base);
+    }
+    c->connected = true;
+    return BPHF_OK;
+    API_END
+}
+
+BPHF_API void bphf_comm_destroy(bphf_comm* c) {
+    if (!c) return;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    if (cudaSetDevice(c->device) == cudaSuccess) {
+        cudaDeviceSynchronize();
+        for (int p = 0; p < c->world; p++)
+            if (c->peer_is_ipc[p] && c->peer_base[p]) cudaIpcCloseMemHandle(c->peer_base[p]);
+        if (c->base) cudaFree(c->base);
+        if (c->stream) cudaStreamDestroy(c->stream);
+        if (c->pinned) cudaFreeHost(c->pinned);
+    }
+    if (prev >= 0) cudaSetDevice(prev);
+    delete c;
+}
+
+BPHF_API int bphf_build_sharded_u64(bphf_comm* c, const uint64_t* keys, uint64_t n_local, uint64_t n_global, double gamma,
+                                    int has_seed, uint64_t seed, int keys_mem, bphf_mphf** out) {
+    API_BEGIN
+    if (!out) return fail(BPHF_ERR_ARG, "out is null");
+    *out = nullptr;
+    if (!c) return fail(BPHF_ERR_ARG, "null comm");
+    if (!c->connected) return fail(BPHF_ERR_ARG, "comm is not connected to its peers");
+    if (n_local && !keys) return fail(BPHF_ERR_ARG, "keys is null");
+    if (n_local > n_global) return fail(BPHF_ERR_ARG, "n_local > n_global");
+    if (keys_mem != BPHF_MEM_HOST && keys_mem != BPHF_MEM_DEVICE) return fail(BPHF_ERR_ARG, "bad keys_mem");
+    if (!(gamma > 1.01)) return fail(BPHF_ERR_GAMMA, "assertion failed: gamma > 1.01");
+    if (c->world == 1) return build_impl(keys, n_local, gamma, has_seed, seed, c->device, keys_mem, nullptr, out);
+    return build_once(keys, n_local, gamma, has_seed, seed, c->device, keys_mem, c->stream, false, 0, out, c, n_global);
     API_END
 }
 

@@ -73,7 +73,7 @@ __host__ __device__ inline bool try_make_level(BuildState* st, uint32_t level, u
         d.b_range = g.range;
         d.b_count = g.count;
         d.b_cap = g.cap;
-    } else if (level >= 1 && k > st->list_cap[level & 1]) {
+    } else if (level >= 1 && st->shard_world <= 1 && k > st->list_cap[level & 1]) {
         st->status = ST_NEED_LIST;
         st->need = k;
         return false;
@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(PASS_THREADS)
     if (level >= 1) {
         keys = (level & 1) ? buf1 : buf0;
         key_begin = 0;
-        key_end = st->lv[level].k_in;
+        key_end = st->lv[level].k_loc;
     }
     const uint64_t bits = st->lv[level].bits;
     const uint64_t sp0 = st->lv[level].sp0;
@@ -194,12 +194,13 @@ __global__ void __launch_bounds__(PASS_THREADS)
 
     const LevelDesc* __restrict__ pv = &st->lv[level - 1];
     const LevelDesc* __restrict__ cu = &st->lv[level];
-    const uint64_t p_bits = pv->bits, p_sp0 = pv->sp0, p_off32 = pv->word_off * 2, k_src = pv->k_in;
+    const uint64_t p_bits = pv->bits, p_sp0 = pv->sp0, p_off32 = pv->word_off * 2, k_src = pv->k_loc;
     const uint64_t c_bits = cu->bits, c_sp0 = cu->sp0, c_off32 = cu->word_off * 2;
     const bool p_big = MAYBE_BIG && (p_bits >> 32) != 0;
     const bool c_big = MAYBE_BIG && (c_bits >> 32) != 0;
     const uint64_t* __restrict__ src = (level == 1) ? user_keys : (((level - 1) & 1) ? buf1 : buf0);
     uint64_t* __restrict__ dst = (level & 1) ? buf1 : buf0;
+    const uint64_t dst_cap = st->list_cap[level & 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
     const uint64_t n_tiles = (k_src + PASS_TILE - 1) / PASS_TILE;
@@ -250,6 +251,13 @@ __global__ void __launch_bounds__(PASS_THREADS)
             sh_base = (uint64_t)atomicAdd((unsigned long long*)&st->redo_count, (unsigned long long)total);
         __syncthreads();
         const uint64_t out = sh_base;
+        // an unsharded build knows k(level) before this kernel runs and sized the list for it; a shard of a
+        // sharded build only has an estimate of its own share
+        if (out + total > dst_cap) {
+            if (threadIdx.x == 0) st->status = ST_ERR_LIST_OVERFLOW;
+            __syncthreads();
+            continue;
+        }
         // rayon filter_map().collect() (src/lib.rs:374-377): append to level l's list (coalesced), and
         // find_collisions of level l for the same key while it is still on chip
         {
@@ -337,10 +345,15 @@ __global__ void __launch_bounds__(FIN_THREADS)
         __threadfence();
         const uint64_t uq = atomicAdd((unsigned long long*)&st->uniq_count, 0ULL);
         const uint64_t k_in = st->lv[level].k_in;
+        const uint64_t listed = atomicAdd((unsigned long long*)&st->redo_count, 0ULL);
+        const bool sharded = st->shard_world > 1;
+        // sharded: this shard's part of the level's key list is what its filter appended (the shard sum was
+        // checked against k_in at the merge barrier)
+        if (sharded && level >= 1) st->lv[level].k_loc = listed;
         // plain predecessor: pass_kernel appended this level's list through redo_count, which must match k_in
         // (a bucketed predecessor is checked through the bucket cursors instead)
-        const bool check_list = level >= 1 && st->lv[level - 1].b_range == 0;
-        if (uq > k_in || (check_list && atomicAdd((unsigned long long*)&st->redo_count, 0ULL) != k_in)) {
+        const bool check_list = !sharded && level >= 1 && st->lv[level - 1].b_range == 0;
+        if (uq > k_in || (check_list && listed != k_in)) {
             st->status = ST_ERR_INTERNAL;
             st->err_info = ((uint64_t)level << 48) | uq;
         } else {
@@ -364,7 +377,7 @@ struct TailSmem {
 __global__ void __launch_bounds__(TAIL_THREADS)
     tail_kernel(BuildState* __restrict__ st, const uint64_t* __restrict__ user_keys, const uint64_t* __restrict__ buf0,
                 const uint64_t* __restrict__ buf1, uint32_t* __restrict__ words32, const uint32_t* __restrict__ c32,
-                uint32_t* __restrict__ blockpop) {
+                uint32_t* __restrict__ blockpop, CommDev cd) {
     extern __shared__ __align__(16) unsigned char tail_smem_raw[];
     TailSmem& s = *reinterpret_cast<TailSmem*>(tail_smem_raw);
     if (st->status != ST_RUNNING || st->tail_level == NO_TAIL || st->n_levels != st->tail_level) return;
@@ -374,7 +387,19 @@ __global__ void __launch_bounds__(TAIL_THREADS)
     if (tid == 0) s.count = 0;
     __syncthreads();
     // gather the keys entering `level`
-    if (level == 0) {
+    if (st->shard_world > 1) {
+        // sharded build: every shard left its part in its exchange slot (tail_gather_kernel + barrier); all
+        // shards read all slots over peer memory and finish the cascade redundantly -> identical replicas
+        uint32_t base = 0;
+        for (uint32_t p = 0; p < cd.world; p++) {
+            const volatile uint64_t* xk = cd.xkeys[p];
+            const uint32_t cnt = (uint32_t)min(xk[0], (uint64_t)TAIL_MAX_KEYS);
+            for (uint32_t i = tid; i < cnt; i += TAIL_THREADS)
+                if (base + i < TAIL_MAX_KEYS) s.keys[0][base + i] = xk[8 + i];
+            base += cnt;
+        }
+        if (tid == 0) s.count = base;
+    } else if (level == 0) {
         for (uint32_t i = tid; i < k; i += TAIL_THREADS) s.keys[0][i] = user_keys[i];
         if (tid == 0) s.count = k;
     } else if (st->lv[level - 1].b_range != 0) {

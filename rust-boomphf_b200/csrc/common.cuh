@@ -22,7 +22,8 @@ struct LevelDesc {
     uint64_t bits;      // BitVector.bits = capacity()  (src/bitvector.rs:359)
     uint64_t n_words;   // u64s(bits)                   (src/bitvector.rs:426-428)
     uint64_t word_off;  // first arena word of this level (multiple of 8)
-    uint64_t k_in;      // keys entering this level (build only)
+    uint64_t k_in;      // keys entering this level, over ALL shards (build only): sizes the level
+    uint64_t k_loc;     // keys of THIS shard entering the level (== k_in for an unsharded build)
     uint64_t sp0;       // seed_xor_p0(seed index) used to BUILD this level
     uint64_t sp0_query; // seed_xor_p0(level index): what Mphf::hash uses (src/lib.rs:327)
     // bucketed construction (build only): the level's bit range is cut into b_count buckets of b_range bits
@@ -43,6 +44,8 @@ enum BuildStatus : uint32_t {
     ST_NEED_LIST = 4,      // redo list buffer too small for the next level: host grows it and resumes
     ST_ERR_INTERNAL = 5,
     ST_BUCKET_OVERFLOW = 6,  // a bucket region or a kernel's shared memory was too small: host rebuilds unbucketed
+    ST_ERR_COMM = 7,         // sharded build: a peer did not arrive at a barrier in time, or reported an error
+    ST_ERR_LIST_OVERFLOW = 8,  // sharded build: this shard's redo list outgrew its buffer (no host round trip there)
 };
 
 // device-resident build state; the level loop runs without host round trips (kernels for all
@@ -65,6 +68,8 @@ struct BuildState {
     uint32_t bucket_slots;     // CTAs that run concurrently (SM count x 2): bucket counts are multiples of it
     uint32_t bucket_enable;
     uint64_t bucket_keys_seen; // sum of bucket fills seen by the mark kernel (consistency check)
+    uint32_t shard_rank;       // sharded build: this shard's index ...
+    uint32_t shard_world;      // ... of shard_world shards (1 = unsharded)
     LevelDesc lv[BPHF_MAX_LEVELS + 1];
 };
 
@@ -77,6 +82,20 @@ constexpr uint32_t TAIL_MAX_WORDS = TAIL_MAX_BITS / 64;      // 1024
 constexpr uint64_t TAIL_RESERVE_WORDS = (uint64_t)(BPHF_MAX_LEVELS + 1) * (TAIL_MAX_WORDS + LEVEL_ALIGN_WORDS);
 
 __host__ __device__ __forceinline__ uint64_t round_up8(uint64_t w) { return (w + 7) & ~7ULL; }
+
+// ---- sharded build: peer-visible memory of every shard ------------------------------------
+// Each shard owns ONE peer-mapped allocation: [words arena | collide arena | tail exchange slot | flags].
+// Passed to the kernels by value; pointer p of every array is shard p's copy (own pointers for p == rank).
+constexpr int SHARD_MAX = 8;
+constexpr uint32_t FLAG_STRIDE = 16;                      // u64 per writer: one 128-byte line each
+constexpr uint64_t XKEYS_WORDS = TAIL_MAX_KEYS + 16;      // [0] = count, [8..] = keys
+struct CommDev {
+    uint32_t rank, world;
+    uint64_t* words[SHARD_MAX];   // level bit vectors (raw a while marking, final a after the merge)
+    uint64_t* coll[SHARD_MAX];    // collision bit vectors
+    uint64_t* xkeys[SHARD_MAX];   // keys this shard hands to the tail
+    uint64_t* flags[SHARD_MAX];   // flags[p][r * FLAG_STRIDE + {0: epoch, 1: payload, 2: status}] written by shard r
+};
 
 // ---- bucket geometry --------------------------------------------------------------------------------
 constexpr uint32_t BUCKET_R_MAX = 442368;    // bits per bucket: a + collide = 110,592 B of shared memory -> 2 CTAs / SM
@@ -129,6 +148,7 @@ __host__ __device__ inline void make_level(BuildState* st, uint32_t level, uint6
     d.n_words = (d.bits + 63) / 64;
     d.word_off = st->words_used;
     d.k_in = k;
+    d.k_loc = (st->shard_world > 1 && level > 0) ? 0 : k;  // sharded: known once this shard's filter has run
     d.sp0 = seed_xor_p0(st->seed0 + level);
     d.sp0_query = seed_xor_p0(level);
     d.b_div = 0;

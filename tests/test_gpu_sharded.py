@@ -1,0 +1,124 @@
+"""Sharded (multi-GPU) construction on the GPU: G shards -- here G logical shards on ONE device, one
+thread each, talking through exactly the peer-memory kernels a multi-GPU run uses -- must produce, on every
+shard, the structure an unsharded build of the union produces (bit-exact vs the CPU oracle)."""
+import numpy as np
+import pytest
+
+from test_gpu_parity import assert_same_levels
+
+pytestmark = pytest.mark.gpu
+
+
+def _sharded(pkg):
+    import importlib
+    return importlib.import_module(pkg.__name__ + ".sharded")
+
+
+def _split(keys, world, how):
+    n = len(keys)
+    if how == "even":
+        b = _sharded_bounds(n, world)
+    elif how == "first_empty":
+        b = [0, 0] + _sharded_bounds(n, world - 1)[1:]
+    elif how == "skewed":
+        cut = sorted(set([0, n] + [min(n, (n * (2 ** r - 1)) // (2 ** world - 1)) for r in range(1, world)]))
+        while len(cut) < world + 1:
+            cut.append(n)
+        b = sorted(cut)
+    else:
+        raise ValueError(how)
+    return [keys[b[r]:b[r + 1]] for r in range(world)]
+
+
+def _sharded_bounds(n, world):
+    base, rem = divmod(n, world)
+    b = [0]
+    for r in range(world):
+        b.append(b[-1] + base + (1 if r < rem else 0))
+    return b
+
+
+def _run(pkg, oracle, keys, world, gamma=1.7, seed=None, how="even", max_keys=None):
+    sh = _sharded(pkg)
+    comms = sh.ShardComm.local_group([0] * world, max_keys or max(len(keys), 1), gamma)
+    try:
+        shards = _split(keys, world, how)
+        assert sum(len(s) for s in shards) == len(keys)
+        ms = sh.build_in_threads(comms, gamma, shards, seed)
+        ref = oracle.OracleMphf.new_parallel(gamma, keys, seed)
+        exp = ref.levels()
+        for m in ms:
+            assert_same_levels(m.levels(), exp)
+        if len(keys) and seed is None:
+            h = ms[-1].hash_batch(keys)
+            assert np.array_equal(h, ref.hash_batch(keys, nthreads=0))
+            assert np.array_equal(np.sort(h), np.arange(len(keys), dtype=np.uint64))
+        return ms
+    finally:
+        for c in comms:
+            c.close()
+
+
+@pytest.mark.parametrize("world", [2, 3, 4, 8])
+@pytest.mark.parametrize("n", [0, 1, 100, 4096, 5000, 9001, 70_000, 1_000_003])
+def test_sharded_build_parity(pkg, oracle, world, n):
+    _run(pkg, oracle, oracle.keygen(n, seed=3 * n + world, kind=0), world)
+
+
+@pytest.mark.parametrize("how", ["first_empty", "skewed"])
+def test_unbalanced_shards(pkg, oracle, how):
+    _run(pkg, oracle, oracle.keygen(300_001, seed=9, kind=0), 4, how=how)
+
+
+@pytest.mark.parametrize("gamma", [1.02, 2.0, 5.0])
+def test_sharded_gamma(pkg, oracle, gamma):
+    _run(pkg, oracle, oracle.keygen(200_000, seed=21, kind=1), 3, gamma=gamma)
+
+
+@pytest.mark.parametrize("seed", [5, 31, 2 ** 64 - 3])
+def test_sharded_starting_seed(pkg, oracle, seed):
+    _run(pkg, oracle, oracle.keygen(150_000, seed=4, kind=0), 2, seed=seed)
+
+
+def test_comm_is_reusable_and_matches_unsharded_gpu_build(pkg, oracle):
+    sh = _sharded(pkg)
+    world = 4
+    comms = sh.ShardComm.local_group([0] * world, 6_000_000, 2.0)
+    try:
+        for n, gamma in [(6_000_000, 1.7), (1_234_567, 2.0), (6_000_000, 1.7)]:
+            keys = oracle.keygen(n, seed=n, kind=0)
+            ms = sh.build_in_threads(comms, gamma, _split(keys, world, "even"))
+            one = pkg.Mphf.new_parallel(gamma, keys, None)
+            fp = oracle.fingerprint(one.levels())
+            for m in ms:
+                assert oracle.fingerprint(m.levels()) == fp
+    finally:
+        for c in comms:
+            c.close()
+
+
+def test_duplicates_across_shards_report_max_iters(pkg):
+    sh = _sharded(pkg)
+    keys = np.arange(1000, dtype=np.uint64)
+    comms = sh.ShardComm.local_group([0, 0], 2000, 1.7)
+    try:
+        with pytest.raises(pkg.MphfPanic) as e:
+            sh.build_in_threads(comms, 1.7, [keys, keys.copy()])  # every key appears in both shards
+        assert "unique hashes" in str(e.value)
+    finally:
+        for c in comms:
+            c.close()
+
+
+def test_sharded_argument_errors(pkg):
+    sh = _sharded(pkg)
+    with pytest.raises(pkg.MphfPanic):
+        sh.ShardComm.create(0, 0, 9, 1000)            # world > 8
+    with pytest.raises(pkg.MphfPanic):
+        sh.ShardComm.create(0, 2, 2, 1000)            # rank out of range
+    c = sh.ShardComm.create(0, 0, 2, 1000)
+    try:
+        with pytest.raises(pkg.MphfPanic):            # not connected yet
+            c.build(1.7, np.arange(10, dtype=np.uint64), 10)
+    finally:
+        c.close()
