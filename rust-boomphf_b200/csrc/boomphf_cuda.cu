@@ -98,7 +98,9 @@ static const DeviceInfo& device_info(int dev) {
                 (const void*)pass_kernel<true>, (const void*)finalize_kernel, (const void*)tail_kernel,
                 (const void*)scan_sums_kernel, (const void*)scan_top_kernel, (const void*)scan_apply_kernel,
                 (const void*)scatter0_kernel, (const void*)scatter_kernel, (const void*)bucket_mark_kernel,
-                (const void*)query_kernel, (const void*)map_permute_kernel, (const void*)map_get_kernel,
+                (const void*)query_kernel<false>, (const void*)query_kernel<true>, (const void*)map_permute_kernel<false>,
+                (const void*)map_permute_kernel<true>, (const void*)map_get_kernel<false>, (const void*)map_get_kernel<true>,
+                (const void*)pack_query_kernel, (const void*)set_base_rank_kernel,
                 (const void*)keygen_kernel, (const void*)check_perm_kernel, (const void*)checksum_kernel,
                 (const void*)shard_barrier_kernel, (const void*)or_collide_merge_kernel, (const void*)tail_gather_kernel};
             for (const void* k : all_kernels) CK(cudaFuncGetAttributes(&fa, k));
@@ -152,6 +154,9 @@ struct bphf_mphf {
     uint64_t* d_words = nullptr;
     uint64_t* d_ranks = nullptr;
     QLevel* d_lv = nullptr;
+    QLevelP* d_lvp = nullptr;   // packed lookup structure (query_kernels.cuh); null when a level has >= 2^32 bits
+    uint4* d_packed = nullptr;
+    uint64_t total_gran = 0;
     std::vector<LevelDesc> lv;
     bphf_build_stats stats;
     bphf_mphf() { memset(&stats, 0, sizeof stats); }
@@ -195,7 +200,41 @@ static void upload_level_table(bphf_mphf* m, cudaStream_t s) {
     }
     CK(cudaMallocAsync((void**)&m->d_lv, q.size() * sizeof(QLevel), s));
     CK(cudaMemcpyAsync(m->d_lv, q.data(), q.size() * sizeof(QLevel), cudaMemcpyHostToDevice, s));
-    CK(cudaStreamSynchronize(s));  // q is a stack vector
+    // packed lookup structure: needs the ranks (already enqueued on s) and 32-bit slot indices
+    bool can_pack = m->n_levels > 0;
+    for (uint32_t l = 0; l < m->n_levels; l++) can_pack = can_pack && (m->lv[l].bits >> 32) == 0;
+    std::vector<QLevelP> qp(std::max<uint32_t>(m->n_levels, 1));
+    if (can_pack) {
+        uint64_t off = 0;
+        for (uint32_t l = 0; l < m->n_levels; l++) {
+            qp[l].sp0 = m->lv[l].sp0_query;
+            qp[l].base_rank = 0;  // first rank entry of the level: filled in on the device (no host round trip)
+            qp[l].gran_off = off;
+            qp[l].bits = (uint32_t)m->lv[l].bits;
+            qp[l].n_gran = (uint32_t)((m->lv[l].bits + GRAN_BITS - 1) / GRAN_BITS);
+            off += qp[l].n_gran;
+        }
+        m->total_gran = off;
+        CK(cudaMallocAsync((void**)&m->d_lvp, qp.size() * sizeof(QLevelP), s));
+        CK(cudaMemcpyAsync(m->d_lvp, qp.data(), qp.size() * sizeof(QLevelP), cudaMemcpyHostToDevice, s));
+        CK(cudaMallocAsync((void**)&m->d_packed, std::max<uint64_t>(off, 1) * sizeof(uint4), s));
+        const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((off + 255) / 256, (uint64_t)g_dev[m->device].sm_count * 16));
+        set_base_rank_kernel<<<1, 128, 0, s>>>(m->d_lvp, m->d_lv, m->n_levels, m->d_ranks);
+        pack_query_kernel<<<grid, 256, 0, s>>>(m->d_lvp, m->d_lv, m->n_levels, m->d_words, m->d_ranks, off, m->d_packed);
+        CK(cudaGetLastError());
+    }
+    CK(cudaStreamSynchronize(s));  // q / qp are stack vectors
+}
+
+static QView query_view(const bphf_mphf* m) {
+    QView v;
+    v.lv = m->d_lv;
+    v.lvp = m->d_lvp;
+    v.words = m->d_words;
+    v.ranks = m->d_ranks;
+    v.packed = m->d_packed;
+    v.n_levels = m->n_levels;
+    return v;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -296,7 +335,6 @@ struct Builder {
     uint32_t* d_blockpop = nullptr;
     uint32_t* d_cursors = nullptr;  // [2][MAX_BUCKETS_ALLOC]
     uint64_t* d_buf[2] = {nullptr, nullptr};   // key lists / bucket key regions, level l in d_buf[l & 1]
-    uint32_t* d_ibuf[2] = {nullptr, nullptr};  // slot index within the bucket, same offsets (bucketed levels)
     uint64_t phys_words = 0;  // words_cap + TAIL_RESERVE_WORDS
     uint64_t n = 0;
     bool maybe_big = false;
@@ -318,7 +356,6 @@ struct Builder {
         if (d_cursors) cudaFreeAsync(d_cursors, s);
         for (int i = 0; i < 2; i++) {
             if (d_buf[i]) cudaFreeAsync(d_buf[i], s);
-            if (d_ibuf[i]) cudaFreeAsync(d_ibuf[i], s);
         }
         for (auto& e : events) {
             if (e.a) cudaEventDestroy(e.a);
@@ -394,11 +431,8 @@ struct Builder {
     void grow_list(int which, uint64_t need) {
         const uint64_t cap = need + need / 8 + 1024;
         if (d_buf[which]) CK(cudaFreeAsync(d_buf[which], s));
-        if (d_ibuf[which]) CK(cudaFreeAsync(d_ibuf[which], s));
         d_buf[which] = nullptr;
-        d_ibuf[which] = nullptr;
         CK(cudaMallocAsync((void**)&d_buf[which], cap * 8, s));
-        if (hst.bucket_enable) CK(cudaMallocAsync((void**)&d_ibuf[which], cap * 4, s));
         hst.list_cap[which] = cap;
     }
 
@@ -479,7 +513,7 @@ struct Builder {
         const uint64_t tiles = (end - begin + BK_TILE - 1) / BK_TILE;
         const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (220 * 1024) / (smem + 1024)));
         const int grid = (int)std::min<uint64_t>(tiles, (uint64_t)info.sm_count * per_sm);
-        scatter0_kernel<<<grid, BK_THREADS, smem, s>>>(d_state, d_keys, begin, end, d_buf[0], d_ibuf[0], d_cursors, (uint32_t)smem);
+        scatter0_kernel<<<grid, BK_THREADS, smem, s>>>(d_state, d_keys, begin, end, d_buf[0], d_cursors, (uint32_t)smem);
         CK(cudaGetLastError());
         launches++;
     }
@@ -487,7 +521,7 @@ struct Builder {
         const size_t smem = std::min(MAX_DYN_SMEM, (size_t)src_range_max / 8 + scatter_smem_bytes(dst_count_max));
         const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (220 * 1024) / (smem + 1024)));
         const int grid = (int)std::max<uint32_t>(1, std::min<uint32_t>(src_count_max, (uint32_t)(info.sm_count * per_sm)));
-        scatter_kernel<<<grid, BK_THREADS, smem, s>>>(d_state, level, d_buf[0], d_buf[1], d_ibuf[0], d_ibuf[1], c32(), d_cursors, (uint32_t)smem);
+        scatter_kernel<<<grid, BK_THREADS, smem, s>>>(d_state, level, d_buf[0], d_buf[1], c32(), d_cursors, (uint32_t)smem);
         CK(cudaGetLastError());
         launches++;
     }
@@ -495,7 +529,7 @@ struct Builder {
         const size_t smem = std::min(MAX_DYN_SMEM, (size_t)range_max / 4);
         const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (220 * 1024) / (smem + 1024)));
         const int grid = (int)std::max<uint32_t>(1, std::min<uint32_t>(count_max, (uint32_t)(info.sm_count * per_sm)));
-        bucket_mark_kernel<<<grid, BK_THREADS, smem, s>>>(d_state, level, d_ibuf[0], d_ibuf[1], a32(), c32(), d_blockpop,
+        bucket_mark_kernel<<<grid, BK_THREADS, smem, s>>>(d_state, level, d_buf[0], d_buf[1], a32(), c32(), d_blockpop,
                                                          d_cursors, (uint32_t)smem);
         CK(cudaGetLastError());
         launches++;
@@ -577,7 +611,6 @@ static int build_once(const uint64_t* keys, uint64_t n, double gamma, int has_se
     b.alloc_arena(plan.words_cap);
     for (int i = 0; i < 2; i++) {
         if (plan.list_cap[i]) CK(cudaMallocAsync((void**)&b.d_buf[i], plan.list_cap[i] * 8, s));
-        if (plan.list_cap[i] && bucket_enable) CK(cudaMallocAsync((void**)&b.d_ibuf[i], plan.list_cap[i] * 4, s));
     }
 
     BuildState& st = b.hst;
@@ -747,8 +780,9 @@ static int build_once(const uint64_t* keys, uint64_t n, double gamma, int has_se
         m->d_words = b.d_words;  // the handle keeps the arena (padded, <= planned capacity)
         b.d_words = nullptr;
     }
+    upload_level_table(m.get(), s);  // level tables + packed lookup structure
     CK(cudaEventRecord(b.ev_end, s));
-    upload_level_table(m.get(), s);  // synchronises the stream
+    CK(cudaStreamSynchronize(s));
     b.syncs++;
 
     // ---- statistics
@@ -1115,6 +1149,8 @@ BPHF_API void bphf_free(bphf_mphf* m) {
         if (m->d_words) cudaFreeAsync(m->d_words, s);
         if (m->d_ranks) cudaFreeAsync(m->d_ranks, s);
         if (m->d_lv) cudaFreeAsync(m->d_lv, s);
+        if (m->d_lvp) cudaFreeAsync(m->d_lvp, s);
+        if (m->d_packed) cudaFreeAsync(m->d_packed, s);
     }
     if (prev >= 0) cudaSetDevice(prev);
     delete m;
@@ -1132,6 +1168,13 @@ static int query_grid(const DeviceInfo& info, uint64_t n) {
     return (int)std::max<uint64_t>(1, std::min<uint64_t>(blocks, (uint64_t)info.sm_count * 16));
 }
 
+static void launch_query(const bphf_mphf* m, const DeviceInfo& info, const uint64_t* keys, uint64_t n, uint64_t* out, cudaStream_t s) {
+    const QView v = query_view(m);
+    if (v.lvp) query_kernel<true><<<query_grid(info, n), QUERY_THREADS, 0, s>>>(v, keys, n, out);
+    else query_kernel<false><<<query_grid(info, n), QUERY_THREADS, 0, s>>>(v, keys, n, out);
+    CK(cudaGetLastError());
+}
+
 BPHF_API int bphf_hash_batch_u64(const bphf_mphf* m, const uint64_t* keys, uint64_t n, uint64_t* out, int mem, void* stream) {
     API_BEGIN
     if (!m) return fail(BPHF_ERR_ARG, "null handle");
@@ -1141,8 +1184,7 @@ BPHF_API int bphf_hash_batch_u64(const bphf_mphf* m, const uint64_t* keys, uint6
     DeviceGuard guard(m->device);
     cudaStream_t s = stream ? (cudaStream_t)stream : own_stream(m->device, false);
     if (mem == BPHF_MEM_DEVICE) {
-        query_kernel<<<query_grid(info, n), QUERY_THREADS, 0, s>>>(m->d_lv, m->n_levels, m->d_words, m->d_ranks, keys, n, out);
-        CK(cudaGetLastError());
+        launch_query(m, info, keys, n, out, s);
         if (!stream) CK(cudaStreamSynchronize(s));
         return BPHF_OK;
     }
@@ -1171,8 +1213,7 @@ BPHF_API int bphf_hash_batch_u64(const bphf_mphf* m, const uint64_t* keys, uint6
         CK(cudaMemcpyAsync(d_in[bi], keys + lo, cnt * 8, cudaMemcpyHostToDevice, cs));
         CK(cudaEventRecord(in_ready[bi], cs));
         CK(cudaStreamWaitEvent(s, in_ready[bi], 0));
-        query_kernel<<<query_grid(info, cnt), QUERY_THREADS, 0, s>>>(m->d_lv, m->n_levels, m->d_words, m->d_ranks, d_in[bi], cnt, d_out[bi]);
-        CK(cudaGetLastError());
+        launch_query(m, info, d_in[bi], cnt, d_out[bi], s);
         CK(cudaMemcpyAsync(out + lo, d_out[bi], cnt * 8, cudaMemcpyDeviceToHost, s));
         CK(cudaEventRecord(out_done[bi], s));
     }
@@ -1209,7 +1250,8 @@ BPHF_API int bphf_map_permute_u64(const bphf_mphf* m, const uint64_t* keys, cons
     }
     unsigned long long* d_bad = st.scratch<unsigned long long>(1);
     CK(cudaMemsetAsync(d_bad, 0, 8, s));
-    map_permute_kernel<<<query_grid(info, n), QUERY_THREADS, 0, s>>>(m->d_lv, m->n_levels, m->d_words, m->d_ranks, dk, dv, n, dko, dvo, d_bad);
+    if (m->d_lvp) map_permute_kernel<true><<<query_grid(info, n), QUERY_THREADS, 0, s>>>(query_view(m), dk, dv, n, dko, dvo, d_bad);
+    else map_permute_kernel<false><<<query_grid(info, n), QUERY_THREADS, 0, s>>>(query_view(m), dk, dv, n, dko, dvo, d_bad);
     CK(cudaGetLastError());
     unsigned long long bad = 0;
     CK(cudaMemcpyAsync(&bad, d_bad, 8, cudaMemcpyDeviceToHost, s));
@@ -1244,7 +1286,8 @@ BPHF_API int bphf_map_get_batch_u64(const bphf_mphf* m, const uint64_t* map_keys
         dvo = st.scratch<uint64_t>(nq);
         dfo = st.scratch<uint8_t>(nq);
     }
-    map_get_kernel<<<query_grid(info, nq), QUERY_THREADS, 0, s>>>(m->d_lv, m->n_levels, m->d_words, m->d_ranks, dmk, dmv, n_map, dq, nq, dvo, dfo);
+    if (m->d_lvp) map_get_kernel<true><<<query_grid(info, nq), QUERY_THREADS, 0, s>>>(query_view(m), dmk, dmv, n_map, dq, nq, dvo, dfo);
+    else map_get_kernel<false><<<query_grid(info, nq), QUERY_THREADS, 0, s>>>(query_view(m), dmk, dmv, n_map, dq, nq, dvo, dfo);
     CK(cudaGetLastError());
     if (mem == BPHF_MEM_HOST) {
         CK(cudaMemcpyAsync(values_out, dvo, nq * 8, cudaMemcpyDeviceToHost, s));

@@ -6,11 +6,11 @@
 // keys/s.  So the large levels are built like this:
 //
 //   scatter(l) : the keys entering level l are grouped by the bit range their level-l slot falls in
-//                ("bucket" = lv[l].b_range bits, a multiple of 512).  scatter(0) streams the input;
-//                scatter(l>=1) streams level l-1's buckets, keeps the keys whose level-(l-1) slot collided
-//                (Context::filter, src/lib.rs:443-452; collide slice of the bucket staged in shared memory)
-//                and groups the survivors by their level-l bucket.  Tile-local binning in shared memory, one
-//                global cursor atomicAdd per (tile, bucket), keys staged in bucket order so the stores are runs.
+//                ("bucket" = 2^b_shift bits).  scatter(0) streams the input; scatter(l>=1) streams level l-1's
+//                buckets, keeps the keys whose level-(l-1) slot collided (Context::filter, src/lib.rs:443-452;
+//                collide slice of the source bucket staged in shared memory) and groups the survivors by their
+//                level-l bucket.  Tile-local binning in shared memory, one global cursor atomicAdd per
+//                (tile, bucket), keys staged in bucket order so the stores are runs.
 //   mark(l)    : one CTA per bucket: (a, collide) slice of the bucket lives in shared memory, the bucket's keys
 //                are streamed once (Context::find_collisions, src/lib.rs:429-434, with ATOMS), then
 //                a & ~collide (the net effect of every a.remove), collide, the per-512-bit popcounts
@@ -27,36 +27,30 @@ namespace bphf {
 constexpr int BK_THREADS = 512;
 constexpr int BK_KPT = 8;
 constexpr int BK_TILE = BK_THREADS * BK_KPT;  // 4096 keys per tile
+constexpr uint32_t BK_POS_BITS = 13;          // position of a key within (tile, bucket): < 4096
 
 // destination of a scatter: level l's bucket regions (or one contiguous list when level l is plain).
-// Bucket b of a bucketed level owns keys[b * cap .. ) and, at the same offsets, loc[]: the key's slot index
-// relative to the bucket's first bit.  mark(l) reads only loc (4 B/key, no hashing); scatter(l+1) reads both,
-// tests collide with loc, and hashes only the survivors for the next level.
+// Bucket b owns keys[b * cap .. b * cap + cursor[b]).
 struct ScatterDst {
-    uint64_t sp0, bits;
-    uint32_t count, cap, range, mul;  // count == 1 for a plain level: one "bucket" = the contiguous key list
+    uint64_t sp0;
+    uint32_t bits, count, cap, shift;  // count == 1 for a plain level: one "bucket" = the contiguous key list
     uint64_t* keys;
-    uint32_t* loc;
     uint32_t* cursor;
 };
 
-__device__ __forceinline__ ScatterDst make_dst(const BuildState* st, uint32_t level, uint64_t* keys, uint32_t* loc,
-                                               uint32_t* cursor) {
+__device__ __forceinline__ ScatterDst make_dst(const BuildState* st, uint32_t level, uint64_t* keys, uint32_t* cursor) {
     const LevelDesc* d = &st->lv[level];
     ScatterDst o;
     o.sp0 = d->sp0;
-    o.bits = d->bits;
+    o.bits = (uint32_t)d->bits;
     o.keys = keys;
-    o.loc = loc;
     o.cursor = cursor;
     if (d->b_range) {
-        o.range = d->b_range;
-        o.mul = (uint32_t)d->b_div;  // ceil(2^32 / range)
+        o.shift = (uint32_t)d->b_shift;
         o.count = d->b_count;
         o.cap = d->b_cap;
     } else {
-        o.range = 0;
-        o.mul = 0;
+        o.shift = 0;
         o.count = 1;
         o.cap = 0xffffffffu;  // bounded by list_cap, checked when the level was set up
     }
@@ -66,59 +60,61 @@ __device__ __forceinline__ ScatterDst make_dst(const BuildState* st, uint32_t le
 // shared-memory carve-up of the scatter stage (dynamic shared memory)
 struct ScatterSmem {
     uint64_t* stage_key;  // [BK_TILE] keys in bucket order
-    uint32_t* stage_loc;  // [BK_TILE] slot index within the bucket
-    uint32_t* stage_off;  // [BK_TILE] destination offset (b * cap + reserved base + position), ~0 = dropped
-    uint32_t* hist;       // [count] keys of this tile per bucket
+    uint32_t* stage_dst;  // [BK_TILE] destination key index of every staged key
+    uint32_t* hist;       // [count] keys of this tile per bucket (zero between tiles)
     uint32_t* sbase;      // [count] exclusive scan of hist (position in the stage)
-    uint32_t* gbase;      // [count] position reserved in the bucket's global region
+    uint32_t* delta;      // [count] destination index - stage position, per bucket
     uint32_t* warp_tot;   // [BK_THREADS / 32]
+    uint32_t* ovf;        // [1] a bucket region overflowed in this CTA
 };
 __host__ __device__ inline size_t scatter_smem_bytes(uint32_t count) {
-    return (size_t)BK_TILE * 16 + (size_t)count * 12 + (BK_THREADS / 32) * 4 + 64;
+    return (size_t)BK_TILE * 12 + (size_t)count * 12 + (BK_THREADS / 32) * 4 + 64;
 }
 __device__ __forceinline__ ScatterSmem carve_scatter(unsigned char* p, uint32_t count) {
     ScatterSmem s;
     s.stage_key = reinterpret_cast<uint64_t*>(p);
     p += (size_t)BK_TILE * 8;
-    s.stage_loc = reinterpret_cast<uint32_t*>(p);
-    p += (size_t)BK_TILE * 4;
-    s.stage_off = reinterpret_cast<uint32_t*>(p);
+    s.stage_dst = reinterpret_cast<uint32_t*>(p);
     p += (size_t)BK_TILE * 4;
     s.hist = reinterpret_cast<uint32_t*>(p);
     p += (size_t)count * 4;
     s.sbase = reinterpret_cast<uint32_t*>(p);
     p += (size_t)count * 4;
-    s.gbase = reinterpret_cast<uint32_t*>(p);
+    s.delta = reinterpret_cast<uint32_t*>(p);
     p += (size_t)count * 4;
     s.warp_tot = reinterpret_cast<uint32_t*>(p);
+    p += (BK_THREADS / 32) * 4;
+    s.ovf = reinterpret_cast<uint32_t*>(p);
     return s;
 }
 
 // One tile: every thread brings up to BK_KPT keys (valid mask); they are hashed for the destination level, binned
 // by destination bucket and written to the bucket regions as runs.  Must be called by all BK_THREADS threads.
-// hist[] must be zero on entry and is zero again on exit.
+// hist[] must be zero on entry and is zero again on exit.  Three block barriers per tile; the stage is protected
+// from the next tile by that tile's first barrier.
 __device__ __forceinline__ void scatter_tile(BuildState* st, const ScatterDst& dst, const ScatterSmem& sm,
                                              const uint64_t (&key)[BK_KPT], uint32_t valid) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    uint32_t bp[BK_KPT], loc[BK_KPT];  // bp = bucket << 16 | position within (tile, bucket); both < 4096
+    uint32_t bp[BK_KPT];  // bucket << 13 | position within (tile, bucket)
+    if (dst.count > 1) {
 #pragma unroll
-    for (int j = 0; j < BK_KPT; j++) {
-        bp[j] = 0;
-        loc[j] = 0;
-        if (valid & (1u << j)) {
-            uint32_t b = 0;
-            if (dst.count > 1) {
-                const uint32_t idx = hashmod_small(dst.sp0, key[j], (uint32_t)dst.bits);
-                // idx / range with mul = ceil(2^32 / range): the estimate is exact or one too high
-                b = __umulhi(idx, dst.mul);
-                uint32_t l = idx - b * dst.range;
-                if ((int32_t)l < 0) {
-                    b -= 1;
-                    l += dst.range;
-                }
-                loc[j] = l;
+        for (int j = 0; j < BK_KPT; j++) {
+            bp[j] = 0;
+            if (valid & (1u << j)) {
+                const uint32_t b = hashmod_small(dst.sp0, key[j], dst.bits) >> dst.shift;
+                bp[j] = (b << BK_POS_BITS) | atomicAdd(&sm.hist[b], 1u);
             }
-            bp[j] = (b << 16) | atomicAdd(&sm.hist[b], 1u);
+        }
+    } else {
+        // plain destination list: one bucket, position by warp ballot (all lanes would hit the same counter)
+#pragma unroll
+        for (int j = 0; j < BK_KPT; j++) {
+            const bool v = (valid >> j) & 1u;
+            const uint32_t m = __ballot_sync(0xffffffffu, v);
+            uint32_t base = 0;
+            if (lane == 0 && m) base = atomicAdd(&sm.hist[0], (uint32_t)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            bp[j] = base + __popc(m & ((1u << lane) - 1u));
         }
     }
     __syncthreads();
@@ -145,59 +141,52 @@ __device__ __forceinline__ void scatter_tile(BuildState* st, const ScatterDst& d
     uint32_t run = woff + incl - sum;
     for (uint32_t b = b0; b < b1; b++) {
         const uint32_t h = sm.hist[b];
-        sm.sbase[b] = run;
-        run += h;
         if (h) {
             const uint32_t g = atomicAdd(dst.cursor + (size_t)b * CURSOR_STRIDE, h);
-            sm.gbase[b] = g;
-            if ((uint64_t)g + h > dst.cap) st->status = ST_BUCKET_OVERFLOW;  // region too small: host rebuilds unbucketed
+            if ((uint64_t)g + h > dst.cap) {  // region too small: host rebuilds unbucketed
+                st->status = ST_BUCKET_OVERFLOW;
+                *sm.ovf = 1;
+            }
+            sm.sbase[b] = run;
+            sm.delta[b] = (dst.count > 1 ? b * dst.cap : 0u) + g - run;
             sm.hist[b] = 0;
+            run += h;
         }
     }
     __syncthreads();
-    const uint32_t region = dst.count > 1 ? dst.cap : 0;
 #pragma unroll
     for (int j = 0; j < BK_KPT; j++) {
         if (valid & (1u << j)) {
-            const uint32_t b = bp[j] >> 16, ps = bp[j] & 0xffffu;
-            const uint32_t s = sm.sbase[b] + ps;
-            const uint32_t o = sm.gbase[b] + ps;
+            const uint32_t b = dst.count > 1 ? (bp[j] >> BK_POS_BITS) : 0u;
+            const uint32_t s = sm.sbase[b] + (dst.count > 1 ? (bp[j] & ((1u << BK_POS_BITS) - 1u)) : bp[j]);
             sm.stage_key[s] = key[j];
-            sm.stage_loc[s] = loc[j];
-            sm.stage_off[s] = (o < dst.cap) ? b * region + o : 0xffffffffu;
+            sm.stage_dst[s] = sm.delta[b] + s;
         }
     }
     __syncthreads();
-    if (dst.count > 1) {
-        for (uint32_t i = tid; i < total; i += BK_THREADS) {
-            const uint32_t o = sm.stage_off[i];
-            if (o != 0xffffffffu) {
-                dst.keys[o] = sm.stage_key[i];
-                dst.loc[o] = sm.stage_loc[i];
-            }
-        }
-    } else {
-        for (uint32_t i = tid; i < total; i += BK_THREADS) dst.keys[sm.stage_off[i]] = sm.stage_key[i];
+    if (*sm.ovf == 0) {
+        for (uint32_t i = tid; i < total; i += BK_THREADS) dst.keys[sm.stage_dst[i]] = sm.stage_key[i];
     }
-    __syncthreads();
 }
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // -------------------------------------------------------------------------------------------------------
 // scatter0_kernel: input keys [key_begin, key_end) -> level-0 buckets
 // -------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(BK_THREADS, 2)
     scatter0_kernel(BuildState* __restrict__ st, const uint64_t* __restrict__ keys, uint64_t key_begin,
-                    uint64_t key_end, uint64_t* __restrict__ buf0, uint32_t* __restrict__ ibuf0,
-                    uint32_t* __restrict__ cursor0, uint32_t smem_bytes) {
+                    uint64_t key_end, uint64_t* __restrict__ buf0, uint32_t* __restrict__ cursor0, uint32_t smem_bytes) {
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     if (st->status != ST_RUNNING || st->n_levels != 0 || st->lv[0].b_range == 0) return;
-    const ScatterDst dst = make_dst(st, 0, buf0, ibuf0, cursor0);
+    const ScatterDst dst = make_dst(st, 0, buf0, cursor0);
     if (scatter_smem_bytes(dst.count) > smem_bytes) {
         if (threadIdx.x == 0) st->status = ST_BUCKET_OVERFLOW;
         return;
     }
     const ScatterSmem sm = carve_scatter(dyn_smem, dst.count);
     for (uint32_t b = threadIdx.x; b < dst.count; b += BK_THREADS) sm.hist[b] = 0;
+    if (threadIdx.x == 0) *sm.ovf = 0;
     __syncthreads();
     const uint64_t n = key_end - key_begin;
     const uint64_t n_tiles = (n + BK_TILE - 1) / BK_TILE;
@@ -220,14 +209,15 @@ __global__ void __launch_bounds__(BK_THREADS, 2)
                 }
             }
         }
+        // the tile this CTA takes next: pull it into L2 while this one is binned (one 128-byte line per 16 lanes)
+        if ((threadIdx.x & 15) == 0 && tile + gridDim.x < n_tiles) {
+            const uint64_t nb = key_begin + (tile + gridDim.x) * BK_TILE + threadIdx.x;
+#pragma unroll
+            for (int j = 0; j < BK_KPT; j++)
+                if (nb + (uint64_t)j * BK_THREADS < key_end) prefetch_l2(keys + nb + (uint64_t)j * BK_THREADS);
+        }
         scatter_tile(st, dst, sm, key, valid);
     }
-}
-
-__device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
-    return v;
 }
 
 // -------------------------------------------------------------------------------------------------------
@@ -236,18 +226,18 @@ __device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t* p) {
 // -------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(BK_THREADS, 2)
     scatter_kernel(BuildState* __restrict__ st, uint32_t level, uint64_t* __restrict__ buf0,
-                   uint64_t* __restrict__ buf1, uint32_t* __restrict__ ibuf0, uint32_t* __restrict__ ibuf1,
-                   const uint32_t* __restrict__ c32, uint32_t* __restrict__ cursors, uint32_t smem_bytes) {
+                   uint64_t* __restrict__ buf1, const uint32_t* __restrict__ c32, uint32_t* __restrict__ cursors,
+                   uint32_t smem_bytes) {
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     if (st->status != ST_RUNNING || st->n_levels != level || st->lv[level - 1].b_range == 0) return;
     const LevelDesc* pv = &st->lv[level - 1];
-    const uint32_t p_range = pv->b_range, p_count = pv->b_count, p_cap = pv->b_cap;
+    const uint32_t p_range = pv->b_range, p_count = pv->b_count, p_cap = pv->b_cap, p_bits = (uint32_t)pv->bits;
+    const uint64_t p_sp0 = pv->sp0;
     const uint64_t p_off32 = pv->word_off * 2;
     const uint32_t p_words32 = (uint32_t)(round_up8(pv->n_words) * 2);  // u32 words of the (padded) level
     const uint64_t* __restrict__ src = ((level - 1) & 1) ? buf1 : buf0;
-    const uint32_t* __restrict__ src_loc = ((level - 1) & 1) ? ibuf1 : ibuf0;
     const uint32_t* __restrict__ src_cursor = cursors + (size_t)((level - 1) & 1) * MAX_BUCKETS_ALLOC * CURSOR_STRIDE;
-    const ScatterDst dst = make_dst(st, level, (level & 1) ? buf1 : buf0, (level & 1) ? ibuf1 : ibuf0,
+    const ScatterDst dst = make_dst(st, level, (level & 1) ? buf1 : buf0,
                                     cursors + (size_t)(level & 1) * MAX_BUCKETS_ALLOC * CURSOR_STRIDE);
     const size_t c_bytes = (size_t)p_range / 8;
     if (c_bytes + scatter_smem_bytes(dst.count) > smem_bytes) {
@@ -257,6 +247,8 @@ __global__ void __launch_bounds__(BK_THREADS, 2)
     uint32_t* c_sm = reinterpret_cast<uint32_t*>(dyn_smem);
     const ScatterSmem sm = carve_scatter(dyn_smem + c_bytes, dst.count);
     for (uint32_t b = threadIdx.x; b < dst.count; b += BK_THREADS) sm.hist[b] = 0;
+    if (threadIdx.x == 0) *sm.ovf = 0;
+    const uint32_t p_mask = p_range - 1;
 
     for (uint32_t bucket = blockIdx.x; bucket < p_count; bucket += gridDim.x) {
         __syncthreads();
@@ -267,22 +259,24 @@ __global__ void __launch_bounds__(BK_THREADS, 2)
         __syncthreads();
         const uint32_t fill = min(src_cursor[(size_t)bucket * CURSOR_STRIDE], p_cap);
         const uint64_t* __restrict__ bsrc = src + (uint64_t)bucket * p_cap;
-        const uint32_t* __restrict__ lsrc = src_loc + (uint64_t)bucket * p_cap;
         for (uint32_t t0 = 0; t0 < fill; t0 += BK_TILE) {
             uint64_t key[BK_KPT];
-            uint32_t l[BK_KPT];
             uint32_t valid = 0;
 #pragma unroll
             for (int j = 0; j < BK_KPT; j++) {
                 const uint32_t i = t0 + j * BK_THREADS + threadIdx.x;
-                const bool in = i < fill;
-                key[j] = in ? ld_stream_u64(bsrc + i) : 0;
-                l[j] = in ? ld_stream_u32(lsrc + i) : 0xffffffffu;
+                key[j] = 0;
+                if (i < fill) {
+                    key[j] = ld_stream_u64(bsrc + i);
+                    valid |= 1u << j;
+                }
             }
             // Context::filter (src/lib.rs:443-452): the key is redone iff its slot collided
 #pragma unroll
-            for (int j = 0; j < BK_KPT; j++)
-                if (l[j] != 0xffffffffu && ((c_sm[l[j] >> 5] >> (l[j] & 31)) & 1u)) valid |= 1u << j;
+            for (int j = 0; j < BK_KPT; j++) {
+                const uint32_t l = hashmod_small(p_sp0, key[j], p_bits) & p_mask;
+                if (!((c_sm[l >> 5] >> (l & 31)) & 1u)) valid &= ~(1u << j);
+            }
             scatter_tile(st, dst, sm, key, valid);
         }
     }
@@ -297,16 +291,19 @@ __device__ __forceinline__ void mark_smem(uint32_t* a_sm, uint32_t* c_sm, uint32
     if (old & m) atomicOr(&c_sm[idx >> 5], m);
 }
 
+constexpr int MARK_KPT = 8;
+
 __global__ void __launch_bounds__(BK_THREADS)
-    bucket_mark_kernel(BuildState* __restrict__ st, uint32_t level, const uint32_t* __restrict__ ibuf0,
-                       const uint32_t* __restrict__ ibuf1, uint32_t* __restrict__ a32, uint32_t* __restrict__ c32,
+    bucket_mark_kernel(BuildState* __restrict__ st, uint32_t level, const uint64_t* __restrict__ buf0,
+                       const uint64_t* __restrict__ buf1, uint32_t* __restrict__ a32, uint32_t* __restrict__ c32,
                        uint32_t* __restrict__ blockpop, uint32_t* __restrict__ cursors, uint32_t smem_bytes) {
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     __shared__ uint64_t warp_u[BK_THREADS / 32];
     __shared__ bool is_last;
     if (st->status != ST_RUNNING || st->n_levels != level || st->lv[level].b_range == 0) return;
     const LevelDesc* cu = &st->lv[level];
-    const uint32_t range = cu->b_range, count = cu->b_count, cap = cu->b_cap;
+    const uint32_t range = cu->b_range, count = cu->b_count, cap = cu->b_cap, bits = (uint32_t)cu->bits;
+    const uint64_t sp0 = cu->sp0;
     const uint64_t off32 = cu->word_off * 2;
     const uint32_t words32 = (uint32_t)(round_up8(cu->n_words) * 2);
     const uint32_t rw = range / 32;  // u32 words per bucket (multiple of 16)
@@ -316,28 +313,42 @@ __global__ void __launch_bounds__(BK_THREADS)
     }
     uint32_t* a_sm = reinterpret_cast<uint32_t*>(dyn_smem);
     uint32_t* c_sm = a_sm + rw;
-    const uint32_t* __restrict__ src = (level & 1) ? ibuf1 : ibuf0;
+    const uint64_t* __restrict__ src = (level & 1) ? buf1 : buf0;
     const uint32_t* __restrict__ cursor = cursors + (size_t)(level & 1) * MAX_BUCKETS_ALLOC * CURSOR_STRIDE;
     const int lane = threadIdx.x & 31;
+    const uint32_t mask = range - 1;
     uint64_t uniq = 0, seen = 0;
 
     for (uint32_t bucket = blockIdx.x; bucket < count; bucket += gridDim.x) {
         __syncthreads();
-        for (uint32_t w = threadIdx.x; w < 2 * rw; w += BK_THREADS) a_sm[w] = 0;
+        {
+            uint4* z = reinterpret_cast<uint4*>(a_sm);
+            for (uint32_t w = threadIdx.x; w < rw / 2; w += BK_THREADS) z[w] = make_uint4(0, 0, 0, 0);
+        }
         __syncthreads();
         const uint32_t fill = min(cursor[(size_t)bucket * CURSOR_STRIDE], cap);
         if (threadIdx.x == 0) seen += fill;
-        // the bucket's slot indices, 16 bytes (4 keys) per load; cap is a multiple of 32 so the region is aligned
-        const uint4* __restrict__ v4 = reinterpret_cast<const uint4*>(src + (uint64_t)bucket * cap);
-        const uint32_t n4 = fill / 4;
-        for (uint32_t i = threadIdx.x; i < n4; i += BK_THREADS) {
-            const uint4 v = __ldg(v4 + i);
-            mark_smem(a_sm, c_sm, v.x);
-            mark_smem(a_sm, c_sm, v.y);
-            mark_smem(a_sm, c_sm, v.z);
-            mark_smem(a_sm, c_sm, v.w);
+        const uint64_t* __restrict__ bsrc = src + (uint64_t)bucket * cap;
+        for (uint32_t t0 = 0; t0 < fill; t0 += BK_THREADS * MARK_KPT) {
+            uint64_t key[MARK_KPT];
+            if (t0 + BK_THREADS * MARK_KPT <= fill) {
+#pragma unroll
+                for (int j = 0; j < MARK_KPT; j++) key[j] = ld_stream_u64(bsrc + t0 + j * BK_THREADS + threadIdx.x);
+#pragma unroll
+                for (int j = 0; j < MARK_KPT; j++) mark_smem(a_sm, c_sm, hashmod_small(sp0, key[j], bits) & mask);
+            } else {
+#pragma unroll
+                for (int j = 0; j < MARK_KPT; j++) {
+                    const uint32_t i = t0 + j * BK_THREADS + threadIdx.x;
+                    key[j] = (i < fill) ? ld_stream_u64(bsrc + i) : 0;
+                }
+#pragma unroll
+                for (int j = 0; j < MARK_KPT; j++) {
+                    const uint32_t i = t0 + j * BK_THREADS + threadIdx.x;
+                    if (i < fill) mark_smem(a_sm, c_sm, hashmod_small(sp0, key[j], bits) & mask);
+                }
+            }
         }
-        if (threadIdx.x < (fill & 3)) mark_smem(a_sm, c_sm, src[(uint64_t)bucket * cap + n4 * 4 + threadIdx.x]);
         __syncthreads();
         // a &= ~collide; write a and collide slices; popcount per 512-bit block (16 consecutive u32 = 16 lanes)
         const uint32_t w_first = bucket * rw;

@@ -69,7 +69,7 @@ __host__ __device__ inline bool try_make_level(BuildState* st, uint32_t level, u
             st->need = need_keys;
             return false;
         }
-        d.b_div = g.div;
+        d.b_shift = g.shift;
         d.b_range = g.range;
         d.b_count = g.count;
         d.b_cap = g.cap;

@@ -29,8 +29,8 @@ struct LevelDesc {
     // bucketed construction (build only): the level's bit range is cut into b_count buckets of b_range bits
     // (multiple of 512); the keys entering the level are stored grouped by bucket, bucket b at
     // buf[level & 1] + b * b_cap, so one CTA owns a bucket's slice of (a, collide) in shared memory
-    uint64_t b_div;     // ceil(2^32 / b_range): bucket ~ umulhi(idx, b_div), exact or one too high
-    uint32_t b_range;   // 0 = plain level (one contiguous key list, L2-atomic kernels)
+    uint64_t b_shift;   // log2(b_range): bucket = idx >> b_shift
+    uint32_t b_range;   // 0 = plain level (one contiguous key list, L2-atomic kernels); else a power of two
     uint32_t b_count;
     uint32_t b_cap;     // key capacity of each bucket region
     uint32_t pad_;
@@ -98,46 +98,45 @@ struct CommDev {
 };
 
 // ---- bucket geometry --------------------------------------------------------------------------------
-constexpr uint32_t BUCKET_R_MAX = 442368;    // bits per bucket: a + collide = 110,592 B of shared memory -> 2 CTAs / SM
-constexpr uint32_t BUCKET_MAX_COUNT = 4096;  // per-tile histogram / base tables live in shared memory
-constexpr uint32_t MAX_BUCKETS_ALLOC = 4096; // buckets per parity in the cursor array
-// every bucket cursor sits in its own 128-byte line: the per-tile reservations (one atomicAdd per bucket per
-// tile) would otherwise pile onto a handful of L2 slices
-constexpr uint32_t CURSOR_STRIDE = 32;
+// A bucketed level is cut into b_count ranges of 2^b_shift bits (power of two: bucket = idx >> shift, slot within
+// the bucket = idx & (range - 1); a multiple of 512 bits, so a bucket owns whole rank blocks and 64-byte lines).
+constexpr uint32_t BUCKET_SHIFT_MAX = 18;    // 2^18 bits: a + collide = 64 KB of shared memory -> 3 CTAs / SM
+constexpr uint32_t BUCKET_SHIFT_MIN = 10;
+constexpr uint32_t BUCKET_R_MAX = 1u << BUCKET_SHIFT_MAX;
+constexpr uint32_t BUCKET_MAX_COUNT = 8192;  // per-tile histogram / base tables live in shared memory
+constexpr uint32_t MAX_BUCKETS_ALLOC = 8192; // buckets per parity in the cursor array
+// every bucket cursor sits in its own 32-byte sector: the per-tile reservations (one atomicAdd per bucket per
+// tile) would otherwise pile onto a handful of L2 lines
+constexpr uint32_t CURSOR_STRIDE = 8;
 
 struct BucketGeom {
-    uint64_t div;
-    uint32_t range, count, cap;
+    uint32_t shift, range, count, cap;
 };
 
-// range = multiple of 512 bits so buckets own whole rank blocks; count ~ multiple of the concurrent CTA slots
+// count ~ 2..4 x the concurrent CTA slots so every SM stays busy and the tail of the last wave is short
 __host__ __device__ inline bool bucket_geometry(uint64_t bits, uint64_t k, uint32_t slots, uint64_t min_keys,
                                                BucketGeom* g) {
     if (slots == 0 || k < min_keys || (bits >> 32) != 0) return false;
-    if (bits > (uint64_t)BUCKET_R_MAX * BUCKET_MAX_COUNT) return false;
-    uint64_t per_wave = (uint64_t)slots * BUCKET_R_MAX;
-    uint64_t m = (bits + per_wave - 1) / per_wave;
-    uint64_t target = (uint64_t)slots * m;
-    uint64_t range = (bits + target - 1) / target;
-    range = (range + 511) & ~511ULL;
-    if (range < 512) range = 512;
-    if (range > BUCKET_R_MAX) range = BUCKET_R_MAX;
-    uint64_t count = (bits + range - 1) / range;
+    const uint64_t target = 2ull * slots;
+    uint32_t shift = BUCKET_SHIFT_MAX;
+    while (shift > BUCKET_SHIFT_MIN && (bits >> shift) < target) shift--;
+    const uint64_t range = 1ull << shift;
+    const uint64_t count = (bits + range - 1) >> shift;
     if (count > BUCKET_MAX_COUNT) return false;
     // expected fill k * range / bits, + 6 sigma + slack
-    double mean = (double)k * (double)range / (double)bits;
+    const double mean = (double)k * (double)range / (double)bits;
 #ifdef __CUDA_ARCH__
-    double sd = sqrt(mean);
+    const double sd = sqrt(mean);
 #else
-    double sd = __builtin_sqrt(mean);
+    const double sd = __builtin_sqrt(mean);
 #endif
     uint64_t cap = (uint64_t)(mean + 6.0 * sd + 96.0);
     cap = (cap + 31) & ~31ULL;
-    if (cap > 0xffffffffULL) return false;
+    if (cap * count > 0xffffffffULL) return false;  // destinations are 32-bit key indices
+    g->shift = shift;
     g->range = (uint32_t)range;
     g->count = (uint32_t)count;
     g->cap = (uint32_t)cap;
-    g->div = (0xffffffffULL / range) + 1ULL;
     return true;
 }
 
@@ -151,7 +150,7 @@ __host__ __device__ inline void make_level(BuildState* st, uint32_t level, uint6
     d.k_loc = (st->shard_world > 1 && level > 0) ? 0 : k;  // sharded: known once this shard's filter has run
     d.sp0 = seed_xor_p0(st->seed0 + level);
     d.sp0_query = seed_xor_p0(level);
-    d.b_div = 0;
+    d.b_shift = 0;
     d.b_range = d.b_count = d.b_cap = 0;
     d.pad_ = 0;
 }

@@ -44,33 +44,139 @@ __device__ __forceinline__ uint64_t lookup_one(const QLevel* __restrict__ lv, ui
     return BPHF_NONE;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Packed lookup structure.  Random 32-byte-sector accesses are what bounds a lookup on B200 (one sector per clock
+// and SM through the L1 tag stage, measured): the reference layout costs a word probe per visited level plus, on
+// the hit, a rank entry and up to 7 more words (src/lib.rs:299-318) -- 6.5 sectors per key at gamma = 1.7.
+// Here every level is re-packed into 16-byte granules {96 bits of the level, u32 rank of the granule's first bit
+// relative to the level} so that ONE 16-byte load both tests the bit and yields everything get_rank needs:
+//   rank = level_base + granule.rank + popc(full words below) + popc(partial word)
+// which is the same number the reference computes (same bits, same running popcount).  Built on the device
+// right after compute_ranks; used when every level has fewer than 2^32 bits (else the generic kernel runs).
+// ---------------------------------------------------------------------------------------------
+struct QLevelP {
+    uint64_t sp0;        // seed_xor_p0(level index)
+    uint64_t base_rank;  // ranks[first block of the level]: set bits of all previous levels
+    uint64_t gran_off;   // first granule of the level in the packed array
+    uint32_t bits;       // BitVector.capacity() (< 2^32)
+    uint32_t n_gran;     // ceil(bits / 96)
+};
+constexpr uint32_t GRAN_BITS = 96;
+
+__global__ void set_base_rank_kernel(QLevelP* __restrict__ lvp, const QLevel* __restrict__ lv, uint32_t n_levels,
+                                     const uint64_t* __restrict__ ranks) {
+    for (uint32_t l = threadIdx.x; l < n_levels; l += blockDim.x) lvp[l].base_rank = ranks[lv[l].bit_off / 512];
+}
+
+// one thread per granule: 96-bit window of the level's words + popcount of the level below it
+__global__ void __launch_bounds__(256)
+    pack_query_kernel(const QLevelP* __restrict__ lvp, const QLevel* __restrict__ lv, uint32_t n_levels,
+                      const uint64_t* __restrict__ words, const uint64_t* __restrict__ ranks, uint64_t total_gran,
+                      uint4* __restrict__ out) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total_gran; g += stride) {
+        // level of this granule (few levels: linear search from the top is cheap, the big levels come first)
+        uint32_t l = 0;
+        while (l + 1 < n_levels && g >= lvp[l + 1].gran_off) l++;
+        const uint64_t gi = g - lvp[l].gran_off;
+        const uint64_t s = gi * GRAN_BITS;                 // first bit of the granule within the level
+        const uint64_t w0 = lv[l].bit_off / 64;            // first arena word of the level (multiple of 8)
+        const uint64_t n_words = (lv[l].bits + 63) / 64;
+        auto word = [&](uint64_t i) -> uint64_t { return i < n_words ? words[w0 + i] : 0ULL; };
+        const uint64_t wi = s >> 6;
+        const uint32_t sh = (uint32_t)s & 63;
+        const uint64_t a = word(wi), b = word(wi + 1), c = word(wi + 2);
+        uint64_t lo = sh ? ((a >> sh) | (b << (64 - sh))) : a;
+        uint64_t hi = sh ? ((b >> sh) | (c << (64 - sh))) : b;
+        // rank of bit s relative to the level: block rank + words of the block below wi + bits of word wi below sh
+        uint64_t r = ranks[(w0 + wi) / 8] - lvp[l].base_rank;
+        for (uint64_t j = wi & ~7ULL; j < wi; j++) r += __popcll(word(j));
+        if (sh) r += __popcll(a & ((1ULL << sh) - 1ULL));
+        // bits at or beyond the level's capacity are zero already (the build never sets them)
+        out[g] = make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)r);
+    }
+}
+
+__device__ __forceinline__ uint64_t lookup_packed(const QLevelP* __restrict__ lv, uint32_t n_levels,
+                                                  const uint4* __restrict__ q, uint64_t key) {
+    for (uint32_t l = 0; l < n_levels; l++) {
+        const uint32_t idx = hashmod_small(lv[l].sp0, key, lv[l].bits);
+        const uint32_t g = __umulhi(idx >> 5, 0x55555556u);  // (idx / 32) / 3, exact below 2^31
+        const uint32_t bit = idx - g * GRAN_BITS;            // 0..95
+        const uint4 v = __ldg(q + lv[l].gran_off + g);
+        const uint32_t w = bit >> 5;
+        const uint32_t word = w == 0 ? v.x : (w == 1 ? v.y : v.z);
+        const uint32_t sh = bit & 31;
+        if ((word >> sh) & 1u) {
+            uint32_t below = __popc(word & ((1u << sh) - 1u));
+            if (w > 0) below += __popc(v.x);
+            if (w > 1) below += __popc(v.y);
+            return lv[l].base_rank + v.w + below;
+        }
+    }
+    return BPHF_NONE;
+}
+
+// handle-side view of either layout
+struct QView {
+    const QLevel* lv;
+    const QLevelP* lvp;  // non-null: packed layout available
+    const uint64_t* words;
+    const uint64_t* ranks;
+    const uint4* packed;
+    uint32_t n_levels;
+};
+
+// level table in shared memory + the lookup of either layout
+template <bool PACKED>
+struct LevelTab;
+template <>
+struct LevelTab<false> {
+    QLevel lv[BPHF_MAX_LEVELS + 1];
+    __device__ __forceinline__ void load(const QView& v) {
+        for (uint32_t i = threadIdx.x; i < v.n_levels; i += blockDim.x) lv[i] = v.lv[i];
+    }
+    __device__ __forceinline__ uint64_t lookup(const QView& v, uint64_t key) const {
+        return lookup_one(lv, v.n_levels, v.words, v.ranks, key);
+    }
+};
+template <>
+struct LevelTab<true> {
+    QLevelP lv[BPHF_MAX_LEVELS + 1];
+    __device__ __forceinline__ void load(const QView& v) {
+        for (uint32_t i = threadIdx.x; i < v.n_levels; i += blockDim.x) lv[i] = v.lvp[i];
+    }
+    __device__ __forceinline__ uint64_t lookup(const QView& v, uint64_t key) const {
+        return lookup_packed(lv, v.n_levels, v.packed, key);
+    }
+};
+
+// Mphf::hash / try_hash over a batch (src/lib.rs:324-355)
+template <bool PACKED>
 __global__ void __launch_bounds__(QUERY_THREADS)
-    query_kernel(const QLevel* __restrict__ lv_g, uint32_t n_levels, const uint64_t* __restrict__ words,
-                 const uint64_t* __restrict__ ranks, const uint64_t* __restrict__ keys, uint64_t n,
-                 uint64_t* __restrict__ out) {
-    __shared__ QLevel lv[BPHF_MAX_LEVELS + 1];
-    for (uint32_t i = threadIdx.x; i < n_levels; i += QUERY_THREADS) lv[i] = lv_g[i];
+    query_kernel(QView v, const uint64_t* __restrict__ keys, uint64_t n, uint64_t* __restrict__ out) {
+    __shared__ LevelTab<PACKED> tab;
+    tab.load(v);
     __syncthreads();
     const uint64_t stride = (uint64_t)gridDim.x * QUERY_THREADS;
-    for (uint64_t i = (uint64_t)blockIdx.x * QUERY_THREADS + threadIdx.x; i < n; i += stride) {
-        out[i] = lookup_one(lv, n_levels, words, ranks, keys[i]);
-    }
+    for (uint64_t i = (uint64_t)blockIdx.x * QUERY_THREADS + threadIdx.x; i < n; i += stride)
+        out[i] = tab.lookup(v, keys[i]);
 }
 
 // create_map as an out-of-place scatter: keys_out[hash(k)] = k, values_out[hash(k)] = v.
 // bad counts keys whose hash is None or >= n (a key outside the construction set)
+template <bool PACKED>
 __global__ void __launch_bounds__(QUERY_THREADS)
-    map_permute_kernel(const QLevel* __restrict__ lv_g, uint32_t n_levels, const uint64_t* __restrict__ words,
-                       const uint64_t* __restrict__ ranks, const uint64_t* __restrict__ keys,
-                       const uint64_t* __restrict__ values, uint64_t n, uint64_t* __restrict__ keys_out,
-                       uint64_t* __restrict__ values_out, unsigned long long* __restrict__ bad) {
-    __shared__ QLevel lv[BPHF_MAX_LEVELS + 1];
-    for (uint32_t i = threadIdx.x; i < n_levels; i += QUERY_THREADS) lv[i] = lv_g[i];
+    map_permute_kernel(QView v, const uint64_t* __restrict__ keys, const uint64_t* __restrict__ values, uint64_t n,
+                       uint64_t* __restrict__ keys_out, uint64_t* __restrict__ values_out,
+                       unsigned long long* __restrict__ bad) {
+    __shared__ LevelTab<PACKED> tab;
+    tab.load(v);
     __syncthreads();
     const uint64_t stride = (uint64_t)gridDim.x * QUERY_THREADS;
     for (uint64_t i = (uint64_t)blockIdx.x * QUERY_THREADS + threadIdx.x; i < n; i += stride) {
         const uint64_t k = keys[i];
-        const uint64_t pos = lookup_one(lv, n_levels, words, ranks, k);
+        const uint64_t pos = tab.lookup(v, k);
         if (pos >= n) {
             atomicAdd(bad, 1ULL);
             continue;
@@ -81,18 +187,18 @@ __global__ void __launch_bounds__(QUERY_THREADS)
 }
 
 // BoomHashMap::get over a batch
+template <bool PACKED>
 __global__ void __launch_bounds__(QUERY_THREADS)
-    map_get_kernel(const QLevel* __restrict__ lv_g, uint32_t n_levels, const uint64_t* __restrict__ words,
-                   const uint64_t* __restrict__ ranks, const uint64_t* __restrict__ map_keys,
-                   const uint64_t* __restrict__ map_values, uint64_t n_map, const uint64_t* __restrict__ queries,
-                   uint64_t nq, uint64_t* __restrict__ values_out, uint8_t* __restrict__ found_out) {
-    __shared__ QLevel lv[BPHF_MAX_LEVELS + 1];
-    for (uint32_t i = threadIdx.x; i < n_levels; i += QUERY_THREADS) lv[i] = lv_g[i];
+    map_get_kernel(QView v, const uint64_t* __restrict__ map_keys, const uint64_t* __restrict__ map_values,
+                   uint64_t n_map, const uint64_t* __restrict__ queries, uint64_t nq, uint64_t* __restrict__ values_out,
+                   uint8_t* __restrict__ found_out) {
+    __shared__ LevelTab<PACKED> tab;
+    tab.load(v);
     __syncthreads();
     const uint64_t stride = (uint64_t)gridDim.x * QUERY_THREADS;
     for (uint64_t i = (uint64_t)blockIdx.x * QUERY_THREADS + threadIdx.x; i < nq; i += stride) {
         const uint64_t q = queries[i];
-        const uint64_t pos = lookup_one(lv, n_levels, words, ranks, q);
+        const uint64_t pos = tab.lookup(v, q);
         const bool found = pos < n_map && __ldg(map_keys + pos) == q;
         values_out[i] = found ? (map_values ? __ldg(map_values + pos) : pos) : 0;
         found_out[i] = found ? 1 : 0;
