@@ -170,6 +170,9 @@ BPHF_API int bphf_set_profile(int level);
  * by bit range ("bucketed"), levels with fewer than bucket_min_keys keys (0 = default 2^20) by L2 atomics;
  * mode 1 = L2-atomic kernels only.  Both produce identical structures. */
 BPHF_API int bphf_set_build_mode(int mode, uint64_t bucket_min_keys);
+/* lookup strategy (measurement only; identical results): 0 (default) = level-synchronous kernel over the packed
+ * lookup structure, 1 = one thread per key over the same structure */
+BPHF_API int bphf_set_query_mode(int mode);
 
 /* ---- utilities used by tests and bench (device side) ------------------------------------ */
 /* distinct-by-construction synthetic keys: kind 0 = splitmix64 finaliser of

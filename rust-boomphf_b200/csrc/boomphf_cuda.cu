@@ -64,6 +64,7 @@ struct DeviceInfo {
 static DeviceInfo g_dev[MAX_DEVICES];
 static std::mutex g_dev_mutex;
 static int g_profile = 0;
+static int g_query_mode = 0;  // 0: level-synchronous packed kernel, 1: thread-per-key packed kernel (measurement)
 
 static const DeviceInfo& device_info(int dev) {
     if (dev < 0 || dev >= MAX_DEVICES) throw CudaFailure{BPHF_ERR_ARG, "device ordinal out of range"};
@@ -100,7 +101,7 @@ static const DeviceInfo& device_info(int dev) {
                 (const void*)scatter0_kernel, (const void*)scatter_kernel, (const void*)bucket_mark_kernel,
                 (const void*)query_kernel<false>, (const void*)query_kernel<true>, (const void*)map_permute_kernel<false>,
                 (const void*)map_permute_kernel<true>, (const void*)map_get_kernel<false>, (const void*)map_get_kernel<true>,
-                (const void*)pack_query_kernel, (const void*)set_base_rank_kernel,
+                (const void*)pack_query_kernel, (const void*)set_base_rank_kernel, (const void*)query_sync_kernel,
                 (const void*)keygen_kernel, (const void*)check_perm_kernel, (const void*)checksum_kernel,
                 (const void*)shard_barrier_kernel, (const void*)or_collide_merge_kernel, (const void*)tail_gather_kernel};
             for (const void* k : all_kernels) CK(cudaFuncGetAttributes(&fa, k));
@@ -898,6 +899,11 @@ BPHF_API int bphf_set_build_mode(int mode, uint64_t bucket_min_keys) {
     return BPHF_OK;
 }
 
+BPHF_API int bphf_set_query_mode(int mode) {
+    g_query_mode = mode == 1 ? 1 : 0;
+    return BPHF_OK;
+}
+
 BPHF_API int bphf_set_profile(int level) {
     g_profile = level < 0 ? 0 : (level > 2 ? 2 : level);
     return BPHF_OK;
@@ -1170,7 +1176,17 @@ static int query_grid(const DeviceInfo& info, uint64_t n) {
 
 static void launch_query(const bphf_mphf* m, const DeviceInfo& info, const uint64_t* keys, uint64_t n, uint64_t* out, cudaStream_t s) {
     const QView v = query_view(m);
-    if (v.lvp) query_kernel<true><<<query_grid(info, n), QUERY_THREADS, 0, s>>>(v, keys, n, out);
+    if (v.lvp && g_query_mode == 0) {
+        const uint64_t tiles = (n + (uint64_t)QS_WTILE * QS_WARPS - 1) / ((uint64_t)QS_WTILE * QS_WARPS);
+        // persistent CTAs: exactly one wave of resident CTAs, each walks tiles blockIdx, +gridDim, ...
+        static int per_sm = 0;
+        if (!per_sm) {
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, query_sync_kernel, QS_THREADS, 0));
+            if (per_sm < 1) per_sm = 1;
+        }
+        const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(tiles, (uint64_t)info.sm_count * per_sm));
+        query_sync_kernel<<<grid, QS_THREADS, 0, s>>>(v, keys, n, out);
+    } else if (v.lvp) query_kernel<true><<<query_grid(info, n), QUERY_THREADS, 0, s>>>(v, keys, n, out);
     else query_kernel<false><<<query_grid(info, n), QUERY_THREADS, 0, s>>>(v, keys, n, out);
     CK(cudaGetLastError());
 }

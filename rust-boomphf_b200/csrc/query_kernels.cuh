@@ -117,6 +117,28 @@ __device__ __forceinline__ uint64_t lookup_packed(const QLevelP* __restrict__ lv
     return BPHF_NONE;
 }
 
+// one probe of the packed layout: does `key` own a bit in level `lv`?  rank is valid on a hit
+struct PackedProbe {
+    uint32_t g, bit;
+};
+__device__ __forceinline__ PackedProbe packed_slot(const QLevelP& lv, uint64_t key) {
+    const uint32_t idx = hashmod_small(lv.sp0, key, lv.bits);
+    PackedProbe p;
+    p.g = __umulhi(idx >> 5, 0x55555556u);
+    p.bit = idx - p.g * GRAN_BITS;
+    return p;
+}
+__device__ __forceinline__ bool packed_hit(const QLevelP& lv, const uint4 v, uint32_t bit, uint64_t* rank) {
+    const uint32_t w = bit >> 5;
+    const uint32_t word = w == 0 ? v.x : (w == 1 ? v.y : v.z);
+    const uint32_t sh = bit & 31;
+    uint32_t below = __popc(word & ((1u << sh) - 1u));
+    if (w > 0) below += __popc(v.x);
+    if (w > 1) below += __popc(v.y);
+    *rank = lv.base_rank + v.w + below;
+    return (word >> sh) & 1u;
+}
+
 // handle-side view of either layout
 struct QView {
     const QLevel* lv;
@@ -161,6 +183,132 @@ __global__ void __launch_bounds__(QUERY_THREADS)
     const uint64_t stride = (uint64_t)gridDim.x * QUERY_THREADS;
     for (uint64_t i = (uint64_t)blockIdx.x * QUERY_THREADS + threadIdx.x; i < n; i += stride)
         out[i] = tab.lookup(v, keys[i]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// query_sync_kernel: the level walk of Mphf::hash (src/lib.rs:325-332) run level-synchronously per WARP.
+// A thread-per-key walk leaves ~11 of 32 lanes active (a warp lasts as long as its deepest key, and the hash is
+// re-evaluated per level).  Here a warp takes a tile of QS_WTILE keys, probes level 0 for all of them (independent
+// loads), and the keys that missed are compacted into a per-warp index queue in shared memory; round l probes
+// level l for the queue with full lanes.  The last few stragglers walk the remaining levels one per lane.
+// No block barrier anywhere: warps drift apart and hide each other's latency.  Results are staged in shared
+// memory and written coalesced.
+// ---------------------------------------------------------------------------------------------
+constexpr int QS_THREADS = 256;
+constexpr int QS_WARPS = QS_THREADS / 32;
+constexpr int QS_KPL = 8;                    // keys per lane per tile
+constexpr int QS_WTILE = 32 * QS_KPL;        // 256 keys per warp tile: 2 KB of results + 2 x 512 B of queues
+constexpr int QS_TILE = QS_WTILE;            // (host: tiles are per warp)
+constexpr uint32_t QS_STRAGGLERS = 8;        // at most this many keys left: one lane each walks the rest
+
+// append lane's entry to the warp's queue; returns the new count (uniform)
+__device__ __forceinline__ uint32_t wqueue_append(bool miss, uint32_t i, uint16_t* __restrict__ q, uint32_t count) {
+    const uint32_t m = __ballot_sync(0xffffffffu, miss);
+    const int lane = threadIdx.x & 31;
+    if (miss) q[count + __popc(m & ((1u << lane) - 1u))] = (uint16_t)i;
+    return count + __popc(m);
+}
+
+__global__ void __launch_bounds__(QS_THREADS, 5)
+    query_sync_kernel(QView v, const uint64_t* __restrict__ keys, uint64_t n, uint64_t* __restrict__ out) {
+    __shared__ QLevelP lv[BPHF_MAX_LEVELS + 1];
+    __shared__ uint64_t res_all[QS_WARPS][QS_WTILE];      // key while unresolved, rank (or NONE) once resolved
+    __shared__ uint16_t queue_all[QS_WARPS][2][QS_WTILE];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (uint32_t i = tid; i < v.n_levels; i += QS_THREADS) lv[i] = v.lvp[i];
+    __syncthreads();
+    uint64_t* __restrict__ res = res_all[warp];
+    const uint4* __restrict__ q = v.packed;
+    const uint32_t n_levels = v.n_levels;
+    const uint64_t n_tiles = (n + QS_WTILE - 1) / QS_WTILE;
+    const uint64_t w_stride = (uint64_t)gridDim.x * QS_WARPS;
+    for (uint64_t tile = (uint64_t)blockIdx.x * QS_WARPS + warp; tile < n_tiles; tile += w_stride) {
+        const uint64_t base = tile * QS_WTILE;
+        const uint32_t t_n = (uint32_t)min((uint64_t)QS_WTILE, n - base);
+        uint32_t n_q = 0;
+        // ---- round 0: every key of the tile against level 0 (batches of 4 independent probes per lane)
+#pragma unroll
+        for (int h = 0; h < QS_KPL; h += 4) {
+            uint64_t key[4];
+            PackedProbe pp[4];
+            uint4 g[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint32_t i = (h + j) * 32 + lane;
+                key[j] = i < t_n ? keys[base + i] : 0;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                pp[j] = packed_slot(lv[0], key[j]);
+                g[j] = __ldg(q + lv[0].gran_off + pp[j].g);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint32_t i = (h + j) * 32 + lane;
+                uint64_t rank;
+                const bool hit = packed_hit(lv[0], g[j], pp[j].bit, &rank);
+                res[i] = hit ? rank : key[j];
+                n_q = wqueue_append(!hit && i < t_n, i, queue_all[warp][1], n_q);
+            }
+        }
+        __syncwarp();
+        // ---- round r: the queue against level r, two entries per lane in flight
+        uint32_t r = 1;
+        for (; r < n_levels && n_q > QS_STRAGGLERS; r++) {
+            const uint16_t* __restrict__ qin = queue_all[warp][r & 1];
+            uint16_t* __restrict__ qout = queue_all[warp][(r + 1) & 1];
+            const QLevelP L = lv[r];
+            uint32_t n_out = 0;
+            for (uint32_t t0 = 0; t0 < n_q; t0 += 64) {
+                uint32_t i[2];
+                uint64_t key[2];
+                PackedProbe pp[2];
+                uint4 g[2];
+                bool live[2];
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    const uint32_t t = t0 + j * 32 + lane;
+                    live[j] = t < n_q;
+                    i[j] = live[j] ? qin[t] : 0;
+                    key[j] = res[i[j]];
+                    pp[j] = packed_slot(L, key[j]);
+                    g[j] = __ldg(q + L.gran_off + pp[j].g);
+                }
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    uint64_t rank;
+                    const bool hit = packed_hit(L, g[j], pp[j].bit, &rank);
+                    if (live[j] && hit) res[i[j]] = rank;
+                    n_out = wqueue_append(live[j] && !hit, i[j], qout, n_out);
+                }
+            }
+            n_q = n_out;
+            __syncwarp();
+        }
+        // ---- stragglers: one lane per key walks the remaining levels; None when no level claims the key
+        if ((uint32_t)lane < n_q) {
+            const uint32_t i = queue_all[warp][r & 1][lane];
+            const uint64_t key = res[i];
+            uint64_t rank = BPHF_NONE;
+            for (uint32_t l = r; l < n_levels; l++) {
+                const PackedProbe pp = packed_slot(lv[l], key);
+                const uint4 g = __ldg(q + lv[l].gran_off + pp.g);
+                uint64_t rk;
+                if (packed_hit(lv[l], g, pp.bit, &rk)) {
+                    rank = rk;
+                    break;
+                }
+            }
+            res[i] = rank;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < QS_KPL; j++) {
+            const uint32_t i = j * 32 + lane;
+            if (i < t_n) out[base + i] = res[i];
+        }
+        __syncwarp();
+    }
 }
 
 // create_map as an out-of-place scatter: keys_out[hash(k)] = k, values_out[hash(k)] = v.
