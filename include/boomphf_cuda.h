@@ -161,14 +161,18 @@ typedef struct bphf_build_stats {
     uint32_t bucketed_levels;              /* levels built by the shared-memory (bucketed) kernels  */
     uint32_t rebuilds;                     /* 1 when a bucket overflow forced an unbucketed rebuild */
     float merge_ms[BPHF_MAX_LEVELS + 1];   /* sharded build: barrier + OR-collide merge + barrier (profile 2) */
+    float cascade_ms;                      /* persistent kernel that runs every level >= 1 (build mode 0)     */
 } bphf_build_stats;
 BPHF_API int bphf_get_build_stats(const bphf_mphf *m, bphf_build_stats *out);
 /* 0: no events; 1: CUDA events around the kernels of levels 0 and 1; 2: around every kernel.
  * pass_ms[l] = entry step of level l (scatter / filter+mark), fin_ms[l] = completion step (bucket mark / finalize) */
 BPHF_API int bphf_set_profile(int level);
-/* construction strategy: mode 0 (default) = large levels are built in shared memory after grouping the keys
- * by bit range ("bucketed"), levels with fewer than bucket_min_keys keys (0 = default 2^20) by L2 atomics;
- * mode 1 = L2-atomic kernels only.  Both produce identical structures. */
+/* construction strategy (all produce identical structures):
+ *   mode 0 (default) = L2-atomic kernels; every level >= 1 runs inside one persistent, cooperatively launched
+ *                      kernel with grid-wide barriers (no per-level launch gaps);
+ *   mode 1           = L2-atomic kernels, two launches per level (what a sharded build uses between its merges);
+ *   mode 2           = large levels are built in shared memory after grouping the keys by bit range ("bucketed"),
+ *                      levels with fewer than bucket_min_keys keys (0 = default 2^20) by the mode-1 kernels. */
 BPHF_API int bphf_set_build_mode(int mode, uint64_t bucket_min_keys);
 /* lookup strategy (measurement only; identical results): 0 (default) = level-synchronous kernel over the packed
  * lookup structure, 1 = one thread per key over the same structure */

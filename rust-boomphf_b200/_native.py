@@ -54,6 +54,7 @@ class BuildStats(C.Structure):
         ("bucketed_levels", C.c_uint32),
         ("rebuilds", C.c_uint32),
         ("merge_ms", C.c_float * (MAX_LEVELS + 1)),
+        ("cascade_ms", C.c_float),
     ]
 
 

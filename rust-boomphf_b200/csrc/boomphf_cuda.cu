@@ -97,6 +97,7 @@ static const DeviceInfo& device_info(int dev) {
             const void* all_kernels[] = {
                 (const void*)mark_list_kernel<false>, (const void*)mark_list_kernel<true>, (const void*)pass_kernel<false>,
                 (const void*)pass_kernel<true>, (const void*)finalize_kernel, (const void*)tail_kernel,
+                (const void*)cascade_kernel<false>, (const void*)cascade_kernel<true>,
                 (const void*)scan_sums_kernel, (const void*)scan_top_kernel, (const void*)scan_apply_kernel,
                 (const void*)scatter0_kernel, (const void*)scatter_kernel, (const void*)bucket_mark_kernel,
                 (const void*)query_kernel<false>, (const void*)query_kernel<true>, (const void*)map_permute_kernel<false>,
@@ -256,7 +257,9 @@ struct Plan {
     bool maybe_big = false;
 };
 
-static int g_build_mode = 0;                      // 0 auto (bucketed prefix), 1 plain L2-atomic kernels only
+// 0: L2-atomic kernels, levels >= 1 in one persistent cascade kernel (default, fastest measured)
+// 1: L2-atomic kernels, two launches per level   2: bucketed shared-memory kernels for the large levels
+static int g_build_mode = 0;
 static uint64_t g_bucket_min_keys = 1ull << 20;   // levels below this are built by the plain kernels
 
 static Plan make_plan(uint64_t n, double gamma, uint32_t slots, bool bucket_enable, uint64_t min_keys) {
@@ -370,7 +373,7 @@ struct Builder {
     uint32_t slots() const { return (uint32_t)info.sm_count * 2; }
 
     size_t begin_event(int kind, uint32_t level) {
-        const bool want = profile >= 2 || (profile == 1 && kind <= 1 && level <= 1);
+        const bool want = profile >= 2 || (profile == 1 && ((kind <= 1 && level <= 1) || kind == 5));
         if (!want) return (size_t)-1;
         EventPair e;
         e.kind = kind;
@@ -470,6 +473,24 @@ struct Builder {
                                                  (uint64_t)max_grid());
         finalize_kernel<<<grid, FIN_THREADS, 0, s>>>(d_state, level, d_words, d_coll, d_blockpop);
         CK(cudaGetLastError());
+        launches++;
+    }
+    // levels >= 1 of an unsharded L2-atomic build: one cooperative launch, every CTA resident
+    bool use_cascade() const { return !comm && !hst.bucket_enable && g_build_mode == 0; }
+    void launch_cascade() {
+        static int per_sm[2] = {0, 0};
+        const int v = maybe_big ? 1 : 0;
+        if (!per_sm[v]) {
+            int n = 0;
+            if (maybe_big) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, cascade_kernel<true>, PASS_THREADS, 0));
+            else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, cascade_kernel<false>, PASS_THREADS, 0));
+            per_sm[v] = std::max(1, std::min(n, 8));
+        }
+        const size_t ev = begin_event(5, 0);
+        void* args[] = {(void*)&d_state, (void*)&d_keys, (void*)&d_buf[0], (void*)&d_buf[1], (void*)&d_words, (void*)&d_coll, (void*)&d_blockpop};
+        const void* fn = maybe_big ? (const void*)cascade_kernel<true> : (const void*)cascade_kernel<false>;
+        CK(cudaLaunchCooperativeKernel(fn, dim3(info.sm_count * per_sm[v]), dim3(PASS_THREADS), args, 0, s));
+        end_event(ev);
         launches++;
     }
     void launch_tail() {
@@ -678,7 +699,11 @@ static int build_once(const uint64_t* keys, uint64_t n, double gamma, int has_se
     if (lps.empty()) lps.push_back(lp0);
     else lps[0] = lp0;
     b.launch_level(0, nullptr, lps[0]);
-    for (uint32_t l = 1; l < lps.size(); l++) b.launch_level(l, &lps[l - 1], lps[l]);
+    if (b.use_cascade()) {
+        if (lps.size() > 1) b.launch_cascade();
+    } else {
+        for (uint32_t l = 1; l < lps.size(); l++) b.launch_level(l, &lps[l - 1], lps[l]);
+    }
     // the first tail-owned level right after a bucketed one gets its keys from the scatter step as a plain list
     if (lps.back().maybe_bucket)
         b.launch_scatter((uint32_t)lps.size(), lps.back().range_max, lps.back().count_max, 1);
@@ -722,6 +747,10 @@ static int build_once(const uint64_t* keys, uint64_t n, double gamma, int has_se
             b.upload_state();
         } else if (st.status != ST_RUNNING) {
             return fail(BPHF_ERR_INTERNAL, "unknown build status");
+        }
+        if (b.use_cascade()) {
+            b.launch_cascade();
+            continue;
         }
         // enqueue a few more levels from where the device stopped (k only shrinks from here); both kernel
         // families are enqueued because the modes of the coming levels are decided on the device
@@ -808,6 +837,7 @@ static int build_once(const uint64_t* keys, uint64_t n, double gamma, int has_se
         else if (e.kind == 2) bs.tail_ms += ms;
         else if (e.kind == 3) bs.ranks_ms += ms;
         else if (e.kind == 4 && e.level <= BPHF_MAX_LEVELS) bs.merge_ms[e.level] += ms;
+        else if (e.kind == 5) bs.cascade_ms += ms;
     }
     bs.h2d_ms = 0.f;
     uint32_t nb = 0;
@@ -826,7 +856,7 @@ static int build_impl(const uint64_t* keys, uint64_t n, double gamma, int has_se
     if (keys_mem != BPHF_MEM_HOST && keys_mem != BPHF_MEM_DEVICE) return fail(BPHF_ERR_ARG, "bad keys_mem");
     // assert!(gamma > 1.01)  src/lib.rs:236,364  (NaN fails the assertion too)
     if (!(gamma > 1.01)) return fail(BPHF_ERR_GAMMA, "assertion failed: gamma > 1.01");
-    int rc = build_once(keys, n, gamma, has_seed, seed, device, keys_mem, stream, g_build_mode == 0, 0, out);
+    int rc = build_once(keys, n, gamma, has_seed, seed, device, keys_mem, stream, g_build_mode == 2, 0, out);
     if (rc == BUILD_RETRY_PLAIN) {
         // a bucket region overflowed (heavily duplicated or otherwise non-random input): the plain L2-atomic
         // kernels have no such limit.  Still the GPU path -- there is no CPU fallback anywhere.
@@ -894,7 +924,7 @@ BPHF_API int bphf_device_count(int* count) {
 }
 
 BPHF_API int bphf_set_build_mode(int mode, uint64_t bucket_min_keys) {
-    g_build_mode = mode == 1 ? 1 : 0;
+    g_build_mode = (mode == 1 || mode == 2) ? mode : 0;
     g_bucket_min_keys = bucket_min_keys ? bucket_min_keys : (1ull << 20);
     return BPHF_OK;
 }

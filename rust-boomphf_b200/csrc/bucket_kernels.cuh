@@ -68,7 +68,7 @@ struct ScatterSmem {
     uint32_t* ovf;        // [1] a bucket region overflowed in this CTA
 };
 __host__ __device__ inline size_t scatter_smem_bytes(uint32_t count) {
-    return (size_t)BK_TILE * 12 + (size_t)count * 12 + (BK_THREADS / 32) * 4 + 64;
+    return (size_t)BK_TILE * 12 + (size_t)((count + 3) & ~3u) * 12 + (BK_THREADS / 32) * 4 + 64;
 }
 __device__ __forceinline__ ScatterSmem carve_scatter(unsigned char* p, uint32_t count) {
     ScatterSmem s;
@@ -76,22 +76,24 @@ __device__ __forceinline__ ScatterSmem carve_scatter(unsigned char* p, uint32_t 
     p += (size_t)BK_TILE * 8;
     s.stage_dst = reinterpret_cast<uint32_t*>(p);
     p += (size_t)BK_TILE * 4;
+    const size_t padded = (size_t)((count + 3) & ~3u);  // tables are read / written two entries at a time
     s.hist = reinterpret_cast<uint32_t*>(p);
-    p += (size_t)count * 4;
+    p += padded * 4;
     s.sbase = reinterpret_cast<uint32_t*>(p);
-    p += (size_t)count * 4;
+    p += padded * 4;
     s.delta = reinterpret_cast<uint32_t*>(p);
-    p += (size_t)count * 4;
+    p += padded * 4;
     s.warp_tot = reinterpret_cast<uint32_t*>(p);
     p += (BK_THREADS / 32) * 4;
     s.ovf = reinterpret_cast<uint32_t*>(p);
     return s;
 }
 
-// One tile: every thread brings up to BK_KPT keys (valid mask); they are hashed for the destination level, binned
-// by destination bucket and written to the bucket regions as runs.  Must be called by all BK_THREADS threads.
-// hist[] must be zero on entry and is zero again on exit.  Three block barriers per tile; the stage is protected
-// from the next tile by that tile's first barrier.
+// One tile: every thread brings up to BK_KPT keys (valid mask; FULL = all of them, known at compile time); they
+// are hashed for the destination level, binned by destination bucket and written to the bucket regions as runs.
+// Must be called by all BK_THREADS threads.  hist[] must be zero on entry and is zero again on exit.  Four block
+// barriers per tile; the stage is protected from the next tile by that tile's first barrier.
+template <bool FULL>
 __device__ __forceinline__ void scatter_tile(BuildState* st, const ScatterDst& dst, const ScatterSmem& sm,
                                              const uint64_t (&key)[BK_KPT], uint32_t valid) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -100,7 +102,7 @@ __device__ __forceinline__ void scatter_tile(BuildState* st, const ScatterDst& d
 #pragma unroll
         for (int j = 0; j < BK_KPT; j++) {
             bp[j] = 0;
-            if (valid & (1u << j)) {
+            if (FULL || (valid & (1u << j))) {
                 const uint32_t b = hashmod_small(dst.sp0, key[j], dst.bits) >> dst.shift;
                 bp[j] = (b << BK_POS_BITS) | atomicAdd(&sm.hist[b], 1u);
             }
@@ -109,7 +111,7 @@ __device__ __forceinline__ void scatter_tile(BuildState* st, const ScatterDst& d
         // plain destination list: one bucket, position by warp ballot (all lanes would hit the same counter)
 #pragma unroll
         for (int j = 0; j < BK_KPT; j++) {
-            const bool v = (valid >> j) & 1u;
+            const bool v = FULL || ((valid >> j) & 1u);
             const uint32_t m = __ballot_sync(0xffffffffu, v);
             uint32_t base = 0;
             if (lane == 0 && m) base = atomicAdd(&sm.hist[0], (uint32_t)__popc(m));
@@ -118,45 +120,94 @@ __device__ __forceinline__ void scatter_tile(BuildState* st, const ScatterDst& d
         }
     }
     __syncthreads();
-    // exclusive scan of hist over the buckets (each thread owns a contiguous chunk) + global reservations
-    const uint32_t per = (dst.count + BK_THREADS - 1) / BK_THREADS;
-    const uint32_t b0 = min(dst.count, (uint32_t)tid * per), b1 = min(dst.count, b0 + per);
-    uint32_t sum = 0;
-    for (uint32_t b = b0; b < b1; b++) sum += sm.hist[b];
-    uint32_t incl = sum;
+    uint32_t total;
+    if (dst.count <= 2 * BK_THREADS) {
+        // common case: two buckets per thread; the global reservations are issued before the scan so that their
+        // round trip overlaps it
+        const uint32_t b0 = 2 * tid;
+        uint2 h = make_uint2(0, 0);
+        if (b0 < dst.count) {
+            h = *reinterpret_cast<const uint2*>(sm.hist + b0);  // hist is padded to an even count
+            if (b0 + 1 >= dst.count) h.y = 0;
+            if (h.x | h.y) *reinterpret_cast<uint2*>(sm.hist + b0) = make_uint2(0, 0);
+        }
+        uint32_t g0 = 0, g1 = 0;
+        if (h.x) g0 = atomicAdd(dst.cursor + (size_t)b0 * CURSOR_STRIDE, h.x);
+        if (h.y) g1 = atomicAdd(dst.cursor + (size_t)(b0 + 1) * CURSOR_STRIDE, h.y);
+        const uint32_t sum = h.x + h.y;
+        uint32_t incl = sum;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += t;
-    }
-    if (lane == 31) sm.warp_tot[warp] = incl;
-    __syncthreads();
-    uint32_t woff = 0, total = 0;
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        if (lane == 31) sm.warp_tot[warp] = incl;
+        __syncthreads();
+        uint32_t woff = 0;
+        total = 0;
+        const uint4* wt = reinterpret_cast<const uint4*>(sm.warp_tot);
 #pragma unroll
-    for (int w = 0; w < BK_THREADS / 32; w++) {
-        const uint32_t t = sm.warp_tot[w];
-        if (w < warp) woff += t;
-        total += t;
-    }
-    uint32_t run = woff + incl - sum;
-    for (uint32_t b = b0; b < b1; b++) {
-        const uint32_t h = sm.hist[b];
-        if (h) {
-            const uint32_t g = atomicAdd(dst.cursor + (size_t)b * CURSOR_STRIDE, h);
-            if ((uint64_t)g + h > dst.cap) {  // region too small: host rebuilds unbucketed
-                st->status = ST_BUCKET_OVERFLOW;
+        for (int q4 = 0; q4 < BK_THREADS / 128; q4++) {
+            const uint4 t = wt[q4];
+            const uint32_t e[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (q4 * 4 + k < warp) woff += e[k];
+                total += e[k];
+            }
+        }
+        if (sum) {
+            const uint32_t run = woff + incl - sum;
+            const uint32_t region = dst.count > 1 ? dst.cap : 0u;
+            if ((h.x && (uint64_t)g0 + h.x > dst.cap) || (h.y && (uint64_t)g1 + h.y > dst.cap)) {
+                st->status = ST_BUCKET_OVERFLOW;  // region too small: host rebuilds unbucketed
                 *sm.ovf = 1;
             }
-            sm.sbase[b] = run;
-            sm.delta[b] = (dst.count > 1 ? b * dst.cap : 0u) + g - run;
-            sm.hist[b] = 0;
-            run += h;
+            *reinterpret_cast<uint2*>(sm.sbase + b0) = make_uint2(run, run + h.x);
+            *reinterpret_cast<uint2*>(sm.delta + b0) = make_uint2(b0 * region + g0 - run, (b0 + 1) * region + g1 - (run + h.x));
+        }
+    } else {
+        // many buckets: each thread owns a contiguous chunk
+        const uint32_t per = (dst.count + BK_THREADS - 1) / BK_THREADS;
+        const uint32_t b0 = min(dst.count, (uint32_t)tid * per), b1 = min(dst.count, b0 + per);
+        uint32_t sum = 0;
+        for (uint32_t b = b0; b < b1; b++) sum += sm.hist[b];
+        uint32_t incl = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        if (lane == 31) sm.warp_tot[warp] = incl;
+        __syncthreads();
+        uint32_t woff = 0;
+        total = 0;
+#pragma unroll
+        for (int w = 0; w < BK_THREADS / 32; w++) {
+            const uint32_t t = sm.warp_tot[w];
+            if (w < warp) woff += t;
+            total += t;
+        }
+        uint32_t run = woff + incl - sum;
+        for (uint32_t b = b0; b < b1; b++) {
+            const uint32_t h = sm.hist[b];
+            if (h) {
+                const uint32_t g = atomicAdd(dst.cursor + (size_t)b * CURSOR_STRIDE, h);
+                if ((uint64_t)g + h > dst.cap) {
+                    st->status = ST_BUCKET_OVERFLOW;
+                    *sm.ovf = 1;
+                }
+                sm.sbase[b] = run;
+                sm.delta[b] = b * dst.cap + g - run;
+                sm.hist[b] = 0;
+                run += h;
+            }
         }
     }
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < BK_KPT; j++) {
-        if (valid & (1u << j)) {
+        if (FULL || (valid & (1u << j))) {
             const uint32_t b = dst.count > 1 ? (bp[j] >> BK_POS_BITS) : 0u;
             const uint32_t s = sm.sbase[b] + (dst.count > 1 ? (bp[j] & ((1u << BK_POS_BITS) - 1u)) : bp[j]);
             sm.stage_key[s] = key[j];
@@ -165,7 +216,15 @@ __device__ __forceinline__ void scatter_tile(BuildState* st, const ScatterDst& d
     }
     __syncthreads();
     if (*sm.ovf == 0) {
-        for (uint32_t i = tid; i < total; i += BK_THREADS) dst.keys[sm.stage_dst[i]] = sm.stage_key[i];
+        if (FULL) {
+#pragma unroll
+            for (int j = 0; j < BK_KPT; j++) {
+                const uint32_t i = j * BK_THREADS + tid;
+                dst.keys[sm.stage_dst[i]] = sm.stage_key[i];
+            }
+        } else {
+            for (uint32_t i = tid; i < total; i += BK_THREADS) dst.keys[sm.stage_dst[i]] = sm.stage_key[i];
+        }
     }
 }
 
@@ -174,7 +233,7 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 // -------------------------------------------------------------------------------------------------------
 // scatter0_kernel: input keys [key_begin, key_end) -> level-0 buckets
 // -------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(BK_THREADS, 2)
+__global__ void __launch_bounds__(BK_THREADS, 3)
     scatter0_kernel(BuildState* __restrict__ st, const uint64_t* __restrict__ keys, uint64_t key_begin,
                     uint64_t key_end, uint64_t* __restrict__ buf0, uint32_t* __restrict__ cursor0, uint32_t smem_bytes) {
     extern __shared__ __align__(16) unsigned char dyn_smem[];
@@ -185,7 +244,7 @@ __global__ void __launch_bounds__(BK_THREADS, 2)
         return;
     }
     const ScatterSmem sm = carve_scatter(dyn_smem, dst.count);
-    for (uint32_t b = threadIdx.x; b < dst.count; b += BK_THREADS) sm.hist[b] = 0;
+    for (uint32_t b = threadIdx.x; b < dst.count + 1; b += BK_THREADS) sm.hist[b] = 0;
     if (threadIdx.x == 0) *sm.ovf = 0;
     __syncthreads();
     const uint64_t n = key_end - key_begin;
@@ -193,12 +252,19 @@ __global__ void __launch_bounds__(BK_THREADS, 2)
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const uint64_t base = key_begin + tile * BK_TILE + threadIdx.x;
         uint64_t key[BK_KPT];
-        uint32_t valid = 0;
+        // the tile this CTA takes next: pull it into L2 while this one is binned (one 128-byte line per 16 lanes)
+        if ((threadIdx.x & 15) == 0 && tile + gridDim.x < n_tiles) {
+            const uint64_t nb = key_begin + (tile + gridDim.x) * BK_TILE + threadIdx.x;
+#pragma unroll
+            for (int j = 0; j < BK_KPT; j++)
+                if (nb + (uint64_t)j * BK_THREADS < key_end) prefetch_l2(keys + nb + (uint64_t)j * BK_THREADS);
+        }
         if (key_begin + (tile + 1) * BK_TILE <= key_end) {
 #pragma unroll
             for (int j = 0; j < BK_KPT; j++) key[j] = ld_stream_u64(keys + base + (uint64_t)j * BK_THREADS);
-            valid = (1u << BK_KPT) - 1;
+            scatter_tile<true>(st, dst, sm, key, 0xffu);
         } else {
+            uint32_t valid = 0;
 #pragma unroll
             for (int j = 0; j < BK_KPT; j++) {
                 const uint64_t i = base + (uint64_t)j * BK_THREADS;
@@ -208,27 +274,53 @@ __global__ void __launch_bounds__(BK_THREADS, 2)
                     valid |= 1u << j;
                 }
             }
+            scatter_tile<false>(st, dst, sm, key, valid);
         }
-        // the tile this CTA takes next: pull it into L2 while this one is binned (one 128-byte line per 16 lanes)
-        if ((threadIdx.x & 15) == 0 && tile + gridDim.x < n_tiles) {
-            const uint64_t nb = key_begin + (tile + gridDim.x) * BK_TILE + threadIdx.x;
-#pragma unroll
-            for (int j = 0; j < BK_KPT; j++)
-                if (nb + (uint64_t)j * BK_THREADS < key_end) prefetch_l2(keys + nb + (uint64_t)j * BK_THREADS);
-        }
-        scatter_tile(st, dst, sm, key, valid);
     }
 }
 
 // -------------------------------------------------------------------------------------------------------
-// scatter_kernel(level >= 1): filter level-1's buckets against their collide slice, survivors -> level's buckets
-// one CTA per source bucket (grid-stride over buckets)
+// scatter_kernel(level >= 1): filter level-1's buckets against their collide slice, survivors -> level's buckets.
+// One CTA per source bucket (grid-stride over buckets).  The filter streams sub-tiles of the source bucket and
+// appends the surviving keys to a pending buffer in shared memory (the same buffer the partition later stages
+// into); the partition runs whenever another sub-tile might not fit, i.e. on (nearly) full tiles.  The pending
+// keys carry over from one source bucket to the next -- they all go to the same destination level.
 // -------------------------------------------------------------------------------------------------------
+constexpr int SRC_KPT = 4;
+constexpr int SRC_TILE = BK_THREADS * SRC_KPT;  // 2048 source keys per filter step
+
+__device__ __forceinline__ void flush_pending(BuildState* st, const ScatterDst& dst, const ScatterSmem& sm,
+                                              uint32_t* pend_cnt) {
+    // all threads: *pend_cnt is stable (read after a barrier); the pending keys sit at stage_key[0 .. n_p)
+    const uint32_t n_p = *pend_cnt;
+    uint64_t key[BK_KPT];
+    if (n_p == BK_TILE) {
+#pragma unroll
+        for (int j = 0; j < BK_KPT; j++) key[j] = sm.stage_key[j * BK_THREADS + threadIdx.x];
+        scatter_tile<true>(st, dst, sm, key, 0xffu);
+    } else {
+        uint32_t valid = 0;
+#pragma unroll
+        for (int j = 0; j < BK_KPT; j++) {
+            const uint32_t i = j * BK_THREADS + threadIdx.x;
+            key[j] = 0;
+            if (i < n_p) {
+                key[j] = sm.stage_key[i];
+                valid |= 1u << j;
+            }
+        }
+        scatter_tile<false>(st, dst, sm, key, valid);
+    }
+    if (threadIdx.x == 0) *pend_cnt = 0;
+    __syncthreads();  // the stage has been written out; the buffer takes pending keys again
+}
+
 __global__ void __launch_bounds__(BK_THREADS, 2)
     scatter_kernel(BuildState* __restrict__ st, uint32_t level, uint64_t* __restrict__ buf0,
                    uint64_t* __restrict__ buf1, const uint32_t* __restrict__ c32, uint32_t* __restrict__ cursors,
                    uint32_t smem_bytes) {
     extern __shared__ __align__(16) unsigned char dyn_smem[];
+    __shared__ uint32_t pend_cnt;
     if (st->status != ST_RUNNING || st->n_levels != level || st->lv[level - 1].b_range == 0) return;
     const LevelDesc* pv = &st->lv[level - 1];
     const uint32_t p_range = pv->b_range, p_count = pv->b_count, p_cap = pv->b_cap, p_bits = (uint32_t)pv->bits;
@@ -246,9 +338,13 @@ __global__ void __launch_bounds__(BK_THREADS, 2)
     }
     uint32_t* c_sm = reinterpret_cast<uint32_t*>(dyn_smem);
     const ScatterSmem sm = carve_scatter(dyn_smem + c_bytes, dst.count);
-    for (uint32_t b = threadIdx.x; b < dst.count; b += BK_THREADS) sm.hist[b] = 0;
-    if (threadIdx.x == 0) *sm.ovf = 0;
+    for (uint32_t b = threadIdx.x; b < dst.count + 1; b += BK_THREADS) sm.hist[b] = 0;
+    if (threadIdx.x == 0) {
+        *sm.ovf = 0;
+        pend_cnt = 0;
+    }
     const uint32_t p_mask = p_range - 1;
+    const int lane = threadIdx.x & 31;
 
     for (uint32_t bucket = blockIdx.x; bucket < p_count; bucket += gridDim.x) {
         __syncthreads();
@@ -259,27 +355,37 @@ __global__ void __launch_bounds__(BK_THREADS, 2)
         __syncthreads();
         const uint32_t fill = min(src_cursor[(size_t)bucket * CURSOR_STRIDE], p_cap);
         const uint64_t* __restrict__ bsrc = src + (uint64_t)bucket * p_cap;
-        for (uint32_t t0 = 0; t0 < fill; t0 += BK_TILE) {
-            uint64_t key[BK_KPT];
-            uint32_t valid = 0;
+        for (uint32_t t0 = 0; t0 < fill; t0 += SRC_TILE) {
+            uint64_t key[SRC_KPT];
+            bool live[SRC_KPT];
 #pragma unroll
-            for (int j = 0; j < BK_KPT; j++) {
+            for (int j = 0; j < SRC_KPT; j++) {
                 const uint32_t i = t0 + j * BK_THREADS + threadIdx.x;
-                key[j] = 0;
-                if (i < fill) {
-                    key[j] = ld_stream_u64(bsrc + i);
-                    valid |= 1u << j;
-                }
+                live[j] = i < fill;
+                key[j] = live[j] ? ld_stream_u64(bsrc + i) : 0;
             }
             // Context::filter (src/lib.rs:443-452): the key is redone iff its slot collided
+            bool redo[SRC_KPT];
 #pragma unroll
-            for (int j = 0; j < BK_KPT; j++) {
+            for (int j = 0; j < SRC_KPT; j++) {
                 const uint32_t l = hashmod_small(p_sp0, key[j], p_bits) & p_mask;
-                if (!((c_sm[l >> 5] >> (l & 31)) & 1u)) valid &= ~(1u << j);
+                redo[j] = live[j] && ((c_sm[l >> 5] >> (l & 31)) & 1u);
             }
-            scatter_tile(st, dst, sm, key, valid);
+            __syncthreads();  // every thread has taken its decision on the previous step's pend_cnt
+#pragma unroll
+            for (int j = 0; j < SRC_KPT; j++) {
+                const uint32_t m = __ballot_sync(0xffffffffu, redo[j]);
+                uint32_t base = 0;
+                if (lane == 0 && m) base = atomicAdd(&pend_cnt, (uint32_t)__popc(m));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (redo[j]) sm.stage_key[base + __popc(m & ((1u << lane) - 1u))] = key[j];
+            }
+            __syncthreads();  // appends complete: pend_cnt is the same for everybody
+            if (pend_cnt > BK_TILE - SRC_TILE) flush_pending(st, dst, sm, &pend_cnt);
         }
     }
+    __syncthreads();
+    if (pend_cnt) flush_pending(st, dst, sm, &pend_cnt);
 }
 
 // -------------------------------------------------------------------------------------------------------

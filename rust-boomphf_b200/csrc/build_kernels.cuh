@@ -27,10 +27,11 @@ constexpr int FIN_THREADS = 256;
 constexpr int TAIL_THREADS = 1024;
 constexpr uint32_t NO_TAIL = 0xffffffffu;
 
-// streaming 8-byte load that does not pollute L1 (keys are read once per pass)
+// streaming 8-byte load, cached in L2 only (keys are read once per pass; and the persistent cascade kernel reads
+// lists another CTA wrote earlier in the same launch, which a non-coherent L1 path must not serve)
 __device__ __forceinline__ uint64_t ld_stream_u64(const uint64_t* p) {
     uint64_t v;
-    asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(v) : "l"(p));
     return v;
 }
 
@@ -182,25 +183,24 @@ __global__ void __launch_bounds__(PASS_THREADS)
 // pass_kernel: level >= 1.  filter(level-1) + compaction + mark(level) fused.
 // ---------------------------------------------------------------------------------------------
 template <bool MAYBE_BIG>
-__global__ void __launch_bounds__(PASS_THREADS)
-    pass_kernel(BuildState* __restrict__ st, uint32_t level, const uint64_t* __restrict__ user_keys,
-                uint64_t* __restrict__ buf0, uint64_t* __restrict__ buf1, uint32_t* __restrict__ a32,
-                uint32_t* __restrict__ c32) {
-    if (st->status != ST_RUNNING || st->n_levels != level || level >= st->tail_level) return;
-    if (st->lv[level - 1].b_range != 0) return;  // bucketed predecessor: scatter_kernel filtered it already
+__device__ __forceinline__ void pass_body(BuildState* __restrict__ st, uint32_t level, const uint64_t* __restrict__ user_keys,
+                                          uint64_t* __restrict__ buf0, uint64_t* __restrict__ buf1,
+                                          uint32_t* __restrict__ a32, uint32_t* __restrict__ c32) {
     __shared__ uint64_t stage[PASS_TILE];
     __shared__ uint32_t warp_tot[PASS_THREADS / 32];
     __shared__ uint64_t sh_base;
 
-    const LevelDesc* __restrict__ pv = &st->lv[level - 1];
-    const LevelDesc* __restrict__ cu = &st->lv[level];
-    const uint64_t p_bits = pv->bits, p_sp0 = pv->sp0, p_off32 = pv->word_off * 2, k_src = pv->k_loc;
-    const uint64_t c_bits = cu->bits, c_sp0 = cu->sp0, c_off32 = cu->word_off * 2;
+    // level descriptors are written by another CTA earlier in the same launch when this runs inside the
+    // persistent cascade kernel: read them through L2
+    const LevelDesc* pv = &st->lv[level - 1];
+    const LevelDesc* cu = &st->lv[level];
+    const uint64_t p_bits = __ldcg(&pv->bits), p_sp0 = __ldcg(&pv->sp0), p_off32 = __ldcg(&pv->word_off) * 2, k_src = __ldcg(&pv->k_loc);
+    const uint64_t c_bits = __ldcg(&cu->bits), c_sp0 = __ldcg(&cu->sp0), c_off32 = __ldcg(&cu->word_off) * 2;
     const bool p_big = MAYBE_BIG && (p_bits >> 32) != 0;
     const bool c_big = MAYBE_BIG && (c_bits >> 32) != 0;
     const uint64_t* __restrict__ src = (level == 1) ? user_keys : (((level - 1) & 1) ? buf1 : buf0);
     uint64_t* __restrict__ dst = (level & 1) ? buf1 : buf0;
-    const uint64_t dst_cap = st->list_cap[level & 1];
+    const uint64_t dst_cap = __ldcg(&st->list_cap[level & 1]);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
     const uint64_t n_tiles = (k_src + PASS_TILE - 1) / PASS_TILE;
@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(PASS_THREADS)
 #pragma unroll
         for (int j = 0; j < PASS_KPT; j++) {
             const uint64_t idx = p_big ? level_index<true>(p_sp0, key[j], p_bits) : level_index<false>(p_sp0, key[j], p_bits);
-            cw[j] = __ldg(c32 + p_off32 + (idx >> 5));
+            cw[j] = __ldcg(c32 + p_off32 + (idx >> 5));
             sh[j] = (uint32_t)idx & 31;
         }
         uint32_t flags = 0;
@@ -289,18 +289,25 @@ __global__ void __launch_bounds__(PASS_THREADS)
     }
 }
 
+template <bool MAYBE_BIG>
+__global__ void __launch_bounds__(PASS_THREADS)
+    pass_kernel(BuildState* __restrict__ st, uint32_t level, const uint64_t* __restrict__ user_keys,
+                uint64_t* __restrict__ buf0, uint64_t* __restrict__ buf1, uint32_t* __restrict__ a32,
+                uint32_t* __restrict__ c32) {
+    if (st->status != ST_RUNNING || st->n_levels != level || level >= st->tail_level) return;
+    if (st->lv[level - 1].b_range != 0) return;  // bucketed predecessor: scatter_kernel filtered it already
+    pass_body<MAYBE_BIG>(st, level, user_keys, buf0, buf1, a32, c32);
+}
+
 // ---------------------------------------------------------------------------------------------
-// finalize_kernel: a &= ~collide; block popcounts; unique count; last CTA sets up level+1
+// finalize: a &= ~collide; block popcounts; unique count; last CTA sets up level+1
 // 4 consecutive lanes own one 8-word rank block (16 B per lane).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(FIN_THREADS)
-    finalize_kernel(BuildState* __restrict__ st, uint32_t level, uint64_t* __restrict__ words,
-                    const uint64_t* __restrict__ coll, uint32_t* __restrict__ blockpop) {
-    if (st->status != ST_RUNNING || st->n_levels != level || level >= st->tail_level) return;
-    if (st->lv[level].b_range != 0) return;  // bucketed levels are finalized by bucket_mark_kernel
+__device__ __forceinline__ void finalize_body(BuildState* __restrict__ st, uint32_t level, uint64_t* __restrict__ words,
+                                              const uint64_t* __restrict__ coll, uint32_t* __restrict__ blockpop) {
     __shared__ bool is_last;
-    const uint64_t word_off = st->lv[level].word_off;
-    const uint64_t n_pairs = round_up8(st->lv[level].n_words) / 2;  // multiple of 4
+    const uint64_t word_off = __ldcg(&st->lv[level].word_off);
+    const uint64_t n_pairs = round_up8(__ldcg(&st->lv[level].n_words)) / 2;  // multiple of 4
     const int lane = threadIdx.x & 31;
     ulonglong2* __restrict__ a2 = reinterpret_cast<ulonglong2*>(words + word_off);
     const ulonglong2* __restrict__ c2 = reinterpret_cast<const ulonglong2*>(coll + word_off);
@@ -344,7 +351,7 @@ __global__ void __launch_bounds__(FIN_THREADS)
     if (is_last && threadIdx.x == 0) {
         __threadfence();
         const uint64_t uq = atomicAdd((unsigned long long*)&st->uniq_count, 0ULL);
-        const uint64_t k_in = st->lv[level].k_in;
+        const uint64_t k_in = __ldcg(&st->lv[level].k_in);
         const uint64_t listed = atomicAdd((unsigned long long*)&st->redo_count, 0ULL);
         const bool sharded = st->shard_world > 1;
         // sharded: this shard's part of the level's key list is what its filter appended (the shard sum was
@@ -352,13 +359,77 @@ __global__ void __launch_bounds__(FIN_THREADS)
         if (sharded && level >= 1) st->lv[level].k_loc = listed;
         // plain predecessor: pass_kernel appended this level's list through redo_count, which must match k_in
         // (a bucketed predecessor is checked through the bucket cursors instead)
-        const bool check_list = !sharded && level >= 1 && st->lv[level - 1].b_range == 0;
+        const bool check_list = !sharded && level >= 1 && __ldcg(&st->lv[level - 1].b_range) == 0;
         if (uq > k_in || (check_list && listed != k_in)) {
             st->status = ST_ERR_INTERNAL;
             st->err_info = ((uint64_t)level << 48) | uq;
         } else {
             finish_level(st, level, k_in - uq);
         }
+    }
+}
+
+__global__ void __launch_bounds__(FIN_THREADS)
+    finalize_kernel(BuildState* __restrict__ st, uint32_t level, uint64_t* __restrict__ words,
+                    const uint64_t* __restrict__ coll, uint32_t* __restrict__ blockpop) {
+    if (st->status != ST_RUNNING || st->n_levels != level || level >= st->tail_level) return;
+    if (st->lv[level].b_range != 0) return;  // bucketed levels are finalized by bucket_mark_kernel
+    finalize_body(st, level, words, coll, blockpop);
+}
+
+// ---------------------------------------------------------------------------------------------
+// cascade_kernel: ONE persistent (cooperatively launched) kernel runs pass + finalize of every level from
+// st->n_levels on, separated by grid-wide barriers, until the tail takes over or the device has to stop
+// (buffer growth, error).  Replaces two launches per level: at 1e8 keys the 12 levels after level 0 spend most
+// of their time in launch gaps and ramp-up, not in work.  Same level bodies, same result.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// all CTAs of the (co-resident) grid; the fence by thread 0 also drops the SM's L1 contents
+__device__ __forceinline__ void grid_barrier(BuildState* st) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const uint32_t gen = ld_volatile_u32(&st->bar_gen);
+        const uint32_t arrived = atomicAdd(&st->bar_count, 1u) + 1u;
+        if (arrived == gridDim.x) {
+            st->bar_count = 0;
+            __threadfence();
+            atomicAdd(&st->bar_gen, 1u);
+        } else {
+            while (ld_volatile_u32(&st->bar_gen) == gen) __nanosleep(40);
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+template <bool MAYBE_BIG>
+__global__ void __launch_bounds__(PASS_THREADS)
+    cascade_kernel(BuildState* __restrict__ st, const uint64_t* __restrict__ user_keys, uint64_t* __restrict__ buf0,
+                   uint64_t* __restrict__ buf1, uint64_t* __restrict__ words, uint64_t* __restrict__ coll,
+                   uint32_t* __restrict__ blockpop) {
+    __shared__ uint32_t ctl[4];
+    for (;;) {
+        if (threadIdx.x == 0) {
+            ctl[0] = ld_volatile_u32(&st->status);
+            ctl[1] = ld_volatile_u32(&st->n_levels);
+            ctl[2] = ld_volatile_u32(&st->tail_level);
+        }
+        __syncthreads();
+        const uint32_t status = ctl[0], level = ctl[1], tail = ctl[2];
+        __syncthreads();
+        // every CTA reads the same values here: they only change before the second barrier of an iteration
+        if (status != ST_RUNNING || level == 0 || level >= tail || level > BPHF_MAX_LEVELS) break;
+        pass_body<MAYBE_BIG>(st, level, user_keys, buf0, buf1, reinterpret_cast<uint32_t*>(words),
+                             reinterpret_cast<uint32_t*>(coll));
+        grid_barrier(st);
+        finalize_body(st, level, words, coll, blockpop);
+        grid_barrier(st);
     }
 }
 

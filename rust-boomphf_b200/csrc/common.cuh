@@ -68,6 +68,7 @@ struct BuildState {
     uint32_t bucket_slots;     // CTAs that run concurrently (SM count x 2): bucket counts are multiples of it
     uint32_t bucket_enable;
     uint64_t bucket_keys_seen; // sum of bucket fills seen by the mark kernel (consistency check)
+    uint32_t bar_count, bar_gen;  // grid barrier of the persistent cascade kernel
     uint32_t shard_rank;       // sharded build: this shard's index ...
     uint32_t shard_world;      // ... of shard_world shards (1 = unsharded)
     LevelDesc lv[BPHF_MAX_LEVELS + 1];

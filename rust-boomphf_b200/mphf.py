@@ -166,7 +166,7 @@ class Mphf:
             "pass_ms": [float(st.pass_ms[i]) for i in range(nl)], "fin_ms": [float(st.fin_ms[i]) for i in range(nl)],
             "tail_ms": float(st.tail_ms), "ranks_ms": float(st.ranks_ms), "total_ms": float(st.total_ms),
             "bucketed_levels": int(st.bucketed_levels), "rebuilds": int(st.rebuilds),
-            "merge_ms": [float(st.merge_ms[i]) for i in range(nl)],
+            "merge_ms": [float(st.merge_ms[i]) for i in range(nl)], "cascade_ms": float(st.cascade_ms),
         }
 
     # ---- lookups ----------------------------------------------------------------------------

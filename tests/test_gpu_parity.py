@@ -277,7 +277,7 @@ def test_baseline_size_100m_properties(pkg, oracle):
 @pytest.fixture
 def small_buckets(pkg):
     """force the bucketed kernels onto small levels so the unit-test sizes exercise them (and every transition)"""
-    pkg.lib().bphf_set_build_mode(0, 3000)
+    pkg.lib().bphf_set_build_mode(2, 3000)
     yield
     pkg.lib().bphf_set_build_mode(0, 0)
 
@@ -319,24 +319,32 @@ def test_bucketed_build_parity_seeds(pkg, oracle, small_buckets, seed):
     assert_same_levels(m.levels(), oracle.OracleMphf.new_parallel(1.7, keys, seed).levels())
 
 
-def test_bucketed_host_keys_in_chunks(pkg, oracle):
-    # 40 M host keys = 3 H2D chunks, each scattered into the level-0 buckets as it lands
+def test_host_keys_in_chunks_every_strategy(pkg, oracle):
+    # 40 M host keys = 3 H2D chunks, each consumed by the level-0 entry kernel as it lands
     n = 40_000_000
     keys = oracle.keygen(n, seed=2, kind=0)
-    m = pkg.Mphf.new_parallel(1.7, keys, None)
-    ref = oracle.OracleMphf.new_parallel(1.7, keys)
-    assert m.build_stats()["bucketed_levels"] >= 4
-    assert_same_levels(m.levels(), ref.levels())
+    exp = oracle.OracleMphf.new_parallel(1.7, keys).levels()
+    try:
+        for mode in (2, 1, 0):
+            pkg.lib().bphf_set_build_mode(mode, 0)
+            m = pkg.Mphf.new_parallel(1.7, keys, None)
+            assert (m.build_stats()["bucketed_levels"] >= 4) == (mode == 2)
+            assert_same_levels(m.levels(), exp)
+    finally:
+        pkg.lib().bphf_set_build_mode(0, 0)
 
 
 def test_plain_and_bucketed_strategies_agree(pkg, oracle, plain_only):
     keys = oracle.keygen(3_000_000, seed=5, kind=0)
     a = pkg.Mphf.new_parallel(1.7, keys, None)
     assert a.build_stats()["bucketed_levels"] == 0
-    pkg.lib().bphf_set_build_mode(0, 0)
+    pkg.lib().bphf_set_build_mode(2, 0)
     b = pkg.Mphf.new_parallel(1.7, keys, None)
     assert b.build_stats()["bucketed_levels"] > 0
-    assert oracle.fingerprint(a.levels()) == oracle.fingerprint(b.levels())
+    pkg.lib().bphf_set_build_mode(0, 0)
+    c = pkg.Mphf.new_parallel(1.7, keys, None)   # default: persistent cascade kernel
+    assert c.build_stats()["bucketed_levels"] == 0 and c.build_stats()["kernel_launches"] < a.build_stats()["kernel_launches"]
+    assert oracle.fingerprint(a.levels()) == oracle.fingerprint(b.levels()) == oracle.fingerprint(c.levels())
     assert_same_levels(a.levels(), oracle.OracleMphf.new_parallel(1.7, keys).levels())
 
 

@@ -32,7 +32,7 @@ for prof in (0, 2):
 st = m.build_stats()
 print("pass_ms", ["%.3f" % x for x in st["pass_ms"]])
 print("fin_ms ", ["%.3f" % x for x in st["fin_ms"]])
-print("tail_ms %.3f ranks_ms %.3f sum %.3f" % (st["tail_ms"], st["ranks_ms"], sum(st["pass_ms"]) + sum(st["fin_ms"]) + st["tail_ms"] + st["ranks_ms"]))
+print("tail_ms %.3f ranks_ms %.3f cascade_ms %.3f sum %.3f" % (st["tail_ms"], st["ranks_ms"], st["cascade_ms"], sum(st["pass_ms"]) + sum(st["fin_ms"]) + st["tail_ms"] + st["ranks_ms"] + st["cascade_ms"]))
 print("keys_in", st["keys_in"])
 out = torch.empty_like(keys)
 for r in range(3):
