@@ -296,10 +296,23 @@ static Plan make_plan(uint64_t n, double gamma, uint32_t slots, bool bucket_enab
             lp.need_keys = std::max<uint64_t>(lp.need_keys, (uint64_t)lp.count_max * cap_max);
         }
         p.lv.push_back(lp);
+        // Expected number of colliding keys of a level.  hashmod (src/lib.rs:78-88) is a fast-range reduction of a
+        // 32-bit hash when bits < 2^32: a slot owns floor(2^32/bits) or ceil(2^32/bits) hash values, so the slots are
+        // NOT equally likely and more keys collide than the uniform 1 - exp(-k/bits) predicts (+0.3 % at 6.8e8 bits,
+        // far more near 2^32).  Model both slot classes (Poisson), then +-6 sigma.
         auto next = [](uint64_t k, uint64_t bits, double sign) {
-            const double frac = 1.0 - std::exp(-(double)k / (double)bits);
+            double frac;
+            if (bits >> 32) {
+                frac = 1.0 - std::exp(-(double)k / (double)bits);
+            } else {
+                const double two32 = 4294967296.0;
+                const double q = two32 / (double)bits, lo = std::floor(q), f = q - lo;
+                const double p_lo = lo / two32, p_hi = (lo + 1.0) / two32;
+                const double share_hi = f * (double)bits * p_hi, share_lo = (1.0 - f) * (double)bits * p_lo;
+                frac = share_hi * (1.0 - std::exp(-(double)k * p_hi)) + share_lo * (1.0 - std::exp(-(double)k * p_lo));
+            }
             const double kn = (double)k * frac;
-            const double v = kn + sign * (6.0 * std::sqrt(kn) + 64.0);
+            const double v = kn + sign * (6.0 * std::sqrt(kn) + 64.0 + 1e-4 * kn);
             return v <= 0.0 ? (uint64_t)0 : (uint64_t)v;
         };
         k_up = std::min(k_up, next(k_up, bits_up, +1.0));
@@ -407,7 +420,13 @@ struct Builder {
     }
     // ST_NEED_WORDS: move to a larger arena, keeping everything built so far
     void grow_arena(uint64_t need_words) {
-        if (comm) throw CudaFailure{BPHF_ERR_NOMEM, "sharded build: level does not fit the comm's arena (duplicate keys?)"};
+        if (comm) {
+            char msg[256];
+            snprintf(msg, sizeof msg, "sharded build: level %u (%llu keys) needs %llu arena words, the comm has %llu (duplicate keys?)",
+                     hst.n_levels, (unsigned long long)hst.lv[hst.n_levels].k_in, (unsigned long long)need_words,
+                     (unsigned long long)hst.words_cap);
+            throw CudaFailure{BPHF_ERR_NOMEM, msg};
+        }
         const uint64_t new_cap = std::max<uint64_t>(need_words + need_words / 2, hst.words_cap * 2);
         const uint64_t new_phys = new_cap + TAIL_RESERVE_WORDS;
         uint64_t *nw = nullptr, *nc = nullptr;
@@ -476,7 +495,7 @@ struct Builder {
         launches++;
     }
     // levels >= 1 of an unsharded L2-atomic build: one cooperative launch, every CTA resident
-    bool use_cascade() const { return !comm && !hst.bucket_enable && g_build_mode == 0; }
+    bool use_cascade() const { return !comm && g_build_mode == 0; }
     void launch_cascade() {
         static int per_sm[2] = {0, 0};
         const int v = maybe_big ? 1 : 0;
@@ -599,7 +618,7 @@ enum { BUILD_RETRY_PLAIN = 1000 };
 
 // n = keys of this shard; comm == nullptr: unsharded (n_global == n)
 static int build_once(const uint64_t* keys, uint64_t n, double gamma, int has_seed, uint64_t seed, int device,
-                      int keys_mem, void* stream, bool bucket_enable, uint32_t rebuilds, bphf_mphf** out,
+                      int keys_mem, void* stream, bool bucket_enable, uint64_t min_keys, uint32_t rebuilds, bphf_mphf** out,
                       bphf_comm* comm = nullptr, uint64_t n_global_arg = 0) {
     const DeviceInfo& info = device_info(device);
     DeviceGuard guard(device);
@@ -614,7 +633,6 @@ static int build_once(const uint64_t* keys, uint64_t n, double gamma, int has_se
     CK(cudaEventCreate(&b.ev_end));
     CK(cudaEventRecord(b.ev_begin, s));
 
-    const uint64_t min_keys = g_bucket_min_keys;
     Plan plan = make_plan(n_global, gamma, b.slots(), bucket_enable, min_keys);
     b.maybe_big = plan.maybe_big;
     if (comm) {
@@ -699,10 +717,15 @@ static int build_once(const uint64_t* keys, uint64_t n, double gamma, int has_se
     if (lps.empty()) lps.push_back(lp0);
     else lps[0] = lp0;
     b.launch_level(0, nullptr, lps[0]);
-    if (b.use_cascade()) {
-        if (lps.size() > 1) b.launch_cascade();
-    } else {
-        for (uint32_t l = 1; l < lps.size(); l++) b.launch_level(l, &lps[l - 1], lps[l]);
+    {
+        // the persistent cascade kernel takes over at the first level whose predecessor is surely plain; the
+        // bucketed prefix (and the level right after it) is launched step by step
+        uint32_t l = 1;
+        for (; l < lps.size(); l++) {
+            if (b.use_cascade() && !lps[l - 1].maybe_bucket) break;
+            b.launch_level(l, &lps[l - 1], lps[l]);
+        }
+        if (l < lps.size()) b.launch_cascade();
     }
     // the first tail-owned level right after a bucketed one gets its keys from the scatter step as a plain list
     if (lps.back().maybe_bucket)
@@ -748,7 +771,7 @@ static int build_once(const uint64_t* keys, uint64_t n, double gamma, int has_se
         } else if (st.status != ST_RUNNING) {
             return fail(BPHF_ERR_INTERNAL, "unknown build status");
         }
-        if (b.use_cascade()) {
+        if (b.use_cascade() && st.lv[level - 1].b_range == 0 && st.lv[level].b_range == 0) {
             b.launch_cascade();
             continue;
         }
@@ -856,11 +879,20 @@ static int build_impl(const uint64_t* keys, uint64_t n, double gamma, int has_se
     if (keys_mem != BPHF_MEM_HOST && keys_mem != BPHF_MEM_DEVICE) return fail(BPHF_ERR_ARG, "bad keys_mem");
     // assert!(gamma > 1.01)  src/lib.rs:236,364  (NaN fails the assertion too)
     if (!(gamma > 1.01)) return fail(BPHF_ERR_GAMMA, "assertion failed: gamma > 1.01");
-    int rc = build_once(keys, n, gamma, has_seed, seed, device, keys_mem, stream, g_build_mode == 2, 0, out);
+    // mode 0: levels whose (a, collide) pair does not fit the L2 are built by the bucketed kernels (random L2
+    // atomics fall from ~126 G/s to ~30 G/s once they miss to HBM; measured crossover ~2.5e8 bits per level)
+    bool bucket = g_build_mode == 2;
+    uint64_t min_keys = g_bucket_min_keys;
+    if (g_build_mode == 0) {
+        const double fit_bits = 2.5e8;
+        bucket = (double)level_size(gamma, n) > fit_bits;
+        min_keys = (uint64_t)(fit_bits / gamma);
+    }
+    int rc = build_once(keys, n, gamma, has_seed, seed, device, keys_mem, stream, bucket, min_keys, 0, out);
     if (rc == BUILD_RETRY_PLAIN) {
         // a bucket region overflowed (heavily duplicated or otherwise non-random input): the plain L2-atomic
         // kernels have no such limit.  Still the GPU path -- there is no CPU fallback anywhere.
-        rc = build_once(keys, n, gamma, has_seed, seed, device, keys_mem, stream, false, 1, out);
+        rc = build_once(keys, n, gamma, has_seed, seed, device, keys_mem, stream, false, 0, 1, out);
         if (rc == BUILD_RETRY_PLAIN) return fail(BPHF_ERR_INTERNAL, "bucket overflow reported by an unbucketed build");
     }
     return rc;
@@ -1060,7 +1092,7 @@ BPHF_API int bphf_build_sharded_u64(bphf_comm* c, const uint64_t* keys, uint64_t
     if (keys_mem != BPHF_MEM_HOST && keys_mem != BPHF_MEM_DEVICE) return fail(BPHF_ERR_ARG, "bad keys_mem");
     if (!(gamma > 1.01)) return fail(BPHF_ERR_GAMMA, "assertion failed: gamma > 1.01");
     if (c->world == 1) return build_impl(keys, n_local, gamma, has_seed, seed, c->device, keys_mem, nullptr, out);
-    return build_once(keys, n_local, gamma, has_seed, seed, c->device, keys_mem, c->stream, false, 0, out, c, n_global);
+    return build_once(keys, n_local, gamma, has_seed, seed, c->device, keys_mem, c->stream, false, 0, 0, out, c, n_global);
     API_END
 }
 

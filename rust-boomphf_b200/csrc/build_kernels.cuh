@@ -425,6 +425,8 @@ __global__ void __launch_bounds__(PASS_THREADS)
         __syncthreads();
         // every CTA reads the same values here: they only change before the second barrier of an iteration
         if (status != ST_RUNNING || level == 0 || level >= tail || level > BPHF_MAX_LEVELS) break;
+        // only plain levels with a plain predecessor (uniform: written before the previous grid barrier)
+        if (__ldcg(&st->lv[level - 1].b_range) != 0 || __ldcg(&st->lv[level].b_range) != 0) break;
         pass_body<MAYBE_BIG>(st, level, user_keys, buf0, buf1, reinterpret_cast<uint32_t*>(words),
                              reinterpret_cast<uint32_t*>(coll));
         grid_barrier(st);
