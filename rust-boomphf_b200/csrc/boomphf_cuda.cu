@@ -262,7 +262,7 @@ struct Plan {
 static int g_build_mode = 0;
 static uint64_t g_bucket_min_keys = 1ull << 20;   // levels below this are built by the plain kernels
 
-static Plan make_plan(uint64_t n, double gamma, uint32_t slots, bool bucket_enable, uint64_t min_keys) {
+static Plan make_plan(uint64_t n, double gamma, uint32_t slots, bool bucket_enable, uint64_t min_keys, double frac = 1.0) {
     Plan p;
     uint64_t k_up = n, k_lo = n;
     uint64_t words = 0;
@@ -277,11 +277,12 @@ static Plan make_plan(uint64_t n, double gamma, uint32_t slots, bool bucket_enab
         const bool prev_maybe = level == 0 || p.lv[level - 1].maybe_bucket;
         const bool prev_surely = level == 0 || p.lv[level - 1].surely_bucket;
         BucketGeom gu, gl;
-        const bool bu = bucket_enable && bucket_geometry(bits_up, k_up, slots, min_keys, &gu);
-        const bool bl = bucket_enable && bucket_geometry(bits_lo, k_lo, slots, min_keys, &gl);
+        const bool bu = bucket_enable && bucket_geometry(bits_up, k_up, slots, min_keys, frac, &gu);
+        const bool bl = bucket_enable && bucket_geometry(bits_lo, k_lo, slots, min_keys, frac, &gl);
         lp.maybe_bucket = prev_maybe && (bu || bl);
         lp.surely_bucket = prev_surely && bu && bl;
         lp.need_keys = level >= 1 ? k_up : 0;
+        if (lp.maybe_bucket && frac < 1.0) lp.need_keys = 0;  // sharded: plain lists are sized by the caller
         if (lp.maybe_bucket) {
             // the real geometry is derived from the real k; size for the worst of both estimates
             if (bu && bl && gu.range == gl.range) {
@@ -459,6 +460,7 @@ struct Builder {
         hst.list_cap[which] = cap;
     }
 
+    const uint32_t* list_cursor(uint32_t level) const { return d_cursors + (size_t)(level & 1) * MAX_BUCKETS_ALLOC * CURSOR_STRIDE; }
     uint32_t* a32() const { return reinterpret_cast<uint32_t*>(d_words); }
     uint32_t* c32() const { return reinterpret_cast<uint32_t*>(d_coll); }
 
@@ -469,9 +471,9 @@ struct Builder {
         const uint64_t tiles = (cnt + PASS_TILE - 1) / PASS_TILE;
         const int grid = (int)std::min<uint64_t>(tiles, (uint64_t)max_grid());
         if (maybe_big)
-            mark_list_kernel<true><<<grid, PASS_THREADS, 0, s>>>(d_state, level, d_keys, begin, end, d_buf[0], d_buf[1], a32(), c32());
+            mark_list_kernel<true><<<grid, PASS_THREADS, 0, s>>>(d_state, level, d_keys, begin, end, d_buf[0], d_buf[1], a32(), c32(), list_cursor(level));
         else
-            mark_list_kernel<false><<<grid, PASS_THREADS, 0, s>>>(d_state, level, d_keys, begin, end, d_buf[0], d_buf[1], a32(), c32());
+            mark_list_kernel<false><<<grid, PASS_THREADS, 0, s>>>(d_state, level, d_keys, begin, end, d_buf[0], d_buf[1], a32(), c32(), list_cursor(level));
         CK(cudaGetLastError());
         launches++;
     }
@@ -518,7 +520,7 @@ struct Builder {
         memset(&cd, 0, sizeof cd);
         if (comm) {
             cd = comm->dev;
-            tail_gather_kernel<<<1, TAIL_THREADS, 0, s>>>(d_state, d_keys, d_buf[0], d_buf[1], c32(), cd.xkeys[cd.rank]);
+            tail_gather_kernel<<<1, TAIL_THREADS, 0, s>>>(d_state, d_keys, d_buf[0], d_buf[1], c32(), cd.xkeys[cd.rank], d_cursors);
             CK(cudaGetLastError());
             launches++;
             launch_barrier(BAR_PLAIN, 0);
@@ -587,6 +589,9 @@ struct Builder {
             if (!prev_surely_b) launch_pass(level, prev->k_up);
             end_event(e0);
         }
+        const size_t e1 = begin_event(1, level);
+        if (cur.maybe_bucket) launch_bucket_mark(level, cur.range_max, cur.count_max);
+        end_event(e1);
         if (comm) {
             // every shard has marked its keys -> fold the (a, collide) pairs of all shards -> everybody holds
             // the merged level.  The first barrier also checks that the shards' lists add up to k(level).
@@ -596,10 +601,9 @@ struct Builder {
             launch_barrier(BAR_PLAIN, level);
             end_event(em);
         }
-        const size_t e1 = begin_event(1, level);
-        if (cur.maybe_bucket) launch_bucket_mark(level, cur.range_max, cur.count_max);
-        if (!cur.surely_bucket) launch_finalize(level, cur.k_up);
-        end_event(e1);
+        const size_t e2 = begin_event(1, level);
+        if (!cur.surely_bucket || comm) launch_finalize(level, cur.k_up);
+        end_event(e2);
     }
 
     void upload_state() { CK(cudaMemcpyAsync(d_state, &hst, sizeof hst, cudaMemcpyHostToDevice, s)); }
@@ -627,22 +631,27 @@ static int build_once(const uint64_t* keys, uint64_t n, double gamma, int has_se
     b.n = n;
     b.comm = comm;
     const uint64_t n_global = comm ? n_global_arg : n;
-    if (comm) bucket_enable = false;  // shards mark full-width arrays with the L2-atomic kernels
+    const double shard_frac = (comm && n_global) ? (double)n / (double)n_global : 1.0;
 
     CK(cudaEventCreate(&b.ev_begin));
     CK(cudaEventCreate(&b.ev_end));
     CK(cudaEventRecord(b.ev_begin, s));
 
-    Plan plan = make_plan(n_global, gamma, b.slots(), bucket_enable, min_keys);
+    Plan plan = make_plan(n_global, gamma, b.slots(), bucket_enable, min_keys, shard_frac);
     b.maybe_big = plan.maybe_big;
     if (comm) {
         // this shard's redo lists: its expected share of every level + 8 sigma (there is no host round trip to
         // grow a list in the middle of a collective build; overflow ends in BPHF_ERR_NOMEM)
         plan.list_cap[0] = plan.list_cap[1] = 1;
-        const double frac = n_global ? (double)n / (double)n_global : 0.0;
-        for (size_t l = 1; l <= plan.lv.size(); l++) {
-            const double est = (l < plan.lv.size() ? (double)plan.lv[l].k_up : (double)TAIL_MAX_KEYS / 0.4) * frac * 1.05;
-            const uint64_t cap = std::min<uint64_t>(n, (uint64_t)(est + 8.0 * std::sqrt(est) + 4096.0));
+        const double frac = shard_frac;
+        for (size_t l = 0; l <= plan.lv.size(); l++) {
+            uint64_t cap = 0;
+            if (l >= 1) {
+                const double est = (l < plan.lv.size() ? (double)plan.lv[l].k_up : (double)TAIL_MAX_KEYS / 0.4) * frac * 1.05;
+                cap = std::min<uint64_t>(n, (uint64_t)(est + 8.0 * std::sqrt(est) + 4096.0));
+            }
+            // bucket regions of a bucketed level (already sized for this shard's share of the keys)
+            if (l < plan.lv.size() && plan.lv[l].maybe_bucket) cap = std::max<uint64_t>(cap, plan.lv[l].need_keys);
             plan.list_cap[l & 1] = std::max<uint64_t>(plan.list_cap[l & 1], cap);
         }
     }
@@ -666,6 +675,7 @@ static int build_once(const uint64_t* keys, uint64_t n, double gamma, int has_se
     st.bucket_min_keys = min_keys;
     st.shard_rank = comm ? (uint32_t)comm->rank : 0;
     st.shard_world = comm ? (uint32_t)comm->world : 1;
+    st.shard_frac = shard_frac;
     if (!try_make_level(&st, 0, n_global)) return fail(BPHF_ERR_INTERNAL, "level 0 does not fit the planned buffers");
     st.lv[0].k_loc = n;
     b.upload_state();
@@ -1092,7 +1102,19 @@ BPHF_API int bphf_build_sharded_u64(bphf_comm* c, const uint64_t* keys, uint64_t
     if (keys_mem != BPHF_MEM_HOST && keys_mem != BPHF_MEM_DEVICE) return fail(BPHF_ERR_ARG, "bad keys_mem");
     if (!(gamma > 1.01)) return fail(BPHF_ERR_GAMMA, "assertion failed: gamma > 1.01");
     if (c->world == 1) return build_impl(keys, n_local, gamma, has_seed, seed, c->device, keys_mem, nullptr, out);
-    return build_once(keys, n_local, gamma, has_seed, seed, c->device, keys_mem, c->stream, false, 0, 0, out, c, n_global);
+    // same policy as an unsharded build, on the GLOBAL level sizes (every shard marks full-width levels)
+    bool bucket = g_build_mode == 2;
+    uint64_t min_keys = g_bucket_min_keys;
+    if (g_build_mode == 0) {
+        const double fit_bits = 2.5e8;
+        bucket = (double)level_size(gamma, n_global) > fit_bits;
+        min_keys = (uint64_t)(fit_bits / gamma);
+    }
+    const int rc = build_once(keys, n_local, gamma, has_seed, seed, c->device, keys_mem, c->stream, bucket, min_keys, 0, out, c, n_global);
+    if (rc == BUILD_RETRY_PLAIN)
+        return fail(BPHF_ERR_NOMEM, "sharded build: a bucket region overflowed (unbalanced shards or heavily duplicated keys); "
+                                    "use bphf_set_build_mode(1, 0) on every shard");
+    return rc;
     API_END
 }
 

@@ -52,7 +52,9 @@ __device__ __forceinline__ ScatterDst make_dst(const BuildState* st, uint32_t le
     } else {
         o.shift = 0;
         o.count = 1;
-        o.cap = 0xffffffffu;  // bounded by list_cap, checked when the level was set up
+        // one contiguous list: bounded by the list buffer (an unsharded build sized it for exactly k(level))
+        const uint64_t lc = st->list_cap[level & 1];
+        o.cap = lc > 0xffffffffULL ? 0xffffffffu : (uint32_t)lc;
     }
     return o;
 }
@@ -423,6 +425,9 @@ __global__ void __launch_bounds__(BK_THREADS)
     const uint32_t* __restrict__ cursor = cursors + (size_t)(level & 1) * MAX_BUCKETS_ALLOC * CURSOR_STRIDE;
     const int lane = threadIdx.x & 31;
     const uint32_t mask = range - 1;
+    // sharded build: write the RAW pair (a = cnt >= 1, collide = cnt >= 2 of this shard's keys); the OR-collide
+    // merge and finalize_kernel follow
+    const bool raw = st->shard_world > 1;
     uint64_t uniq = 0, seen = 0;
 
     for (uint32_t bucket = blockIdx.x; bucket < count; bucket += gridDim.x) {
@@ -464,7 +469,7 @@ __global__ void __launch_bounds__(BK_THREADS)
             const bool in = (w < rw) && (w_first + w < words32);
             if (in) {
                 const uint32_t c = c_sm[w];
-                const uint32_t a = a_sm[w] & ~c;
+                const uint32_t a = raw ? a_sm[w] : (a_sm[w] & ~c);
                 a32[off32 + w_first + w] = a;
                 c32[off32 + w_first + w] = c;
                 pc = __popc(a);
@@ -474,7 +479,7 @@ __global__ void __launch_bounds__(BK_THREADS)
             pc += __shfl_xor_sync(0xffffffffu, pc, 2);
             pc += __shfl_xor_sync(0xffffffffu, pc, 4);
             pc += __shfl_xor_sync(0xffffffffu, pc, 8);
-            if (in && (lane & 15) == 0) blockpop[(off32 + w_first + w) >> 4] = pc;
+            if (in && !raw && (lane & 15) == 0) blockpop[(off32 + w_first + w) >> 4] = pc;
         }
     }
     // unique count + consistency counter, one atomic per CTA; last CTA finishes the level
@@ -501,7 +506,12 @@ __global__ void __launch_bounds__(BK_THREADS)
             const uint64_t sn = atomicAdd((unsigned long long*)&st->bucket_keys_seen, 0ULL);
             const uint64_t k_in = st->lv[level].k_in;
             st->bucket_keys_seen = 0;
-            if (st->status == ST_RUNNING) {
+            if (raw) {
+                // hand over to barrier + merge + finalize_kernel: this shard's key count of the level, counters reset
+                st->redo_count = sn;
+                st->uniq_count = 0;
+                st->fin_ticket = 0;
+            } else if (st->status == ST_RUNNING) {
                 if (uq > k_in || sn != k_in) {
                     st->status = ST_ERR_INTERNAL;
                     st->err_info = ((uint64_t)level << 48) | (sn & 0xffffffffffULL) | (1ULL << 45);

@@ -69,7 +69,7 @@ __host__ __device__ inline bool try_make_level(BuildState* st, uint32_t level, u
     // bucketed (shared-memory) construction for a prefix of large levels, plain L2-atomic kernels after that
     BucketGeom g;
     const bool may_bucket = st->bucket_enable && (level == 0 || st->lv[level - 1].b_range != 0);
-    if (may_bucket && bucket_geometry(d.bits, k, st->bucket_slots, st->bucket_min_keys, &g)) {
+    if (may_bucket && bucket_geometry(d.bits, k, st->bucket_slots, st->bucket_min_keys, st->shard_world > 1 ? st->shard_frac : 1.0, &g)) {
         const uint64_t need_keys = (uint64_t)g.count * g.cap;
         if (need_keys > st->list_cap[level & 1]) {
             st->status = ST_NEED_LIST;
@@ -131,9 +131,10 @@ __device__ __forceinline__ uint64_t level_index(uint64_t sp0, uint64_t key, uint
 // ---------------------------------------------------------------------------------------------
 template <bool MAYBE_BIG>
 __global__ void __launch_bounds__(PASS_THREADS)
-    mark_list_kernel(const BuildState* __restrict__ st, uint32_t level, const uint64_t* __restrict__ user_keys,
+    mark_list_kernel(BuildState* __restrict__ st, uint32_t level, const uint64_t* __restrict__ user_keys,
                      uint64_t key_begin, uint64_t key_end, const uint64_t* __restrict__ buf0,
-                     const uint64_t* __restrict__ buf1, uint32_t* __restrict__ a32, uint32_t* __restrict__ c32) {
+                     const uint64_t* __restrict__ buf1, uint32_t* __restrict__ a32, uint32_t* __restrict__ c32,
+                     const uint32_t* __restrict__ list_cursor) {
     if (st->status != ST_RUNNING || st->n_levels != level || level >= st->tail_level) return;
     if (st->lv[level].b_range != 0) return;                         // bucketed level: bucket_mark_kernel
     if (level >= 1 && st->lv[level - 1].b_range == 0) return;       // plain predecessor: pass_kernel marks
@@ -142,6 +143,12 @@ __global__ void __launch_bounds__(PASS_THREADS)
         keys = (level & 1) ? buf1 : buf0;
         key_begin = 0;
         key_end = st->lv[level].k_loc;
+        if (st->shard_world > 1) {
+            // sharded: this shard's part of the list is what its scatter step appended (count in the list cursor);
+            // publish it as the level's local key count for the merge barrier and for finalize
+            key_end = list_cursor[0];
+            if (blockIdx.x == 0 && threadIdx.x == 0) st->redo_count = key_end;
+        }
     }
     const uint64_t bits = st->lv[level].bits;
     const uint64_t sp0 = st->lv[level].sp0;
@@ -379,7 +386,8 @@ __global__ void __launch_bounds__(FIN_THREADS)
     finalize_kernel(BuildState* __restrict__ st, uint32_t level, uint64_t* __restrict__ words,
                     const uint64_t* __restrict__ coll, uint32_t* __restrict__ blockpop) {
     if (st->status != ST_RUNNING || st->n_levels != level || level >= st->tail_level) return;
-    if (st->lv[level].b_range != 0) return;  // bucketed levels are finalized by bucket_mark_kernel
+    // bucketed levels are finalized by bucket_mark_kernel, except in a sharded build (the merge comes in between)
+    if (st->lv[level].b_range != 0 && st->shard_world <= 1) return;
     finalize_body(st, level, words, coll, blockpop);
 }
 

@@ -71,6 +71,7 @@ struct BuildState {
     uint32_t bar_count, bar_gen;  // grid barrier of the persistent cascade kernel
     uint32_t shard_rank;       // sharded build: this shard's index ...
     uint32_t shard_world;      // ... of shard_world shards (1 = unsharded)
+    double shard_frac;         // this shard's share of the keys (n_local / n_global; 1 unsharded): sizes bucket regions
     LevelDesc lv[BPHF_MAX_LEVELS + 1];
 };
 
@@ -115,8 +116,9 @@ struct BucketGeom {
 };
 
 // count ~ 2..4 x the concurrent CTA slots so every SM stays busy and the tail of the last wave is short
+// frac: share of the level's k keys that this shard holds (bucket regions only hold the shard's own keys)
 __host__ __device__ inline bool bucket_geometry(uint64_t bits, uint64_t k, uint32_t slots, uint64_t min_keys,
-                                               BucketGeom* g) {
+                                               double frac, BucketGeom* g) {
     if (slots == 0 || k < min_keys || (bits >> 32) != 0) return false;
     const uint64_t target = 2ull * slots;
     uint32_t shift = BUCKET_SHIFT_MAX;
@@ -125,7 +127,7 @@ __host__ __device__ inline bool bucket_geometry(uint64_t bits, uint64_t k, uint3
     const uint64_t count = (bits + range - 1) >> shift;
     if (count > BUCKET_MAX_COUNT) return false;
     // expected fill k * range / bits, + 6 sigma + slack
-    const double mean = (double)k * (double)range / (double)bits;
+    const double mean = (double)k * (frac < 1.0 ? frac * 1.02 : 1.0) * (double)range / (double)bits;
 #ifdef __CUDA_ARCH__
     const double sd = sqrt(mean);
 #else

@@ -160,7 +160,8 @@ __global__ void __launch_bounds__(MERGE_THREADS)
 __global__ void __launch_bounds__(TAIL_THREADS)
     tail_gather_kernel(BuildState* __restrict__ st, const uint64_t* __restrict__ user_keys,
                        const uint64_t* __restrict__ buf0, const uint64_t* __restrict__ buf1,
-                       const uint32_t* __restrict__ c32, uint64_t* __restrict__ xk) {
+                       const uint32_t* __restrict__ c32, uint64_t* __restrict__ xk,
+                       const uint32_t* __restrict__ cursors) {
     __shared__ uint32_t count;
     if (st->status != ST_RUNNING || st->tail_level == NO_TAIL || st->n_levels != st->tail_level) return;
     const uint32_t tid = threadIdx.x, level = st->tail_level;
@@ -169,6 +170,12 @@ __global__ void __launch_bounds__(TAIL_THREADS)
     if (level == 0) {
         const uint32_t k = (uint32_t)min(st->lv[0].k_loc, (uint64_t)TAIL_MAX_KEYS);
         for (uint32_t i = tid; i < k; i += TAIL_THREADS) xk[8 + i] = user_keys[i];
+        if (tid == 0) count = k;
+    } else if (st->lv[level - 1].b_range != 0) {
+        // bucketed predecessor: the scatter step already filtered this shard's keys into a plain list
+        const uint64_t* src = (level & 1) ? buf1 : buf0;
+        const uint32_t k = min(cursors[(size_t)(level & 1) * MAX_BUCKETS_ALLOC * CURSOR_STRIDE], (uint32_t)TAIL_MAX_KEYS);
+        for (uint32_t i = tid; i < k; i += TAIL_THREADS) xk[8 + i] = src[i];
         if (tid == 0) count = k;
     } else {
         const LevelDesc* pv = &st->lv[level - 1];

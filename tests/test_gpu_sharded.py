@@ -122,3 +122,43 @@ def test_sharded_argument_errors(pkg):
             c.build(1.7, np.arange(10, dtype=np.uint64), 10)
     finally:
         c.close()
+
+
+# ---- sharded build with the bucketed (shared-memory) marking kernels ---------------------------------------------
+@pytest.fixture
+def small_buckets(pkg):
+    """force the bucketed kernels onto small levels so the unit-test sizes exercise them (and every transition)"""
+    pkg.lib().bphf_set_build_mode(2, 3000)
+    yield
+    pkg.lib().bphf_set_build_mode(0, 0)
+
+
+@pytest.mark.parametrize("world", [2, 3, 4])
+@pytest.mark.parametrize("n", [2999, 5000, 9001, 70_000, 1_000_003, 3_000_000])
+def test_sharded_bucketed_parity(pkg, oracle, small_buckets, world, n):
+    ms = _run(pkg, oracle, oracle.keygen(n, seed=5 * n + world, kind=0), world)
+    assert (ms[0].build_stats()["bucketed_levels"] > 0) == (n > 4096)
+
+
+@pytest.mark.parametrize("gamma", [1.3, 2.0, 5.0, 17.5])
+def test_sharded_bucketed_gammas(pkg, oracle, small_buckets, gamma):
+    _run(pkg, oracle, oracle.keygen(300_001, seed=33, kind=1), 3, gamma=gamma)
+
+
+def test_sharded_bucketed_unbalanced_shards_fail_cleanly_or_match(pkg, oracle, small_buckets):
+    # all keys on the last shard: its bucket regions are sized for a 1/4 share -> overflow is reported as an error
+    # on every shard (no hang, no corruption); the comm must then be discarded
+    sh = _sharded(pkg)
+    keys = oracle.keygen(200_000, seed=8, kind=0)
+    comms = sh.ShardComm.local_group([0] * 4, len(keys), 1.7)
+    try:
+        shards = [keys[:0], keys[:0], keys[:0], keys]
+        try:
+            ms = sh.build_in_threads(comms, 1.7, shards)
+        except pkg.MphfPanic as e:
+            assert e.code in (-4, -5)
+        else:
+            assert_same_levels(ms[0].levels(), oracle.OracleMphf.new_parallel(1.7, keys).levels())
+    finally:
+        for c in comms:
+            c.close()
