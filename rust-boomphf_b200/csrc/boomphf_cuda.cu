@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -104,7 +105,9 @@ static const DeviceInfo& device_info(int dev) {
                 (const void*)map_permute_kernel<true>, (const void*)map_get_kernel<false>, (const void*)map_get_kernel<true>,
                 (const void*)pack_query_kernel, (const void*)set_base_rank_kernel, (const void*)query_sync_kernel,
                 (const void*)keygen_kernel, (const void*)check_perm_kernel, (const void*)checksum_kernel,
-                (const void*)shard_barrier_kernel, (const void*)or_collide_merge_kernel, (const void*)tail_gather_kernel};
+                (const void*)shard_barrier_kernel, (const void*)or_collide_merge_kernel, (const void*)tail_gather_kernel,
+                (const void*)shard_gather_kernel<false>, (const void*)shard_gather_kernel<true>,
+                (const void*)shard_collect_kernel, (const void*)shard_switch_kernel};
             for (const void* k : all_kernels) CK(cudaFuncGetAttributes(&fa, k));
         }
         if (prev != dev) CK(cudaSetDevice(prev));
@@ -176,6 +179,8 @@ struct bphf_comm {
     void* peer_base[SHARD_MAX] = {};  // mapped bases of all shards (own base at [rank])
     bool peer_is_ipc[SHARD_MAX] = {};
     bool connected = false;
+    bool co_located = false;     // another shard shares this GPU (tests): no cooperative launches, they could not
+                                 // become resident next to a peer's spinning barrier kernel
     uint64_t epoch = 0;          // barrier counter; advances identically on every shard
     cudaStream_t stream = nullptr;  // the shard's build stream (owned: one hardware queue per live shard)
     void* pinned = nullptr;         // pinned staging for the build state read-back
@@ -261,6 +266,18 @@ struct Plan {
 // 1: L2-atomic kernels, two launches per level   2: bucketed shared-memory kernels for the large levels
 static int g_build_mode = 0;
 static uint64_t g_bucket_min_keys = 1ull << 20;   // levels below this are built by the plain kernels
+
+// a level is built by the bucketed kernels when its (a, collide) pair clearly exceeds the L2: random L2 atomics fall
+// from ~126 G/s to ~30 G/s once they miss to HBM.  Measured crossover (level-0 cost per 1e8 keys, plain vs
+// bucketed): 1.7e8 bits 0.97 / 1.05 ms, 3.4e8 bits 1.1-1.3 / 1.1-1.2 ms, 6.8e8 bits 2.7 / 1.5 ms.
+static double bucket_fit_bits() {
+    static const double v = [] {
+        const char* e = getenv("BPHF_FIT_BITS");  // measurement override
+        const double x = e ? atof(e) : 0.0;
+        return x > 0.0 ? x : 4.5e8;
+    }();
+    return v;
+}
 
 static Plan make_plan(uint64_t n, double gamma, uint32_t slots, bool bucket_enable, uint64_t min_keys, double frac = 1.0) {
     Plan p;
@@ -358,6 +375,7 @@ struct Builder {
     bool maybe_big = false;
     uint32_t launches = 0, syncs = 0;
     bphf_comm* comm = nullptr;  // sharded build: the arenas live in the comm's peer-visible allocation
+    bool gathered = false;      // sharded build: the remaining keys were collected on every shard; unsharded from here
     std::vector<EventPair> events;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
 
@@ -497,7 +515,35 @@ struct Builder {
         launches++;
     }
     // levels >= 1 of an unsharded L2-atomic build: one cooperative launch, every CTA resident
-    bool use_cascade() const { return !comm && g_build_mode == 0; }
+    bool use_cascade() const {
+        static const bool no_coop = getenv("BPHF_NO_COOP") != nullptr;  // debugging aid
+        if (no_coop) return false;
+        return comm ? (gathered && !comm->co_located) : g_build_mode == 0;
+    }
+    bool sharded_now() const { return comm && !gathered; }
+    // sharded: collect the remaining keys on every shard, then mark + finalize level `level` from the collected list
+    void launch_gather(uint32_t level, uint64_t k_src_up, uint64_t k_up) {
+        const size_t e0 = begin_event(0, level);
+        const uint64_t tiles = std::max<uint64_t>(1, (k_src_up + PASS_TILE - 1) / PASS_TILE);
+        const int grid = (int)std::min<uint64_t>(tiles, (uint64_t)max_grid());
+        uint64_t* xk = comm->dev.xkeys[comm->rank];
+        if (maybe_big) shard_gather_kernel<true><<<grid, PASS_THREADS, 0, s>>>(d_state, level, d_keys, d_buf[0], d_buf[1], c32(), xk);
+        else shard_gather_kernel<false><<<grid, PASS_THREADS, 0, s>>>(d_state, level, d_keys, d_buf[0], d_buf[1], c32(), xk);
+        CK(cudaGetLastError());
+        launches++;
+        end_event(e0);
+        const size_t em = begin_event(4, level);
+        launch_barrier(BAR_LIST_SUM, level);
+        const int cgrid = (int)std::min<uint64_t>(std::max<uint64_t>(1, (k_up + 255) / 256), (uint64_t)info.sm_count * 4);
+        shard_collect_kernel<<<cgrid, 256, 0, s>>>(d_state, level, comm->dev, d_buf[0], d_buf[1]);
+        shard_switch_kernel<<<1, 1, 0, s>>>(d_state, level);
+        CK(cudaGetLastError());
+        launches += 2;
+        end_event(em);
+        gathered = true;
+        launch_mark_list(level, 0, 0, k_up);
+        launch_finalize(level, k_up);
+    }
     void launch_cascade() {
         static int per_sm[2] = {0, 0};
         const int v = maybe_big ? 1 : 0;
@@ -592,7 +638,7 @@ struct Builder {
         const size_t e1 = begin_event(1, level);
         if (cur.maybe_bucket) launch_bucket_mark(level, cur.range_max, cur.count_max);
         end_event(e1);
-        if (comm) {
+        if (sharded_now()) {
             // every shard has marked its keys -> fold the (a, collide) pairs of all shards -> everybody holds
             // the merged level.  The first barrier also checks that the shards' lists add up to k(level).
             const size_t em = begin_event(4, level);
@@ -602,7 +648,7 @@ struct Builder {
             end_event(em);
         }
         const size_t e2 = begin_event(1, level);
-        if (!cur.surely_bucket || comm) launch_finalize(level, cur.k_up);
+        if (!cur.surely_bucket || sharded_now()) launch_finalize(level, cur.k_up);
         end_event(e2);
     }
 
@@ -639,6 +685,7 @@ static int build_once(const uint64_t* keys, uint64_t n, double gamma, int has_se
 
     Plan plan = make_plan(n_global, gamma, b.slots(), bucket_enable, min_keys, shard_frac);
     b.maybe_big = plan.maybe_big;
+    uint32_t gather_level = NO_LEVEL;
     if (comm) {
         // this shard's redo lists: its expected share of every level + 8 sigma (there is no host round trip to
         // grow a list in the middle of a collective build; overflow ends in BPHF_ERR_NOMEM)
@@ -654,6 +701,16 @@ static int build_once(const uint64_t* keys, uint64_t n, double gamma, int has_se
             if (l < plan.lv.size() && plan.lv[l].maybe_bucket) cap = std::max<uint64_t>(cap, plan.lv[l].need_keys);
             plan.list_cap[l & 1] = std::max<uint64_t>(plan.list_cap[l & 1], cap);
         }
+        // collect level: first non-tail level >= 1 with at most GATHER_MAX_KEYS keys and plain neighbours
+        static const bool no_gather = getenv("BPHF_NO_GATHER") != nullptr;  // measurement aid
+        for (size_t l = 1; l < plan.lv.size() && !no_gather; l++) {
+            if (plan.lv[l].k_up <= GATHER_MAX_KEYS && !plan.lv[l - 1].maybe_bucket && !plan.lv[l].maybe_bucket) {
+                gather_level = (uint32_t)l;
+                break;
+            }
+        }
+        if (gather_level != NO_LEVEL)
+            for (int i = 0; i < 2; i++) plan.list_cap[i] = std::max<uint64_t>(plan.list_cap[i], GATHER_MAX_KEYS + 1024);
     }
 
     CK(cudaMallocAsync((void**)&b.d_state, sizeof(BuildState), s));
@@ -676,6 +733,8 @@ static int build_once(const uint64_t* keys, uint64_t n, double gamma, int has_se
     st.shard_rank = comm ? (uint32_t)comm->rank : 0;
     st.shard_world = comm ? (uint32_t)comm->world : 1;
     st.shard_frac = shard_frac;
+    st.gather_level = gather_level;
+    st.list_ready_level = NO_LEVEL;
     if (!try_make_level(&st, 0, n_global)) return fail(BPHF_ERR_INTERNAL, "level 0 does not fit the planned buffers");
     st.lv[0].k_loc = n;
     b.upload_state();
@@ -732,6 +791,11 @@ static int build_once(const uint64_t* keys, uint64_t n, double gamma, int has_se
         // bucketed prefix (and the level right after it) is launched step by step
         uint32_t l = 1;
         for (; l < lps.size(); l++) {
+            if (comm && l == st.gather_level) {
+                b.launch_gather(l, lps[l - 1].k_up, lps[l].k_up);
+                l++;
+            }
+            if (l >= lps.size()) break;
             if (b.use_cascade() && !lps[l - 1].maybe_bucket) break;
             b.launch_level(l, &lps[l - 1], lps[l]);
         }
@@ -889,12 +953,11 @@ static int build_impl(const uint64_t* keys, uint64_t n, double gamma, int has_se
     if (keys_mem != BPHF_MEM_HOST && keys_mem != BPHF_MEM_DEVICE) return fail(BPHF_ERR_ARG, "bad keys_mem");
     // assert!(gamma > 1.01)  src/lib.rs:236,364  (NaN fails the assertion too)
     if (!(gamma > 1.01)) return fail(BPHF_ERR_GAMMA, "assertion failed: gamma > 1.01");
-    // mode 0: levels whose (a, collide) pair does not fit the L2 are built by the bucketed kernels (random L2
-    // atomics fall from ~126 G/s to ~30 G/s once they miss to HBM; measured crossover ~2.5e8 bits per level)
+    // mode 0: levels whose (a, collide) pair does not fit the L2 are built by the bucketed kernels
     bool bucket = g_build_mode == 2;
     uint64_t min_keys = g_bucket_min_keys;
     if (g_build_mode == 0) {
-        const double fit_bits = 2.5e8;
+        const double fit_bits = bucket_fit_bits();
         bucket = (double)level_size(gamma, n) > fit_bits;
         min_keys = (uint64_t)(fit_bits / gamma);
     }
@@ -1059,6 +1122,7 @@ BPHF_API int bphf_comm_connect_local(bphf_comm* c, bphf_comm* const* all) {
         const bphf_comm* o = all[p];
         if (!o || o->rank != p || o->world != c->world || o->phys_words != c->phys_words)
             return fail(BPHF_ERR_ARG, "comms do not match (rank order, world, arena size)");
+        if (o->device == c->device) c->co_located = true;
         if (o->device != c->device) {
             int can = 0;
             CK(cudaDeviceCanAccessPeer(&can, c->device, o->device));
@@ -1106,7 +1170,7 @@ BPHF_API int bphf_build_sharded_u64(bphf_comm* c, const uint64_t* keys, uint64_t
     bool bucket = g_build_mode == 2;
     uint64_t min_keys = g_bucket_min_keys;
     if (g_build_mode == 0) {
-        const double fit_bits = 2.5e8;
+        const double fit_bits = bucket_fit_bits();
         bucket = (double)level_size(gamma, n_global) > fit_bits;
         min_keys = (uint64_t)(fit_bits / gamma);
     }

@@ -137,13 +137,14 @@ __global__ void __launch_bounds__(PASS_THREADS)
                      const uint32_t* __restrict__ list_cursor) {
     if (st->status != ST_RUNNING || st->n_levels != level || level >= st->tail_level) return;
     if (st->lv[level].b_range != 0) return;                         // bucketed level: bucket_mark_kernel
-    if (level >= 1 && st->lv[level - 1].b_range == 0) return;       // plain predecessor: pass_kernel marks
+    const bool list_ready = st->list_ready_level == level;          // collected list of a sharded build
+    if (level >= 1 && st->lv[level - 1].b_range == 0 && !list_ready) return;  // plain predecessor: pass_kernel marks
     const uint64_t* __restrict__ keys = user_keys;
     if (level >= 1) {
         keys = (level & 1) ? buf1 : buf0;
         key_begin = 0;
         key_end = st->lv[level].k_loc;
-        if (st->shard_world > 1) {
+        if (st->shard_world > 1 && !list_ready) {
             // sharded: this shard's part of the list is what its scatter step appended (count in the list cursor);
             // publish it as the level's local key count for the merge barrier and for finalize
             key_end = list_cursor[0];
@@ -195,10 +196,13 @@ __global__ void __launch_bounds__(PASS_THREADS)
 // ---------------------------------------------------------------------------------------------
 // pass_kernel: level >= 1.  filter(level-1) + compaction + mark(level) fused.
 // ---------------------------------------------------------------------------------------------
-template <bool MAYBE_BIG>
+// GATHER: only filter + compact, into `gather_dst` (a shard's exchange slot); level `level` is marked later from
+// the collected list
+template <bool MAYBE_BIG, bool GATHER = false>
 __device__ __forceinline__ void pass_body(BuildState* __restrict__ st, uint32_t level, const uint64_t* __restrict__ user_keys,
                                           uint64_t* __restrict__ buf0, uint64_t* __restrict__ buf1,
-                                          uint32_t* __restrict__ a32, uint32_t* __restrict__ c32) {
+                                          uint32_t* __restrict__ a32, uint32_t* __restrict__ c32,
+                                          uint64_t* __restrict__ gather_dst = nullptr) {
     __shared__ uint64_t stage[PASS_TILE];
     __shared__ uint32_t warp_tot[PASS_THREADS / 32];
     __shared__ uint64_t sh_base;
@@ -212,8 +216,8 @@ __device__ __forceinline__ void pass_body(BuildState* __restrict__ st, uint32_t 
     const bool p_big = MAYBE_BIG && (p_bits >> 32) != 0;
     const bool c_big = MAYBE_BIG && (c_bits >> 32) != 0;
     const uint64_t* __restrict__ src = (level == 1) ? user_keys : (((level - 1) & 1) ? buf1 : buf0);
-    uint64_t* __restrict__ dst = (level & 1) ? buf1 : buf0;
-    const uint64_t dst_cap = __ldcg(&st->list_cap[level & 1]);
+    uint64_t* __restrict__ dst = GATHER ? gather_dst : ((level & 1) ? buf1 : buf0);
+    const uint64_t dst_cap = GATHER ? GATHER_MAX_KEYS : __ldcg(&st->list_cap[level & 1]);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
     const uint64_t n_tiles = (k_src + PASS_TILE - 1) / PASS_TILE;
@@ -284,6 +288,7 @@ __device__ __forceinline__ void pass_body(BuildState* __restrict__ st, uint32_t 
                 if (i < total) {
                     const uint64_t kk = stage[i];
                     dst[out + i] = kk;
+                    if (GATHER) continue;
                     const uint64_t idx = c_big ? level_index<true>(c_sp0, kk, c_bits) : level_index<false>(c_sp0, kk, c_bits);
                     w[j] = c_off32 + (idx >> 5);
                     m[j] = 1u << (idx & 31);

@@ -18,6 +18,8 @@ namespace bphf {
 // During construction a second arena with the same offsets holds the collision bit vectors.
 constexpr uint32_t LEVEL_ALIGN_WORDS = 8;
 
+constexpr int SHARD_MAX = 8;  // shards (GPUs) of a sharded build
+
 struct LevelDesc {
     uint64_t bits;      // BitVector.bits = capacity()  (src/bitvector.rs:359)
     uint64_t n_words;   // u64s(bits)                   (src/bitvector.rs:426-428)
@@ -71,6 +73,9 @@ struct BuildState {
     uint32_t bar_count, bar_gen;  // grid barrier of the persistent cascade kernel
     uint32_t shard_rank;       // sharded build: this shard's index ...
     uint32_t shard_world;      // ... of shard_world shards (1 = unsharded)
+    uint32_t gather_level;     // sharded: level at which all remaining keys are collected on every shard (host plan)
+    uint32_t list_ready_level; // level whose complete key list already sits in buf[level & 1] (after the collect)
+    uint64_t peer_count[SHARD_MAX];  // sharded: every shard's key count, as carried by the last list-sum barrier
     double shard_frac;         // this shard's share of the keys (n_local / n_global; 1 unsharded): sizes bucket regions
     LevelDesc lv[BPHF_MAX_LEVELS + 1];
 };
@@ -88,9 +93,13 @@ __host__ __device__ __forceinline__ uint64_t round_up8(uint64_t w) { return (w +
 // ---- sharded build: peer-visible memory of every shard ------------------------------------
 // Each shard owns ONE peer-mapped allocation: [words arena | collide arena | tail exchange slot | flags].
 // Passed to the kernels by value; pointer p of every array is shard p's copy (own pointers for p == rank).
-constexpr int SHARD_MAX = 8;
 constexpr uint32_t FLAG_STRIDE = 16;                      // u64 per writer: one 128-byte line each
-constexpr uint64_t XKEYS_WORDS = TAIL_MAX_KEYS + 16;      // [0] = count, [8..] = keys
+// sharded build: once at most this many keys are left (over all shards) every shard collects all of them and the
+// remaining levels run redundantly on every GPU with the unsharded kernels -- the many small levels would
+// otherwise pay two device barriers and a merge each
+constexpr uint64_t GATHER_MAX_KEYS = 1ull << 20;
+constexpr uint32_t NO_LEVEL = 0xffffffffu;
+constexpr uint64_t XKEYS_WORDS = GATHER_MAX_KEYS + 16;    // [0] = count (tail hand-over), [8..] = keys
 struct CommDev {
     uint32_t rank, world;
     uint64_t* words[SHARD_MAX];   // level bit vectors (raw a while marking, final a after the merge)

@@ -82,6 +82,7 @@ __global__ void __launch_bounds__(32)
             peer_status = ld_relaxed_sys(src + 2);
         }
     }
+    if (kind == BAR_LIST_SUM && live && p < cd.world) st->peer_count[p] = peer_payload;
     const bool bad = timeout || peer_status != ST_RUNNING;
     const uint32_t any_bad = __ballot_sync(0xffffffffu, bad);
     uint64_t sum = peer_payload;
@@ -164,6 +165,7 @@ __global__ void __launch_bounds__(TAIL_THREADS)
                        const uint32_t* __restrict__ cursors) {
     __shared__ uint32_t count;
     if (st->status != ST_RUNNING || st->tail_level == NO_TAIL || st->n_levels != st->tail_level) return;
+    if (st->shard_world <= 1) return;  // all keys were collected on every shard already: the tail reads local lists
     const uint32_t tid = threadIdx.x, level = st->tail_level;
     if (tid == 0) count = 0;
     __syncthreads();
@@ -196,6 +198,47 @@ __global__ void __launch_bounds__(TAIL_THREADS)
         xk[0] = count;
         __threadfence_system();
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Collect: once at most GATHER_MAX_KEYS keys are left, every shard filters its keys of level gather_level - 1 into
+// its exchange slot (shard_gather_kernel = pass_body without the mark), a list-sum barrier carries the counts,
+// and every shard copies all slots into its own list (shard_collect_kernel).  From here on every shard holds the
+// whole remaining key set and finishes the cascade with the unsharded kernels, redundantly -> identical replicas.
+// ---------------------------------------------------------------------------------------------
+template <bool MAYBE_BIG>
+__global__ void __launch_bounds__(PASS_THREADS)
+    shard_gather_kernel(BuildState* __restrict__ st, uint32_t level, const uint64_t* __restrict__ user_keys,
+                        uint64_t* __restrict__ buf0, uint64_t* __restrict__ buf1, uint32_t* __restrict__ c32,
+                        uint64_t* __restrict__ xk) {
+    if (st->status != ST_RUNNING || st->n_levels != level || level != st->gather_level || level >= st->tail_level) return;
+    pass_body<MAYBE_BIG, true>(st, level, user_keys, buf0, buf1, nullptr, c32, xk + 8);
+}
+
+__global__ void __launch_bounds__(256)
+    shard_collect_kernel(BuildState* __restrict__ st, uint32_t level, CommDev cd, uint64_t* __restrict__ buf0,
+                         uint64_t* __restrict__ buf1) {
+    if (st->status != ST_RUNNING || st->n_levels != level || level != st->gather_level || level >= st->tail_level) return;
+    uint64_t* __restrict__ dst = (level & 1) ? buf1 : buf0;
+    uint64_t off = 0;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint32_t p = 0; p < cd.world; p++) {
+        const uint64_t cnt = st->peer_count[p];
+        const uint64_t* __restrict__ src = cd.xkeys[p] + 8;
+        for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += stride) dst[off + i] = src[i];
+        off += cnt;
+    }
+}
+
+// one thread, after the collect: from now on this shard behaves like an unsharded build of the remaining keys
+__global__ void shard_switch_kernel(BuildState* __restrict__ st, uint32_t level) {
+    if (st->status != ST_RUNNING || st->n_levels != level || level != st->gather_level || level >= st->tail_level) return;
+    uint64_t total = 0;
+    for (uint32_t p = 0; p < st->shard_world; p++) total += st->peer_count[p];
+    st->lv[level].k_loc = st->lv[level].k_in;
+    st->redo_count = total;            // finalize checks it against k(level)
+    st->list_ready_level = level;
+    st->shard_world = 1;
 }
 
 }  // namespace bphf
