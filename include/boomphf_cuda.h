@@ -84,6 +84,18 @@ BPHF_API int bphf_wy_swap_8byte_tail(void);
 BPHF_API int bphf_build_u64(const uint64_t *keys, uint64_t n, double gamma, int has_seed, uint64_t seed,
                             int device, int keys_mem, void *stream, bphf_mphf **out);
 
+/* ---- chunked construction ---------------------------------------------
+ * Mphf::from_chunked_iterator(gamma, &chunks, n)                       src/lib.rs:112   (parallel_variant = 0)
+ * Mphf::from_chunked_iterator_parallel(gamma, &chunks, max_iters, n, num_threads)  :539 (parallel_variant = 1)
+ * for T = u64: n_chunks arrays (all host or all device memory) whose lengths add up to n.  Results follow the
+ * reference bit for bit, including the parallel variant's quirks: its levels use `gamma` only until fewer than
+ * min(50 M, 1 % of n) keys are left and 1.7 afterwards (src/lib.rs:583-585, 654), an empty input yields zero
+ * levels, and max_iters only guards the chunked levels.  The key set is gathered into HBM (it must fit the GPU);
+ * the out-of-core re-iteration of the reference is not reproduced. */
+BPHF_API int bphf_build_chunked_u64(const uint64_t *const *chunks, const uint64_t *chunk_lens, uint64_t n_chunks,
+                                    uint64_t n, double gamma, int parallel_variant, int has_max_iters,
+                                    uint64_t max_iters, int device, int keys_mem, bphf_mphf **out);
+
 /* ---- sharded build over several GPUs --------------------------------------
  * The reference's new_parallel shares one (a, collide) pair per level between all rayon workers
  * (src/lib.rs:373-377).  Here the key set is split into `world` shards, one per GPU (one process or

@@ -409,6 +409,145 @@ BO_API int bo_build_parallel(const uint64_t *keys, uint64_t n, double gamma, int
     return BO_OK;
 }
 
+/* ------------------------------------------------------------------------------------------
+ * src/lib.rs:112-226  Mphf::from_chunked_iterator -- serial, keys arrive as a sequence of chunks that is walked
+ * twice per level; a `done_keys` bit vector over key positions replaces the redo list.
+ * chunks are given as one concatenated array + chunk lengths (n must equal their sum, else the reference
+ * panics "max number of items overflowed" or never finishes).
+ * ---------------------------------------------------------------------------------------- */
+BO_API int bo_build_chunked_serial(const uint64_t *keys, const uint64_t *chunk_lens, uint64_t n_chunks, uint64_t n,
+                                   double gamma, bo_mphf **out) {
+    if (!out || (n && !keys)) return BO_ERR_ARG;
+    *out = NULL;
+    uint64_t total = 0;
+    for (uint64_t c = 0; c < n_chunks; c++) total += chunk_lens[c];
+    if (total != n) return BO_ERR_ARG;
+    if (!(gamma > 1.01)) return BO_ERR_GAMMA; /* src/lib.rs:125 */
+    bo_mphf *m = mphf_alloc();
+    if (!m) return BO_ERR_NOMEM;
+    bo_bitvec done;
+    if (bv_new(&done, n > 255 ? n : 255)) { bo_free(m); return BO_ERR_NOMEM; }
+    uint64_t iter = 0, n_done = 0;
+    int rc = BO_OK;
+    for (;;) {
+        if (iter > BO_MAX_ITERS) { rc = BO_ERR_MAX_ITERS; break; } /* src/lib.rs:128-131 */
+        const uint64_t remaining = iter == 0 ? n : n - n_done;
+        bo_ctx cx;
+        if (ctx_new(&cx, bo_level_size(gamma, remaining), iter)) { rc = BO_ERR_NOMEM; break; }
+        uint64_t offset = 0;
+        for (uint64_t c = 0; c < n_chunks; c++) { /* first walk: find_collisions of the keys not done yet */
+            for (uint64_t i = 0; i < chunk_lens[c]; i++)
+                if (!bv_contains(&done, offset + i)) find_collisions_sync(&cx, keys[offset + i]);
+            offset += chunk_lens[c];
+        }
+        offset = 0;
+        for (uint64_t c = 0; c < n_chunks; c++) { /* second walk: a.remove on collisions, else the key is done */
+            for (uint64_t i = 0; i < chunk_lens[c]; i++) {
+                if (bv_contains(&done, offset + i)) continue;
+                if (!filter(&cx, keys[offset + i])) { bv_insert_sync(&done, offset + i); n_done++; }
+            }
+            offset += chunk_lens[c];
+        }
+        if (m->nlevels >= BO_MAX_LEVELS) { bv_free(&cx.a); bv_free(&cx.collide); rc = BO_ERR_MAX_ITERS; break; }
+        m->bv[m->nlevels++] = cx.a;
+        bv_free(&cx.collide);
+        if (n_done == n) break; /* src/lib.rs:215-217 */
+        iter += 1;
+    }
+    bv_free(&done);
+    if (rc == BO_OK) rc = compute_ranks(m);
+    if (rc != BO_OK) { bo_free(m); return rc; }
+    *out = m;
+    return BO_OK;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * src/lib.rs:539-667  Mphf::from_chunked_iterator_parallel.  Levels are built over the chunks with the caller's
+ * gamma until fewer than min(50 M, 1 % of n) keys are left; the colliding keys of that level are buffered and the
+ * rest is built by Mphf::new_parallel(1.7, &buffered, Some(iter)) -- gamma 1.7 whatever the caller passed
+ * (src/lib.rs:654), seeds continuing at `iter`.  The 1 % threshold is computed in f32 (src/lib.rs:557).
+ * (The work-queue / thread plumbing does not influence the result; the level passes run in OpenMP here.)
+ * ---------------------------------------------------------------------------------------- */
+BO_API int bo_build_chunked_parallel(const uint64_t *keys, const uint64_t *chunk_lens, uint64_t n_chunks, uint64_t n,
+                                     double gamma, int has_max_iters, uint64_t max_iters, int nthreads, bo_mphf **out) {
+    if (!out || (n && !keys)) return BO_ERR_ARG;
+    *out = NULL;
+    uint64_t total = 0;
+    for (uint64_t c = 0; c < n_chunks; c++) total += chunk_lens[c];
+    if (total != n) return BO_ERR_ARG;
+    if (!(gamma > 1.01)) return BO_ERR_GAMMA; /* src/lib.rs:562 */
+#ifdef _OPENMP
+    if (nthreads <= 0) nthreads = omp_get_max_threads();
+#else
+    nthreads = 1;
+#endif
+    const uint64_t MAX_BUFFER_SIZE = 50000000ULL;
+    const uint64_t min_buffer_keys_threshold = (uint64_t)(0.01f * (float)n); /* f32 arithmetic, src/lib.rs:556-557 */
+    bo_mphf *m = mphf_alloc();
+    if (!m) return BO_ERR_NOMEM;
+    uint8_t *done = (uint8_t *)calloc((size_t)(n ? n : 1), 1); /* done_keys, one byte per key position */
+    uint64_t *buffered = NULL;
+    uint64_t n_buffered = 0, n_done = 0, iter = 0;
+    int buffer_keys = 0, rc = BO_OK;
+    if (!done) { bo_free(m); return BO_ERR_NOMEM; }
+    for (;;) {
+        if (has_max_iters && iter > max_iters) { rc = BO_ERR_MAX_ITERS; break; } /* src/lib.rs:570-573 */
+        const uint64_t remaining = iter == 0 ? n : n - n_done;
+        if (remaining == 0) break;
+        if (remaining < MAX_BUFFER_SIZE && remaining < min_buffer_keys_threshold) buffer_keys = 1;
+        if (m->nlevels >= BO_MAX_LEVELS) { rc = BO_ERR_MAX_ITERS; break; }
+        bo_ctx cx;
+        if (ctx_new(&cx, bo_level_size(gamma, remaining), iter)) { rc = BO_ERR_NOMEM; break; }
+        /* job 0 of every chunk, then job 1 of every chunk (Queue::next waits for all of job 0, src/lib.rs:504-532) */
+#pragma omp parallel for num_threads(nthreads) schedule(static)
+        for (uint64_t i = 0; i < n; i++)
+            if (!done[i]) find_collisions(&cx, keys[i]);
+        if (buffer_keys) {
+            buffered = (uint64_t *)malloc((size_t)(remaining ? remaining : 1) * 8);
+            if (!buffered) { bv_free(&cx.a); bv_free(&cx.collide); rc = BO_ERR_NOMEM; break; }
+        }
+        uint64_t newly_done = 0;
+#pragma omp parallel for num_threads(nthreads) schedule(static) reduction(+ : newly_done)
+        for (uint64_t i = 0; i < n; i++) {
+            if (done[i]) continue;
+            if (filter(&cx, keys[i])) {
+                if (buffer_keys) {
+                    uint64_t pos;
+#pragma omp atomic capture
+                    pos = n_buffered++;
+                    buffered[pos] = keys[i];
+                }
+            } else {
+                done[i] = 1;
+                newly_done++;
+            }
+        }
+        n_done += newly_done;
+        m->bv[m->nlevels++] = cx.a;
+        bv_free(&cx.collide);
+        iter += 1;
+        if (buffer_keys) break;
+    }
+    free(done);
+    if (rc == BO_OK && n_buffered > 1) { /* src/lib.rs:652-661 */
+        bo_mphf *tail = NULL;
+        rc = bo_build_parallel(buffered, n_buffered, 1.7, 1, iter, nthreads, &tail);
+        if (rc == BO_OK) {
+            for (uint32_t l = 0; l < tail->nlevels && rc == BO_OK; l++) {
+                if (m->nlevels >= BO_MAX_LEVELS) { rc = BO_ERR_MAX_ITERS; break; }
+                m->bv[m->nlevels++] = tail->bv[l];
+                tail->bv[l].v = NULL;
+            }
+            bo_free(tail);
+        }
+    }
+    free(buffered);
+    if (rc == BO_OK) rc = compute_ranks(m);
+    if (rc != BO_OK) { bo_free(m); return rc; }
+    *out = m;
+    return BO_OK;
+}
+
 /* build an Mphf from already-serialised levels (the serde data model: per level bits, words, ranks) */
 BO_API int bo_from_levels(uint32_t nlevels, const uint64_t *bits, const uint64_t *const *words,
                           const uint64_t *const *ranks, bo_mphf **out) {

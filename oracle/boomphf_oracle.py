@@ -49,6 +49,10 @@ def lib():
     L.bo_build_serial.argtypes = [vp, u64, dbl, C.POINTER(vp)]
     L.bo_build_parallel.restype = i32
     L.bo_build_parallel.argtypes = [vp, u64, dbl, i32, u64, i32, C.POINTER(vp)]
+    L.bo_build_chunked_serial.restype = i32
+    L.bo_build_chunked_serial.argtypes = [vp, vp, u64, u64, dbl, C.POINTER(vp)]
+    L.bo_build_chunked_parallel.restype = i32
+    L.bo_build_chunked_parallel.argtypes = [vp, vp, u64, u64, dbl, i32, u64, i32, C.POINTER(vp)]
     L.bo_from_levels.restype = i32
     L.bo_from_levels.argtypes = [u32, vp, vp, vp, C.POINTER(vp)]
     L.bo_num_levels.restype = u32
@@ -129,6 +133,32 @@ class OracleMphf:
         out = C.c_void_p()
         rc = lib().bo_build_parallel(_ptr(keys), len(keys), float(gamma), 0 if starting_seed is None else 1,
                                      0 if starting_seed is None else int(starting_seed), int(nthreads), C.byref(out))
+        if rc != BO_OK:
+            raise OracleError(rc)
+        return cls(out.value)
+
+    @classmethod
+    def from_chunked_iterator(cls, gamma, chunks, n):
+        """Mphf::from_chunked_iterator(gamma, &chunks, n)  (src/lib.rs:112)"""
+        arrs = [_as_u64(c) for c in chunks]
+        k = np.concatenate(arrs) if arrs else np.zeros(0, dtype=np.uint64)
+        lens = np.array([a.size for a in arrs], dtype=np.uint64)
+        out = C.c_void_p()
+        rc = lib().bo_build_chunked_serial(_ptr(k), _ptr(lens), lens.size, int(n), float(gamma), C.byref(out))
+        if rc != BO_OK:
+            raise OracleError(rc)
+        return cls(out.value)
+
+    @classmethod
+    def from_chunked_iterator_parallel(cls, gamma, chunks, max_iters, n, num_threads=0):
+        """Mphf::from_chunked_iterator_parallel(gamma, &chunks, max_iters, n, num_threads)  (src/lib.rs:539)"""
+        arrs = [_as_u64(c) for c in chunks]
+        k = np.concatenate(arrs) if arrs else np.zeros(0, dtype=np.uint64)
+        lens = np.array([a.size for a in arrs], dtype=np.uint64)
+        out = C.c_void_p()
+        rc = lib().bo_build_chunked_parallel(_ptr(k), _ptr(lens), lens.size, int(n), float(gamma),
+                                             0 if max_iters is None else 1, 0 if max_iters is None else int(max_iters),
+                                             int(num_threads), C.byref(out))
         if rc != BO_OK:
             raise OracleError(rc)
         return cls(out.value)

@@ -33,7 +33,7 @@ SYMBOLS = [
     "bphf_map_get_batch_u64", "bphf_get_build_stats", "bphf_set_profile", "bphf_set_build_mode", "bphf_set_query_mode", "bphf_keygen_u64",
     "bphf_check_permutation", "bphf_checksum_u64", "bphf_host_alloc", "bphf_host_free",
     "bphf_comm_create", "bphf_comm_ipc_handle", "bphf_comm_connect_ipc", "bphf_comm_connect_local",
-    "bphf_comm_destroy", "bphf_build_sharded_u64",
+    "bphf_comm_destroy", "bphf_build_sharded_u64", "bphf_build_chunked_u64",
 ]
 
 
@@ -145,6 +145,8 @@ def lib():
     L.bphf_comm_connect_local.argtypes = [vp, C.POINTER(vp)]
     L.bphf_comm_destroy.restype = None
     L.bphf_comm_destroy.argtypes = [vp]
+    L.bphf_build_chunked_u64.restype = i32
+    L.bphf_build_chunked_u64.argtypes = [vp, vp, u64, u64, dbl, i32, i32, u64, i32, i32, C.POINTER(vp)]
     L.bphf_build_sharded_u64.restype = i32
     L.bphf_build_sharded_u64.argtypes = [vp, vp, u64, u64, dbl, i32, u64, i32, C.POINTER(vp)]
     _lib = L

@@ -249,6 +249,14 @@ static QView query_view(const bphf_mphf* m) {
 // fraction 1 - exp(-k/bits), +-6 sigma).  It only sizes buffers, grids and shared memory and decides
 // which kernel variants get enqueued; the kernels read the real sizes from the device state.
 // ------------------------------------------------------------------------------------------------
+// Mphf::from_chunked_iterator_parallel semantics (src/lib.rs:539-667); mode 0 = plain new / new_parallel
+struct ChunkSpec {
+    int mode = 0;
+    uint64_t thr = 0;        // (0.01f32 * n as f32) as u64
+    int has_max = 0;
+    uint64_t max_iters = 0;
+};
+
 struct LevelPlan {
     uint64_t k_up = 0, k_lo = 0;
     bool maybe_bucket = false, surely_bucket = false;
@@ -279,12 +287,16 @@ static double bucket_fit_bits() {
     return v;
 }
 
-static Plan make_plan(uint64_t n, double gamma, uint32_t slots, bool bucket_enable, uint64_t min_keys, double frac = 1.0) {
+static Plan make_plan(uint64_t n, double gamma, uint32_t slots, bool bucket_enable, uint64_t min_keys, double frac = 1.0,
+                      const ChunkSpec* chunk = nullptr) {
     Plan p;
     uint64_t k_up = n, k_lo = n;
     uint64_t words = 0;
+    bool switched = false;  // chunked-parallel: the levels after the first small one use gamma 1.7
     for (uint32_t level = 0; level <= BPHF_MAX_LEVELS && k_up > 0; level++) {
-        const uint64_t bits_up = level_size(gamma, k_up), bits_lo = level_size(gamma, k_lo);
+        const double g = switched ? 1.7 : gamma;
+        if (chunk && chunk->mode && !switched && k_lo < 50000000ULL && k_lo < chunk->thr) switched = true;
+        const uint64_t bits_up = level_size(g, k_up), bits_lo = level_size(g, k_lo);
         if (level == 0 && (bits_up >> 32)) p.maybe_big = true;
         if (k_up <= TAIL_MAX_KEYS && bits_up <= TAIL_MAX_BITS) break;
         words += round_up8((bits_up + 63) / 64);
@@ -669,7 +681,7 @@ enum { BUILD_RETRY_PLAIN = 1000 };
 // n = keys of this shard; comm == nullptr: unsharded (n_global == n)
 static int build_once(const uint64_t* keys, uint64_t n, double gamma, int has_seed, uint64_t seed, int device,
                       int keys_mem, void* stream, bool bucket_enable, uint64_t min_keys, uint32_t rebuilds, bphf_mphf** out,
-                      bphf_comm* comm = nullptr, uint64_t n_global_arg = 0) {
+                      bphf_comm* comm = nullptr, uint64_t n_global_arg = 0, const ChunkSpec* chunk = nullptr) {
     const DeviceInfo& info = device_info(device);
     DeviceGuard guard(device);
     cudaStream_t s = stream ? (cudaStream_t)stream : own_stream(device, false);
@@ -683,7 +695,7 @@ static int build_once(const uint64_t* keys, uint64_t n, double gamma, int has_se
     CK(cudaEventCreate(&b.ev_end));
     CK(cudaEventRecord(b.ev_begin, s));
 
-    Plan plan = make_plan(n_global, gamma, b.slots(), bucket_enable, min_keys, shard_frac);
+    Plan plan = make_plan(n_global, gamma, b.slots(), bucket_enable, min_keys, shard_frac, chunk);
     b.maybe_big = plan.maybe_big;
     uint32_t gather_level = NO_LEVEL;
     if (comm) {
@@ -733,6 +745,13 @@ static int build_once(const uint64_t* keys, uint64_t n, double gamma, int has_se
     st.shard_rank = comm ? (uint32_t)comm->rank : 0;
     st.shard_world = comm ? (uint32_t)comm->world : 1;
     st.shard_frac = shard_frac;
+    st.switch_level = NO_LEVEL;
+    if (chunk && chunk->mode) {
+        st.chunk_mode = 1;
+        st.chunk_thr = chunk->thr;
+        st.chunk_has_max = (uint32_t)chunk->has_max;
+        st.chunk_max_iters = chunk->max_iters;
+    }
     st.gather_level = gather_level;
     st.list_ready_level = NO_LEVEL;
     if (!try_make_level(&st, 0, n_global)) return fail(BPHF_ERR_INTERNAL, "level 0 does not fit the planned buffers");
@@ -946,7 +965,7 @@ static int build_once(const uint64_t* keys, uint64_t n, double gamma, int has_se
 }
 
 static int build_impl(const uint64_t* keys, uint64_t n, double gamma, int has_seed, uint64_t seed, int device,
-                      int keys_mem, void* stream, bphf_mphf** out) {
+                      int keys_mem, void* stream, bphf_mphf** out, const ChunkSpec* chunk = nullptr) {
     if (!out) return fail(BPHF_ERR_ARG, "out is null");
     *out = nullptr;
     if (n && !keys) return fail(BPHF_ERR_ARG, "keys is null");
@@ -961,11 +980,11 @@ static int build_impl(const uint64_t* keys, uint64_t n, double gamma, int has_se
         bucket = (double)level_size(gamma, n) > fit_bits;
         min_keys = (uint64_t)(fit_bits / gamma);
     }
-    int rc = build_once(keys, n, gamma, has_seed, seed, device, keys_mem, stream, bucket, min_keys, 0, out);
+    int rc = build_once(keys, n, gamma, has_seed, seed, device, keys_mem, stream, bucket, min_keys, 0, out, nullptr, 0, chunk);
     if (rc == BUILD_RETRY_PLAIN) {
         // a bucket region overflowed (heavily duplicated or otherwise non-random input): the plain L2-atomic
         // kernels have no such limit.  Still the GPU path -- there is no CPU fallback anywhere.
-        rc = build_once(keys, n, gamma, has_seed, seed, device, keys_mem, stream, false, 0, 1, out);
+        rc = build_once(keys, n, gamma, has_seed, seed, device, keys_mem, stream, false, 0, 1, out, nullptr, 0, chunk);
         if (rc == BUILD_RETRY_PLAIN) return fail(BPHF_ERR_INTERNAL, "bucket overflow reported by an unbucketed build");
     }
     return rc;
@@ -1048,6 +1067,76 @@ BPHF_API int bphf_build_u64(const uint64_t* keys, uint64_t n, double gamma, int 
                             int keys_mem, void* stream, bphf_mphf** out) {
     API_BEGIN
     return build_impl(keys, n, gamma, has_seed, seed, device, keys_mem, stream, out);
+    API_END
+}
+
+// ---- chunked construction --------------------------------------------------------
+// Mphf::from_chunked_iterator (src/lib.rs:112-226) and from_chunked_iterator_parallel (:539-667) for T = u64.
+// The chunks are gathered into one device array as they are handed over (H2D per chunk for host chunks) and the
+// cascade runs with the reference's chunked semantics.  The key set has to fit the GPU's memory (180 GB ~ 1e10
+// keys with the work buffers); what the reference adds beyond that -- re-iterating an out-of-core source once per
+// level -- is not reproduced.
+BPHF_API int bphf_build_chunked_u64(const uint64_t* const* chunks, const uint64_t* chunk_lens, uint64_t n_chunks, uint64_t n,
+                                    double gamma, int parallel_variant, int has_max_iters, uint64_t max_iters, int device,
+                                    int keys_mem, bphf_mphf** out) {
+    API_BEGIN
+    if (!out) return fail(BPHF_ERR_ARG, "out is null");
+    *out = nullptr;
+    if (n_chunks && (!chunks || !chunk_lens)) return fail(BPHF_ERR_ARG, "null chunk table");
+    if (keys_mem != BPHF_MEM_HOST && keys_mem != BPHF_MEM_DEVICE) return fail(BPHF_ERR_ARG, "bad keys_mem");
+    uint64_t total = 0;
+    for (uint64_t c = 0; c < n_chunks; c++) {
+        if (chunk_lens[c] && !chunks[c]) return fail(BPHF_ERR_ARG, "null chunk");
+        total += chunk_lens[c];
+    }
+    // the reference walks exactly n items: fewer panics ("max number of items overflowed"), more never terminates
+    if (total != n) return fail(BPHF_ERR_ARG, "n does not match the total length of the chunks");
+    if (!(gamma > 1.01)) return fail(BPHF_ERR_GAMMA, "assertion failed: gamma > 1.01");  // src/lib.rs:125,562
+    device_info(device);
+    DeviceGuard guard(device);
+    cudaStream_t s = own_stream(device, false);
+    if (parallel_variant && n == 0) {
+        // keys_remaining == 0 on entry: the loop breaks before the first level (src/lib.rs:580-582) -> no levels
+        std::unique_ptr<bphf_mphf> m(new bphf_mphf());
+        m->device = device;
+        CK(cudaMallocAsync((void**)&m->d_words, 64, s));
+        CK(cudaMallocAsync((void**)&m->d_ranks, 8, s));
+        upload_level_table(m.get(), s);
+        *out = m.release();
+        return BPHF_OK;
+    }
+    // gather: one contiguous device array (a single device chunk is used in place)
+    const uint64_t* d_keys = nullptr;
+    uint64_t* owned = nullptr;
+    if (keys_mem == BPHF_MEM_DEVICE && n_chunks == 1) {
+        d_keys = chunks[0];
+    } else if (n) {
+        CK(cudaMallocAsync((void**)&owned, n * 8, s));
+        uint64_t off = 0;
+        for (uint64_t c = 0; c < n_chunks; c++) {
+            if (!chunk_lens[c]) continue;
+            CK(cudaMemcpyAsync(owned + off, chunks[c], chunk_lens[c] * 8,
+                               keys_mem == BPHF_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s));
+            off += chunk_lens[c];
+        }
+        d_keys = owned;
+    }
+    ChunkSpec cs;
+    if (parallel_variant) {
+        cs.mode = 1;
+        cs.thr = (uint64_t)(0.01f * (float)n);  // f32 arithmetic as in src/lib.rs:556-557
+        cs.has_max = has_max_iters ? 1 : 0;
+        cs.max_iters = max_iters;
+    }
+    int rc;
+    try {
+        rc = build_impl(d_keys, n, gamma, 0, 0, device, BPHF_MEM_DEVICE, s, out, parallel_variant ? &cs : nullptr);
+    } catch (...) {
+        if (owned) cudaFreeAsync(owned, s);
+        throw;
+    }
+    if (owned) CK(cudaFreeAsync(owned, s));
+    return rc;
     API_END
 }
 

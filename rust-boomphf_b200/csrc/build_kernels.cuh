@@ -95,9 +95,23 @@ __host__ __device__ inline void finish_level(BuildState* st, uint32_t level, uin
     st->redo_count = 0;
     st->uniq_count = 0;
     st->fin_ticket = 0;
-    // reference: the `iter > MAX_ITERS` check sits inside `while !redo_keys.is_empty()` after
-    // `iter += 1`, i.e. it fires for level index >= 100 even when nothing is left to redo
-    if (level >= 1 && level + 1 > BPHF_MAX_ITERS) {
+    if (st->chunk_mode) {
+        // from_chunked_iterator_parallel: a chunked level l is refused when l > max_iters (src/lib.rs:570-573, checked
+        // before the level is built, only while keys remain); the tail is a new_parallel of its own whose counter
+        // starts at the switch (src/lib.rs:654) and fires like the check below
+        const uint32_t next = level + 1;
+        const bool tail_phase = st->switch_level != NO_LEVEL && next > st->switch_level;
+        bool fail = next >= BPHF_MAX_LEVELS;
+        if (!tail_phase) fail = fail || (k_next != 0 && st->chunk_has_max && (uint64_t)next > st->chunk_max_iters);
+        else fail = fail || (next - st->switch_level > BPHF_MAX_ITERS);
+        if (fail) {
+            st->status = ST_ERR_MAX_ITERS;
+            st->err_info = k_next;
+            return;
+        }
+    } else if (level >= 1 && level + 1 > BPHF_MAX_ITERS) {
+        // reference: the `iter > MAX_ITERS` check sits inside `while !redo_keys.is_empty()` after
+        // `iter += 1`, i.e. it fires for level index >= 100 even when nothing is left to redo
         st->status = ST_ERR_MAX_ITERS;
         st->err_info = k_next;
         return;

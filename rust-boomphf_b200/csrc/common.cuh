@@ -76,6 +76,13 @@ struct BuildState {
     uint32_t gather_level;     // sharded: level at which all remaining keys are collected on every shard (host plan)
     uint32_t list_ready_level; // level whose complete key list already sits in buf[level & 1] (after the collect)
     uint64_t peer_count[SHARD_MAX];  // sharded: every shard's key count, as carried by the last list-sum barrier
+    // Mphf::from_chunked_iterator_parallel (src/lib.rs:539-667): levels use the caller's gamma until fewer than
+    // min(50 M, chunk_thr) keys are left; the levels after that one are built by new_parallel(1.7, ..) (:654)
+    uint64_t chunk_thr;        // (0.01f32 * n as f32) as u64; only read when chunk_mode != 0
+    uint64_t chunk_max_iters;  // max_iters of the chunked levels (chunk_has_max != 0)
+    uint32_t chunk_mode, chunk_has_max;
+    uint32_t switch_level;     // first level built with gamma 1.7 (NO_LEVEL: not reached yet)
+    uint32_t pad2_;
     double shard_frac;         // this shard's share of the keys (n_local / n_global; 1 unsharded): sizes bucket regions
     LevelDesc lv[BPHF_MAX_LEVELS + 1];
 };
@@ -155,7 +162,12 @@ __host__ __device__ inline bool bucket_geometry(uint64_t bits, uint64_t k, uint3
 // fill in lv[level] for k keys; returns false when the arena cannot hold it (need -> words required)
 __host__ __device__ inline void make_level(BuildState* st, uint32_t level, uint64_t k) {
     LevelDesc& d = st->lv[level];
-    d.bits = level_size(st->gamma, k);
+    double gamma = st->gamma;
+    if (st->chunk_mode) {
+        if (level >= st->switch_level) gamma = 1.7;  // the tail of from_chunked_iterator_parallel, src/lib.rs:654
+        else if (st->switch_level == NO_LEVEL && k < 50000000ULL && k < st->chunk_thr) st->switch_level = level + 1;
+    }
+    d.bits = level_size(gamma, k);
     d.n_words = (d.bits + 63) / 64;
     d.word_off = st->words_used;
     d.k_in = k;

@@ -97,6 +97,37 @@ class Mphf:
         return cls._build(gamma, objects, starting_seed, device, stream)
 
     @classmethod
+    def _build_chunked(cls, gamma, objects, n, parallel, max_iters, device):
+        parts = [_as_keys(c) for c in objects]
+        mems = {p[2] for p in parts}
+        if len(mems) > 1:
+            raise TypeError("chunks must all live in host memory or all on the device")
+        mem = mems.pop() if mems else N.MEM_HOST
+        for p in parts:
+            if p[3] is not None:
+                device = p[3]
+        ptrs = (C.c_void_p * max(len(parts), 1))(*[p[0].value for p in parts])
+        lens = (C.c_uint64 * max(len(parts), 1))(*[p[1] for p in parts])
+        out = C.c_void_p()
+        rc = N.lib().bphf_build_chunked_u64(ptrs, lens, len(parts), int(n), float(gamma), 1 if parallel else 0,
+                                            0 if max_iters is None else 1, 0 if max_iters is None else int(max_iters),
+                                            int(device), mem, C.byref(out))
+        del parts
+        _check(rc)
+        return cls(out.value, int(device))
+
+    @classmethod
+    def from_chunked_iterator(cls, gamma, objects, n, device=0):
+        """Mphf::from_chunked_iterator(gamma, &objects, n)  (src/lib.rs:112): objects = iterable of key chunks"""
+        return cls._build_chunked(gamma, list(objects), n, False, None, device)
+
+    @classmethod
+    def from_chunked_iterator_parallel(cls, gamma, objects, max_iters, n, num_threads=0, device=0):
+        """Mphf::from_chunked_iterator_parallel(gamma, &objects, max_iters, n, num_threads)  (src/lib.rs:539).
+        num_threads is accepted for signature parity; the GPU is the pool."""
+        return cls._build_chunked(gamma, list(objects), n, True, max_iters, device)
+
+    @classmethod
     def from_levels(cls, levels, device=0):
         """Upload a deserialised Mphf: levels = [(bits, words u64[], ranks u64[]), ...]."""
         n = len(levels)

@@ -360,3 +360,50 @@ def test_bucket_overflow_falls_back_to_plain_kernels(pkg, small_buckets):
     # a valid build right after the failed one is unaffected
     ok = pkg.Mphf.new_parallel(1.7, base, None)
     assert ok.total_dims()[2] == len(base)
+
+
+# ---- chunked constructors ---------------------------------------------------------------
+@pytest.mark.parametrize("n", [0, 1, 99, 100, 101, 5000, 300_001, 3_000_000])
+@pytest.mark.parametrize("gamma", [1.7, 2.0, 5.0])
+def test_from_chunked_iterator_parity(pkg, oracle, n, gamma):
+    keys = oracle.keygen(n, seed=n + 17, kind=0)
+    chunks = [keys[:0]] + list(np.array_split(keys, 4)) if n else [keys]
+    m = pkg.Mphf.from_chunked_iterator(gamma, chunks, n)
+    assert_same_levels(m.levels(), oracle.OracleMphf.from_chunked_iterator(gamma, chunks, n).levels())
+    mp = pkg.Mphf.from_chunked_iterator_parallel(gamma, chunks, None, n, 4)
+    ref = oracle.OracleMphf.from_chunked_iterator_parallel(gamma, chunks, None, n)
+    assert_same_levels(mp.levels(), ref.levels())
+    if n:
+        h = mp.hash_batch(keys)
+        assert np.array_equal(h, ref.hash_batch(keys, nthreads=0))
+        assert np.array_equal(np.sort(h), np.arange(n, dtype=np.uint64))
+
+
+def test_from_chunked_iterator_parallel_gamma_switch_and_limits(pkg, oracle):
+    keys = oracle.keygen(1_000_000, seed=4, kind=1)
+    chunks = np.array_split(keys, 9)
+    for gamma in (1.02, 1.3, 17.5):
+        m = pkg.Mphf.from_chunked_iterator_parallel(gamma, chunks, None, len(keys))
+        assert_same_levels(m.levels(), oracle.OracleMphf.from_chunked_iterator_parallel(gamma, chunks, None, len(keys)).levels())
+    # max_iters guards the chunked levels only
+    with pytest.raises(pkg.MphfPanic) as e:
+        pkg.Mphf.from_chunked_iterator_parallel(2.0, chunks, 2, len(keys))
+    assert e.value.code == -3
+    ok = pkg.Mphf.from_chunked_iterator_parallel(2.0, chunks, 8, len(keys))
+    assert_same_levels(ok.levels(), oracle.OracleMphf.from_chunked_iterator_parallel(2.0, chunks, 8, len(keys)).levels())
+    with pytest.raises(pkg.MphfPanic) as e:
+        pkg.Mphf.from_chunked_iterator(1.7, chunks, len(keys) + 1)     # n does not match the chunks
+    assert e.value.code == -1
+    with pytest.raises(pkg.MphfPanic) as e:
+        pkg.Mphf.from_chunked_iterator_parallel(1.0, chunks, None, len(keys))
+    assert e.value.code == -2
+
+
+def test_from_chunked_iterator_device_chunks(pkg, oracle):
+    import torch
+    keys = oracle.keygen(2_000_000, seed=12, kind=0)
+    dev = [torch.from_numpy(c.view(np.int64)).cuda() for c in np.array_split(keys, 3)]
+    m = pkg.Mphf.from_chunked_iterator_parallel(2.0, dev, None, len(keys))
+    assert_same_levels(m.levels(), oracle.OracleMphf.from_chunked_iterator_parallel(2.0, [keys], None, len(keys)).levels())
+    one = pkg.Mphf.from_chunked_iterator(1.7, [torch.from_numpy(keys.view(np.int64)).cuda()], len(keys))
+    assert_same_levels(one.levels(), oracle.OracleMphf.new(1.7, keys).levels())

@@ -224,3 +224,47 @@ def test_keygen_is_distinct_and_matches_golden(oracle):
     assert (oracle.keygen(100000, 3, 1) < np.uint64(1 << 62)).all()
     # chunked generation is consistent
     assert np.array_equal(oracle.keygen(1000, 3, 0, start=500), oracle.keygen(1500, 3, 0)[500:])
+
+
+# ---- chunked constructors ----------------------------------------------------------------
+def _same(a, b):
+    return len(a) == len(b) and all(x[0] == y[0] and np.array_equal(x[1], y[1]) and np.array_equal(x[2], y[2])
+                                    for x, y in zip(a, b))
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 99, 100, 101, 1000, 65_537])
+@pytest.mark.parametrize("gamma", [1.7, 2.0, 5.0])
+def test_chunked_serial_equals_new(oracle, n, gamma):
+    # from_chunked_iterator walks positions with a done_keys bitmap instead of a redo list: same levels as Mphf::new
+    keys = oracle.keygen(n, seed=n + 7, kind=0)
+    chunks = np.array_split(keys, 5) if n else [keys]
+    assert _same(oracle.OracleMphf.from_chunked_iterator(gamma, chunks, n).levels(),
+                 oracle.OracleMphf.new(gamma, keys).levels())
+
+
+@pytest.mark.parametrize("n", [1, 2, 99, 100, 101, 1000, 65_537, 300_001])
+def test_chunked_parallel_with_gamma_1_7_equals_new_parallel(oracle, n):
+    keys = oracle.keygen(n, seed=n + 9, kind=0)
+    got = oracle.OracleMphf.from_chunked_iterator_parallel(1.7, np.array_split(keys, 3), None, n).levels()
+    assert _same(got, oracle.OracleMphf.new_parallel(1.7, keys).levels())
+
+
+def test_chunked_parallel_quirks(oracle):
+    # empty input: the loop breaks before the first level (src/lib.rs:580-582) -> zero levels (Mphf::new has one)
+    assert oracle.OracleMphf.from_chunked_iterator_parallel(1.7, [np.zeros(0, np.uint64)], None, 0).num_levels == 0
+    # gamma != 1.7: the levels after the first one with < 1 % of the keys are built with 1.7 (src/lib.rs:654)
+    keys = oracle.keygen(200_000, seed=3, kind=0)
+    chunked = oracle.OracleMphf.from_chunked_iterator_parallel(2.0, np.array_split(keys, 5), None, len(keys))
+    plain = oracle.OracleMphf.new_parallel(2.0, keys)
+    cb, pb = [l[0] for l in chunked.levels()], [l[0] for l in plain.levels()]
+    first_small = next(i for i, l in enumerate(plain.levels()) if pb[i] < 2.0 * 0.01 * len(keys))
+    assert cb[:first_small + 1] == pb[:first_small + 1] and cb[first_small + 1] != pb[first_small + 1]
+    h = chunked.hash_batch(keys)
+    assert np.array_equal(np.sort(h), np.arange(len(keys), dtype=np.uint64))
+    # max_iters only guards the chunked levels
+    with pytest.raises(oracle.OracleError):
+        oracle.OracleMphf.from_chunked_iterator_parallel(2.0, [keys], 2, len(keys))
+    assert oracle.OracleMphf.from_chunked_iterator_parallel(2.0, [keys], 8, len(keys)).num_levels == chunked.num_levels
+    # n must match
+    with pytest.raises(oracle.OracleError):
+        oracle.OracleMphf.from_chunked_iterator_parallel(1.7, [keys], None, len(keys) - 1)
