@@ -84,6 +84,23 @@ BPHF_API int bphf_wy_swap_8byte_tail(void);
 BPHF_API int bphf_build_u64(const uint64_t *keys, uint64_t n, double gamma, int has_seed, uint64_t seed,
                             int device, int keys_mem, void *stream, bphf_mphf **out);
 
+/* ---- keys other than u64 ----------------------------------------------
+ * Mphf<T> for the T whose Hash byte stream fits one wyhash tail word (the types of the reference's own
+ * quickcheck tests, src/lib.rs:857-879, minus strings):
+ *   BPHF_KEY_U64   (width ignored)  u64, i64, usize, isize            -- identical to bphf_build_u64
+ *   BPHF_KEY_UINT  width 1 | 2 | 4  u8/i8, u16/i16, u32/i32           -- one write of `width` bytes
+ *   BPHF_KEY_BYTES width 1..8       [u8; N], &[u8], Vec<u8> of length N -- write_usize(N), then N bytes
+ * keys: n keys packed back to back, `width` bytes each.  Lookups take keys of the handle's kind. */
+enum { BPHF_KEY_U64 = 0, BPHF_KEY_UINT = 1, BPHF_KEY_BYTES = 2 };
+BPHF_API int bphf_build_keys(const void *keys, uint64_t n, int key_kind, int key_width, double gamma, int has_seed,
+                             uint64_t seed, int device, int keys_mem, bphf_mphf **out);
+BPHF_API int bphf_hash_batch_keys(const bphf_mphf *m, const void *keys, uint64_t n, uint64_t *out, int mem,
+                                  void *stream);
+BPHF_API int bphf_from_levels_keys(uint32_t n_levels, const uint64_t *bits, const uint64_t *const *words,
+                                   const uint64_t *const *ranks, int key_kind, int key_width, int device,
+                                   bphf_mphf **out);
+BPHF_API int bphf_key_kind(const bphf_mphf *m, int *key_kind, int *key_width);
+
 /* ---- chunked construction ---------------------------------------------
  * Mphf::from_chunked_iterator(gamma, &chunks, n)                       src/lib.rs:112   (parallel_variant = 0)
  * Mphf::from_chunked_iterator_parallel(gamma, &chunks, max_iters, n, num_threads)  :539 (parallel_variant = 1)

@@ -28,6 +28,7 @@
 #endif
 
 #define BO_API __attribute__((visibility("default")))
+#define BO_ERR_ARG_EARLY (-1)
 
 /* 1: wyhash-v1 `read64_swapped` for an exactly-8-byte tail (primary candidate, matches the
  * C wyhash v1 `__wyr64` and the crate's `read_rest` case 8).  0: plain little-endian read.
@@ -107,6 +108,9 @@ static inline uint64_t wyhash_finish(uint64_t total_len, uint64_t seed) { return
 BO_API uint64_t bo_wyhash_bytes(const uint8_t *p, uint64_t len, uint64_t seed) {
     return wyhash_finish(len, wyhash_core(p, (size_t)len, seed));
 }
+/* one Hasher::write and Hasher::finish, exposed so tests can rebuild any key's hash from its byte stream */
+BO_API uint64_t bo_wyhash_core(const uint8_t *p, uint64_t len, uint64_t state) { return wyhash_core(p, (size_t)len, state); }
+BO_API uint64_t bo_wyhash_finish(uint64_t total_len, uint64_t state) { return wyhash_finish(total_len, state); }
 /* wyhash::wyrng(&mut seed) -- second README known answer (validates constants + wymum) */
 BO_API uint64_t bo_wyrng(uint64_t *seed) {
     *seed += P0;
@@ -118,11 +122,36 @@ BO_API uint64_t bo_wyrng(uint64_t *seed) {
  * ---------------------------------------------------------------------------------------- */
 /* src/lib.rs:60-65.  `1 << (iter + iter)` on u64: release-mode shift wraps modulo 64
  * (debug builds panic for iter >= 32); u64::hash = one 8-byte native-endian write, then finish. */
+/* Key kind: which byte stream `T::hash` feeds the hasher.  Keys are handed to every function of
+ * this file as u64 values holding the key's bytes little-endian in their low `width` bytes.
+ *   kind 0: u64 / i64 / usize / isize  -> Hasher::write_u64          = one 8-byte write
+ *   kind 1: u8 / u16 / u32 (and signed) -> write_u8 / _u16 / _u32     = one write of `width` bytes
+ *   kind 2: [u8; N], &[u8], Vec<u8>     -> impl Hash for [T]: write_usize(N) (8 bytes), then one write of N bytes
+ * The wyhash Hasher runs the core once per write, carrying h, and finish() mixes in the total byte count.
+ * Process-wide setting (test infrastructure; set before building / hashing). */
+static int g_key_kind = 0, g_key_width = 8;
+BO_API int bo_set_key_kind(int kind, int width) {
+    if (kind == 0) width = 8;
+    if (kind < 0 || kind > 2 || width < 1 || width > 8) return BO_ERR_ARG_EARLY;
+    g_key_kind = kind;
+    g_key_width = width;
+    return 0;
+}
 BO_API uint64_t bo_hash_with_seed(uint64_t iter, uint64_t key) {
-    uint64_t seed = 1ULL << ((iter + iter) & 63);
+    uint64_t h = 1ULL << ((iter + iter) & 63);
+    uint64_t size = 0;
     uint8_t b[8];
-    for (int i = 0; i < 8; i++) b[i] = (uint8_t)(key >> (8 * i));
-    return wyhash_finish(8, wyhash_core(b, 8, seed));
+    if (g_key_kind == 2) { /* length prefix: usize N, native endian */
+        const uint64_t len = (uint64_t)g_key_width;
+        for (int i = 0; i < 8; i++) b[i] = (uint8_t)(len >> (8 * i));
+        h = wyhash_core(b, 8, h);
+        size += 8;
+    }
+    const size_t w = (size_t)g_key_width;
+    for (size_t i = 0; i < w; i++) b[i] = (uint8_t)(key >> (8 * i));
+    h = wyhash_core(b, w, h);
+    size += w;
+    return wyhash_finish(size, h);
 }
 /* src/lib.rs:55-58 */
 static inline uint32_t fold(uint64_t v) { return (uint32_t)(v & 0xFFFFFFFFULL) ^ (uint32_t)(v >> 32); }

@@ -39,6 +39,8 @@ def lib():
     L.bo_wyhash_bytes.argtypes = [vp, u64, u64]
     L.bo_wyrng.restype = u64
     L.bo_wyrng.argtypes = [C.POINTER(u64)]
+    L.bo_set_key_kind.restype = i32
+    L.bo_set_key_kind.argtypes = [i32, i32]
     L.bo_hash_with_seed.restype = u64
     L.bo_hash_with_seed.argtypes = [u64, u64]
     L.bo_hashmod.restype = u64
@@ -89,7 +91,38 @@ def _ptr(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
+KIND_U64, KIND_UINT, KIND_BYTES = 0, 1, 2
+
+
+def key_kind(keys):
+    """(kind, width) of a key array by dtype / shape: u64-like -> (0, 8); u32/u16/u8 (and signed) -> (1, w);
+    2-D uint8 (n, N <= 8) = [u8; N] keys -> (2, N)"""
+    a = keys if isinstance(keys, np.ndarray) else None
+    if a is None:
+        return KIND_U64, 8
+    if a.ndim == 2:
+        if a.dtype != np.uint8 or not 1 <= a.shape[1] <= 8:
+            raise TypeError("byte-array keys must be uint8 of shape (n, N <= 8)")
+        return KIND_BYTES, int(a.shape[1])
+    if a.dtype.itemsize == 8:
+        return KIND_U64, 8
+    if a.dtype.kind in "iu" and a.dtype.itemsize in (1, 2, 4):
+        return KIND_UINT, int(a.dtype.itemsize)
+    raise TypeError("unsupported key dtype %s" % a.dtype)
+
+
 def _as_u64(keys):
+    """keys as u64 values holding the key's bytes little-endian in their low bytes"""
+    if isinstance(keys, np.ndarray) and keys.ndim == 2:
+        out = np.zeros(keys.shape[0], dtype=np.uint64)
+        for b in range(keys.shape[1]):
+            out |= keys[:, b].astype(np.uint64) << np.uint64(8 * b)
+        return out
+    if isinstance(keys, np.ndarray) and keys.dtype.itemsize < 8:
+        unsigned = keys.view(np.dtype("u%d" % keys.dtype.itemsize))
+        return np.ascontiguousarray(unsigned.astype(np.uint64))
+    if isinstance(keys, np.ndarray) and keys.dtype == np.int64:
+        return np.ascontiguousarray(keys.view(np.uint64))
     a = np.ascontiguousarray(np.asarray(keys, dtype=np.uint64))
     return a
 
@@ -104,8 +137,12 @@ class OracleError(RuntimeError):
 class OracleMphf:
     """Mirror of `Mphf<u64>` (/root/reference/src/lib.rs:90-96) over the C restatement."""
 
-    def __init__(self, handle):
+    def __init__(self, handle, kind=(KIND_U64, 8)):
         self._h = C.c_void_p(handle)
+        self.kind = kind
+
+    def _use_kind(self):
+        lib().bo_set_key_kind(*self.kind)
 
     def __del__(self):
         try:
@@ -119,23 +156,33 @@ class OracleMphf:
     @classmethod
     def new(cls, gamma, keys):
         """Mphf::new (src/lib.rs:235)"""
+        kind = key_kind(keys)
         keys = _as_u64(keys)
+        lib().bo_set_key_kind(*kind)
         out = C.c_void_p()
-        rc = lib().bo_build_serial(_ptr(keys), len(keys), float(gamma), C.byref(out))
+        try:
+            rc = lib().bo_build_serial(_ptr(keys), len(keys), float(gamma), C.byref(out))
+        finally:
+            lib().bo_set_key_kind(KIND_U64, 8)
         if rc != BO_OK:
             raise OracleError(rc)
-        return cls(out.value)
+        return cls(out.value, kind)
 
     @classmethod
     def new_parallel(cls, gamma, keys, starting_seed=None, nthreads=0):
         """Mphf::new_parallel (src/lib.rs:363)"""
+        kind = key_kind(keys)
         keys = _as_u64(keys)
+        lib().bo_set_key_kind(*kind)
         out = C.c_void_p()
-        rc = lib().bo_build_parallel(_ptr(keys), len(keys), float(gamma), 0 if starting_seed is None else 1,
-                                     0 if starting_seed is None else int(starting_seed), int(nthreads), C.byref(out))
+        try:
+            rc = lib().bo_build_parallel(_ptr(keys), len(keys), float(gamma), 0 if starting_seed is None else 1,
+                                         0 if starting_seed is None else int(starting_seed), int(nthreads), C.byref(out))
+        finally:
+            lib().bo_set_key_kind(KIND_U64, 8)
         if rc != BO_OK:
             raise OracleError(rc)
-        return cls(out.value)
+        return cls(out.value, kind)
 
     @classmethod
     def from_chunked_iterator(cls, gamma, chunks, n):
@@ -201,7 +248,11 @@ class OracleMphf:
     # -- queries ------------------------------------------------------------------------
     def try_hash(self, key):
         """Mphf::try_hash (src/lib.rs:340); None when no level matched"""
-        v = int(lib().bo_try_hash(self._h, int(key)))
+        self._use_kind()
+        try:
+            v = int(lib().bo_try_hash(self._h, int(key)))
+        finally:
+            lib().bo_set_key_kind(KIND_U64, 8)
         return None if v == NONE else v
 
     def hash(self, key):
@@ -214,7 +265,11 @@ class OracleMphf:
     def hash_batch(self, keys, nthreads=1):
         keys = _as_u64(keys)
         out = np.empty(len(keys), dtype=np.uint64)
-        lib().bo_hash_batch(self._h, _ptr(keys), len(keys), _ptr(out), int(nthreads))
+        self._use_kind()
+        try:
+            lib().bo_hash_batch(self._h, _ptr(keys), len(keys), _ptr(out), int(nthreads))
+        finally:
+            lib().bo_set_key_kind(KIND_U64, 8)
         return out
 
     def create_map(self, keys, values):
@@ -295,6 +350,24 @@ def hash_with_seed(it, key):
 
 def hashmod(it, key, n):
     return int(lib().bo_hashmod(int(it), int(key), int(n)))
+
+
+def hash_key_bytes(it, data, prefixed):
+    """hash_with_seed(it, key) for a key that writes `data` (with an 8-byte usize length prefix first when
+    `prefixed`), computed with the byte-string core alone: an independent cross-check of bo_set_key_kind"""
+    h = 1 << ((2 * it) & 63)
+    size = 0
+    L = lib()
+    L.bo_wyhash_core.restype = C.c_uint64
+    L.bo_wyhash_core.argtypes = [C.c_char_p, C.c_uint64, C.c_uint64]
+    L.bo_wyhash_finish.restype = C.c_uint64
+    L.bo_wyhash_finish.argtypes = [C.c_uint64, C.c_uint64]
+    if prefixed:
+        h = L.bo_wyhash_core(len(data).to_bytes(8, "little"), 8, h)
+        size += 8
+    h = L.bo_wyhash_core(bytes(data), len(data), h)
+    size += len(data)
+    return int(L.bo_wyhash_finish(size, h))
 
 
 def wyhash_bytes(data, seed):

@@ -34,6 +34,7 @@ SYMBOLS = [
     "bphf_check_permutation", "bphf_checksum_u64", "bphf_host_alloc", "bphf_host_free",
     "bphf_comm_create", "bphf_comm_ipc_handle", "bphf_comm_connect_ipc", "bphf_comm_connect_local",
     "bphf_comm_destroy", "bphf_build_sharded_u64", "bphf_build_chunked_u64",
+    "bphf_build_keys", "bphf_hash_batch_keys", "bphf_from_levels_keys", "bphf_key_kind",
 ]
 
 
@@ -145,6 +146,14 @@ def lib():
     L.bphf_comm_connect_local.argtypes = [vp, C.POINTER(vp)]
     L.bphf_comm_destroy.restype = None
     L.bphf_comm_destroy.argtypes = [vp]
+    L.bphf_build_keys.restype = i32
+    L.bphf_build_keys.argtypes = [vp, u64, i32, i32, dbl, i32, u64, i32, i32, C.POINTER(vp)]
+    L.bphf_hash_batch_keys.restype = i32
+    L.bphf_hash_batch_keys.argtypes = [vp, vp, u64, vp, i32, vp]
+    L.bphf_from_levels_keys.restype = i32
+    L.bphf_from_levels_keys.argtypes = [u32, vp, vp, vp, i32, i32, i32, C.POINTER(vp)]
+    L.bphf_key_kind.restype = i32
+    L.bphf_key_kind.argtypes = [vp, C.POINTER(i32), C.POINTER(i32)]
     L.bphf_build_chunked_u64.restype = i32
     L.bphf_build_chunked_u64.argtypes = [vp, vp, u64, u64, dbl, i32, i32, u64, i32, i32, C.POINTER(vp)]
     L.bphf_build_sharded_u64.restype = i32

@@ -104,7 +104,7 @@ static const DeviceInfo& device_info(int dev) {
                 (const void*)query_kernel<false>, (const void*)query_kernel<true>, (const void*)map_permute_kernel<false>,
                 (const void*)map_permute_kernel<true>, (const void*)map_get_kernel<false>, (const void*)map_get_kernel<true>,
                 (const void*)pack_query_kernel, (const void*)set_base_rank_kernel, (const void*)query_sync_kernel,
-                (const void*)keygen_kernel, (const void*)check_perm_kernel, (const void*)checksum_kernel,
+                (const void*)key_words_kernel, (const void*)keygen_kernel, (const void*)check_perm_kernel, (const void*)checksum_kernel,
                 (const void*)shard_barrier_kernel, (const void*)or_collide_merge_kernel, (const void*)tail_gather_kernel,
                 (const void*)shard_gather_kernel<false>, (const void*)shard_gather_kernel<true>,
                 (const void*)shard_collect_kernel, (const void*)shard_switch_kernel};
@@ -162,6 +162,7 @@ struct bphf_mphf {
     QLevelP* d_lvp = nullptr;   // packed lookup structure (query_kernels.cuh); null when a level has >= 2^32 bits
     uint4* d_packed = nullptr;
     uint64_t total_gran = 0;
+    KeyCfg kc = make_key_cfg(BPHF_KIND_U64, 8);
     std::vector<LevelDesc> lv;
     bphf_build_stats stats;
     bphf_mphf() { memset(&stats, 0, sizeof stats); }
@@ -241,6 +242,7 @@ static QView query_view(const bphf_mphf* m) {
     v.ranks = m->d_ranks;
     v.packed = m->d_packed;
     v.n_levels = m->n_levels;
+    v.kc = m->kc;
     return v;
 }
 
@@ -251,6 +253,7 @@ static QView query_view(const bphf_mphf* m) {
 // ------------------------------------------------------------------------------------------------
 // Mphf::from_chunked_iterator_parallel semantics (src/lib.rs:539-667); mode 0 = plain new / new_parallel
 struct ChunkSpec {
+    KeyCfg kc = make_key_cfg(BPHF_KIND_U64, 8);  // key kind of the build
     int mode = 0;
     uint64_t thr = 0;        // (0.01f32 * n as f32) as u64
     int has_max = 0;
@@ -732,6 +735,7 @@ static int build_once(const uint64_t* keys, uint64_t n, double gamma, int has_se
     }
 
     BuildState& st = b.hst;
+    st.kc = chunk ? chunk->kc : make_key_cfg(BPHF_KIND_U64, 8);
     st.status = ST_RUNNING;
     st.tail_level = NO_TAIL;
     st.words_cap = plan.words_cap;
@@ -898,6 +902,7 @@ static int build_once(const uint64_t* keys, uint64_t n, double gamma, int has_se
     std::unique_ptr<bphf_mphf> m(new (std::nothrow) bphf_mphf());
     if (!m) return fail(BPHF_ERR_NOMEM, "host allocation failed");
     m->device = device;
+    m->kc = st.kc;
     m->n_levels = st.n_levels;
     m->words_used = st.words_used;
     m->lv.assign(st.lv, st.lv + st.n_levels);
@@ -1271,6 +1276,74 @@ BPHF_API int bphf_build_sharded_u64(bphf_comm* c, const uint64_t* keys, uint64_t
     API_END
 }
 
+static_assert(BPHF_KIND_U64 == BPHF_KEY_U64 && BPHF_KIND_UINT == BPHF_KEY_UINT && BPHF_KIND_BYTES == BPHF_KEY_BYTES,
+              "key kinds of hash.cuh and of the public header must agree");
+static bool valid_key_kind(int kind, int width) {
+    if (kind == BPHF_KIND_U64) return true;
+    if (kind == BPHF_KIND_UINT) return width == 1 || width == 2 || width == 4;
+    if (kind == BPHF_KIND_BYTES) return width >= 1 && width <= 8;
+    return false;
+}
+
+// ---- keys other than u64 -----------------------------------------------------------
+// packed keys of `width` bytes -> tail words (hash.cuh: key_tail_word), one u64 per key, on the device
+static uint64_t* keys_to_words(const void* keys, uint64_t n, const KeyCfg& kc, int mem, cudaStream_t s, const DeviceInfo& info,
+                               std::vector<void*>& scratch) {
+    const size_t bytes = (size_t)n * kc.width;
+    const uint8_t* d_in = static_cast<const uint8_t*>(keys);
+    if (mem == BPHF_MEM_HOST) {
+        void* tmp = nullptr;
+        CK(cudaMallocAsync(&tmp, std::max<size_t>(bytes, 8), s));
+        scratch.push_back(tmp);
+        CK(cudaMemcpyAsync(tmp, keys, bytes, cudaMemcpyHostToDevice, s));
+        d_in = static_cast<const uint8_t*>(tmp);
+    }
+    uint64_t* d_words = nullptr;
+    CK(cudaMallocAsync((void**)&d_words, std::max<uint64_t>(n, 1) * 8, s));
+    scratch.push_back(d_words);
+    const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((n + 255) / 256, (uint64_t)info.sm_count * 16));
+    key_words_kernel<<<grid, 256, 0, s>>>(d_in, kc.width, n, d_words);
+    CK(cudaGetLastError());
+    return d_words;
+}
+
+BPHF_API int bphf_build_keys(const void* keys, uint64_t n, int key_kind, int key_width, double gamma, int has_seed,
+                             uint64_t seed, int device, int keys_mem, bphf_mphf** out) {
+    API_BEGIN
+    if (!out) return fail(BPHF_ERR_ARG, "out is null");
+    *out = nullptr;
+    if (!valid_key_kind(key_kind, key_width)) return fail(BPHF_ERR_ARG, "unsupported key kind / width");
+    if (key_kind == BPHF_KIND_U64)
+        return build_impl(static_cast<const uint64_t*>(keys), n, gamma, has_seed, seed, device, keys_mem, nullptr, out);
+    if (n && !keys) return fail(BPHF_ERR_ARG, "keys is null");
+    if (keys_mem != BPHF_MEM_HOST && keys_mem != BPHF_MEM_DEVICE) return fail(BPHF_ERR_ARG, "bad keys_mem");
+    if (!(gamma > 1.01)) return fail(BPHF_ERR_GAMMA, "assertion failed: gamma > 1.01");
+    const DeviceInfo& info = device_info(device);
+    DeviceGuard guard(device);
+    cudaStream_t s = own_stream(device, false);
+    ChunkSpec spec;
+    spec.kc = make_key_cfg((uint32_t)key_kind, (uint32_t)key_width);
+    std::vector<void*> scratch;
+    int rc;
+    try {
+        const uint64_t* d_words = keys_to_words(keys, n, spec.kc, keys_mem, s, info, scratch);
+        rc = build_impl(d_words, n, gamma, has_seed, seed, device, BPHF_MEM_DEVICE, s, out, &spec);
+    } catch (...) {
+        for (void* p : scratch) cudaFreeAsync(p, s);
+        throw;
+    }
+    for (void* p : scratch) cudaFreeAsync(p, s);
+    return rc;
+    API_END
+}
+
+BPHF_API int bphf_key_kind(const bphf_mphf* m, int* key_kind, int* key_width) {
+    if (!m) return fail(BPHF_ERR_ARG, "null handle");
+    if (key_kind) *key_kind = (int)m->kc.kind;
+    if (key_width) *key_width = (int)m->kc.width;
+    return BPHF_OK;
+}
+
 BPHF_API int bphf_num_levels(const bphf_mphf* m, uint32_t* n_levels) {
     if (!m || !n_levels) return fail(BPHF_ERR_ARG, "null argument");
     *n_levels = m->n_levels;
@@ -1335,9 +1408,26 @@ BPHF_API int bphf_export_all(const bphf_mphf* m, uint64_t* words_out, uint64_t* 
     API_END
 }
 
+static int from_levels_impl(uint32_t n_levels, const uint64_t* bits, const uint64_t* const* words,
+                            const uint64_t* const* ranks, KeyCfg kc, int device, bphf_mphf** out);
+
 BPHF_API int bphf_from_levels(uint32_t n_levels, const uint64_t* bits, const uint64_t* const* words,
                               const uint64_t* const* ranks, int device, bphf_mphf** out) {
     API_BEGIN
+    return from_levels_impl(n_levels, bits, words, ranks, make_key_cfg(BPHF_KIND_U64, 8), device, out);
+    API_END
+}
+
+BPHF_API int bphf_from_levels_keys(uint32_t n_levels, const uint64_t* bits, const uint64_t* const* words,
+                                   const uint64_t* const* ranks, int key_kind, int key_width, int device, bphf_mphf** out) {
+    API_BEGIN
+    if (!valid_key_kind(key_kind, key_width)) return fail(BPHF_ERR_ARG, "unsupported key kind / width");
+    return from_levels_impl(n_levels, bits, words, ranks, make_key_cfg((uint32_t)key_kind, (uint32_t)key_width), device, out);
+    API_END
+}
+
+static int from_levels_impl(uint32_t n_levels, const uint64_t* bits, const uint64_t* const* words,
+                            const uint64_t* const* ranks, KeyCfg kc, int device, bphf_mphf** out) {
     if (!out) return fail(BPHF_ERR_ARG, "out is null");
     *out = nullptr;
     if (n_levels > BPHF_MAX_LEVELS || (n_levels && (!bits || !words || !ranks))) return fail(BPHF_ERR_ARG, "bad level arrays");
@@ -1346,6 +1436,7 @@ BPHF_API int bphf_from_levels(uint32_t n_levels, const uint64_t* bits, const uin
     cudaStream_t s = own_stream(device, false);
     std::unique_ptr<bphf_mphf> m(new bphf_mphf());
     m->device = device;
+    m->kc = kc;
     m->n_levels = n_levels;
     m->lv.resize(n_levels);
     uint64_t off = 0;
@@ -1355,7 +1446,7 @@ BPHF_API int bphf_from_levels(uint32_t n_levels, const uint64_t* bits, const uin
         d.n_words = (bits[l] + 63) / 64;
         d.word_off = off;
         d.k_in = 0;
-        d.sp0 = d.sp0_query = seed_xor_p0(l);
+        d.sp0 = d.sp0_query = level_spx(kc, l);
         off += round_up8(d.n_words);
         if (d.n_words && (!words[l] || !ranks[l])) return fail(BPHF_ERR_ARG, "null level buffer");
     }
@@ -1376,7 +1467,6 @@ BPHF_API int bphf_from_levels(uint32_t n_levels, const uint64_t* bits, const uin
     m->stats.n_levels = n_levels;
     *out = m.release();
     return BPHF_OK;
-    API_END
 }
 
 BPHF_API void bphf_free(bphf_mphf* m) {
@@ -1483,12 +1573,43 @@ BPHF_API int bphf_hash_batch_u64(const bphf_mphf* m, const uint64_t* keys, uint6
     API_END
 }
 
+BPHF_API int bphf_hash_batch_keys(const bphf_mphf* m, const void* keys, uint64_t n, uint64_t* out, int mem, void* stream) {
+    API_BEGIN
+    if (!m) return fail(BPHF_ERR_ARG, "null handle");
+    if (m->kc.kind == BPHF_KIND_U64) return bphf_hash_batch_u64(m, static_cast<const uint64_t*>(keys), n, out, mem, stream);
+    if (n == 0) return BPHF_OK;
+    if (!keys || !out) return fail(BPHF_ERR_ARG, "null buffer");
+    const DeviceInfo& info = device_info(m->device);
+    DeviceGuard guard(m->device);
+    cudaStream_t s = stream ? (cudaStream_t)stream : own_stream(m->device, false);
+    std::vector<void*> scratch;
+    try {
+        const uint64_t* d_words = keys_to_words(keys, n, m->kc, mem, s, info, scratch);
+        uint64_t* d_out = out;
+        if (mem == BPHF_MEM_HOST) {
+            CK(cudaMallocAsync((void**)&d_out, n * 8, s));
+            scratch.push_back(d_out);
+        }
+        launch_query(m, info, d_words, n, d_out, s);
+        if (mem == BPHF_MEM_HOST) CK(cudaMemcpyAsync(out, d_out, n * 8, cudaMemcpyDeviceToHost, s));
+        for (void* p : scratch) CK(cudaFreeAsync(p, s));
+        scratch.clear();
+        CK(cudaStreamSynchronize(s));
+    } catch (...) {
+        for (void* p : scratch) cudaFreeAsync(p, s);
+        throw;
+    }
+    return BPHF_OK;
+    API_END
+}
+
 BPHF_API int bphf_map_permute_u64(const bphf_mphf* m, const uint64_t* keys, const uint64_t* values, uint64_t n,
                                   uint64_t* keys_out, uint64_t* values_out, int mem, void* stream) {
     API_BEGIN
     if (!m) return fail(BPHF_ERR_ARG, "null handle");
     if (n == 0) return BPHF_OK;
     if (!keys || !keys_out || (values && !values_out)) return fail(BPHF_ERR_ARG, "null buffer");
+    if (m->kc.kind != BPHF_KIND_U64) return fail(BPHF_ERR_ARG, "the map helpers take u64 keys");
     const DeviceInfo& info = device_info(m->device);
     DeviceGuard guard(m->device);
     cudaStream_t s = stream ? (cudaStream_t)stream : own_stream(m->device, false);
@@ -1525,6 +1646,7 @@ BPHF_API int bphf_map_get_batch_u64(const bphf_mphf* m, const uint64_t* map_keys
     if (!m) return fail(BPHF_ERR_ARG, "null handle");
     if (nq == 0) return BPHF_OK;
     if (!queries || !values_out || !found_out || (n_map && !map_keys)) return fail(BPHF_ERR_ARG, "null buffer");
+    if (m->kc.kind != BPHF_KIND_U64) return fail(BPHF_ERR_ARG, "the map helpers take u64 keys");
     const DeviceInfo& info = device_info(m->device);
     DeviceGuard guard(m->device);
     cudaStream_t s = stream ? (cudaStream_t)stream : own_stream(m->device, false);

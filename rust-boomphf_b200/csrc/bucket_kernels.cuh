@@ -32,6 +32,7 @@ constexpr uint32_t BK_POS_BITS = 13;          // position of a key within (tile,
 // destination of a scatter: level l's bucket regions (or one contiguous list when level l is plain).
 // Bucket b owns keys[b * cap .. b * cap + cursor[b]).
 struct ScatterDst {
+    KeyCfg kc;
     uint64_t sp0;
     uint32_t bits, count, cap, shift;  // count == 1 for a plain level: one "bucket" = the contiguous key list
     uint64_t* keys;
@@ -41,6 +42,7 @@ struct ScatterDst {
 __device__ __forceinline__ ScatterDst make_dst(const BuildState* st, uint32_t level, uint64_t* keys, uint32_t* cursor) {
     const LevelDesc* d = &st->lv[level];
     ScatterDst o;
+    o.kc = st->kc;
     o.sp0 = d->sp0;
     o.bits = (uint32_t)d->bits;
     o.keys = keys;
@@ -105,7 +107,7 @@ __device__ __forceinline__ void scatter_tile(BuildState* st, const ScatterDst& d
         for (int j = 0; j < BK_KPT; j++) {
             bp[j] = 0;
             if (FULL || (valid & (1u << j))) {
-                const uint32_t b = hashmod_small(dst.sp0, key[j], dst.bits) >> dst.shift;
+                const uint32_t b = hashmod_small(dst.kc, dst.sp0, key[j], dst.bits) >> dst.shift;
                 bp[j] = (b << BK_POS_BITS) | atomicAdd(&sm.hist[b], 1u);
             }
         }
@@ -370,7 +372,7 @@ __global__ void __launch_bounds__(BK_THREADS, 2)
             bool redo[SRC_KPT];
 #pragma unroll
             for (int j = 0; j < SRC_KPT; j++) {
-                const uint32_t l = hashmod_small(p_sp0, key[j], p_bits) & p_mask;
+                const uint32_t l = hashmod_small(dst.kc, p_sp0, key[j], p_bits) & p_mask;
                 redo[j] = live[j] && ((c_sm[l >> 5] >> (l & 31)) & 1u);
             }
             __syncthreads();  // every thread has taken its decision on the previous step's pend_cnt
@@ -411,6 +413,7 @@ __global__ void __launch_bounds__(BK_THREADS)
     if (st->status != ST_RUNNING || st->n_levels != level || st->lv[level].b_range == 0) return;
     const LevelDesc* cu = &st->lv[level];
     const uint32_t range = cu->b_range, count = cu->b_count, cap = cu->b_cap, bits = (uint32_t)cu->bits;
+    const KeyCfg kc = st->kc;
     const uint64_t sp0 = cu->sp0;
     const uint64_t off32 = cu->word_off * 2;
     const uint32_t words32 = (uint32_t)(round_up8(cu->n_words) * 2);
@@ -446,7 +449,7 @@ __global__ void __launch_bounds__(BK_THREADS)
 #pragma unroll
                 for (int j = 0; j < MARK_KPT; j++) key[j] = ld_stream_u64(bsrc + t0 + j * BK_THREADS + threadIdx.x);
 #pragma unroll
-                for (int j = 0; j < MARK_KPT; j++) mark_smem(a_sm, c_sm, hashmod_small(sp0, key[j], bits) & mask);
+                for (int j = 0; j < MARK_KPT; j++) mark_smem(a_sm, c_sm, hashmod_small(kc, sp0, key[j], bits) & mask);
             } else {
 #pragma unroll
                 for (int j = 0; j < MARK_KPT; j++) {
@@ -456,7 +459,7 @@ __global__ void __launch_bounds__(BK_THREADS)
 #pragma unroll
                 for (int j = 0; j < MARK_KPT; j++) {
                     const uint32_t i = t0 + j * BK_THREADS + threadIdx.x;
-                    if (i < fill) mark_smem(a_sm, c_sm, hashmod_small(sp0, key[j], bits) & mask);
+                    if (i < fill) mark_smem(a_sm, c_sm, hashmod_small(kc, sp0, key[j], bits) & mask);
                 }
             }
         }

@@ -134,9 +134,9 @@ __device__ __forceinline__ void mark_bit(uint32_t* __restrict__ a32, uint32_t* _
 }
 
 template <bool BIG>
-__device__ __forceinline__ uint64_t level_index(uint64_t sp0, uint64_t key, uint64_t bits) {
-    if (BIG) return hashmod_big(sp0, key, bits);
-    return hashmod_small(sp0, key, (uint32_t)bits);
+__device__ __forceinline__ uint64_t level_index(const KeyCfg& kc, uint64_t sp0, uint64_t key, uint64_t bits) {
+    if (BIG) return hashmod_big(kc, sp0, key, bits);
+    return hashmod_small(kc, sp0, key, (uint32_t)bits);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -165,6 +165,7 @@ __global__ void __launch_bounds__(PASS_THREADS)
             if (blockIdx.x == 0 && threadIdx.x == 0) st->redo_count = key_end;
         }
     }
+    const KeyCfg kc = st->kc;
     const uint64_t bits = st->lv[level].bits;
     const uint64_t sp0 = st->lv[level].sp0;
     const uint64_t off32 = st->lv[level].word_off * 2;
@@ -186,7 +187,7 @@ __global__ void __launch_bounds__(PASS_THREADS)
         uint32_t m[PASS_KPT], old[PASS_KPT];
 #pragma unroll
         for (int j = 0; j < PASS_KPT; j++) {
-            const uint64_t idx = big ? level_index<true>(sp0, key[j], bits) : level_index<false>(sp0, key[j], bits);
+            const uint64_t idx = big ? level_index<true>(kc, sp0, key[j], bits) : level_index<false>(kc, sp0, key[j], bits);
             w[j] = off32 + (idx >> 5);
             m[j] = 1u << (idx & 31);
         }
@@ -223,6 +224,7 @@ __device__ __forceinline__ void pass_body(BuildState* __restrict__ st, uint32_t 
 
     // level descriptors are written by another CTA earlier in the same launch when this runs inside the
     // persistent cascade kernel: read them through L2
+    const KeyCfg kc = st->kc;
     const LevelDesc* pv = &st->lv[level - 1];
     const LevelDesc* cu = &st->lv[level];
     const uint64_t p_bits = __ldcg(&pv->bits), p_sp0 = __ldcg(&pv->sp0), p_off32 = __ldcg(&pv->word_off) * 2, k_src = __ldcg(&pv->k_loc);
@@ -247,7 +249,7 @@ __device__ __forceinline__ void pass_body(BuildState* __restrict__ st, uint32_t 
         // Context::filter (src/lib.rs:443-452): does this key's level-(l-1) slot collide?
 #pragma unroll
         for (int j = 0; j < PASS_KPT; j++) {
-            const uint64_t idx = p_big ? level_index<true>(p_sp0, key[j], p_bits) : level_index<false>(p_sp0, key[j], p_bits);
+            const uint64_t idx = p_big ? level_index<true>(kc, p_sp0, key[j], p_bits) : level_index<false>(kc, p_sp0, key[j], p_bits);
             cw[j] = __ldcg(c32 + p_off32 + (idx >> 5));
             sh[j] = (uint32_t)idx & 31;
         }
@@ -303,7 +305,7 @@ __device__ __forceinline__ void pass_body(BuildState* __restrict__ st, uint32_t 
                     const uint64_t kk = stage[i];
                     dst[out + i] = kk;
                     if (GATHER) continue;
-                    const uint64_t idx = c_big ? level_index<true>(c_sp0, kk, c_bits) : level_index<false>(c_sp0, kk, c_bits);
+                    const uint64_t idx = c_big ? level_index<true>(kc, c_sp0, kk, c_bits) : level_index<false>(kc, c_sp0, kk, c_bits);
                     w[j] = c_off32 + (idx >> 5);
                     m[j] = 1u << (idx & 31);
                 }
@@ -488,6 +490,7 @@ __global__ void __launch_bounds__(TAIL_THREADS)
     TailSmem& s = *reinterpret_cast<TailSmem*>(tail_smem_raw);
     if (st->status != ST_RUNNING || st->tail_level == NO_TAIL || st->n_levels != st->tail_level) return;
     const uint32_t tid = threadIdx.x;
+    const KeyCfg kc = st->kc;
     uint32_t level = st->tail_level;
     uint32_t k = (uint32_t)st->lv[level].k_in;
     if (tid == 0) s.count = 0;
@@ -520,7 +523,7 @@ __global__ void __launch_bounds__(TAIL_THREADS)
         const uint64_t* src = (level == 1) ? user_keys : (((level - 1) & 1) ? buf1 : buf0);
         for (uint64_t i = tid; i < k_src; i += TAIL_THREADS) {
             const uint64_t key = src[i];
-            const uint64_t idx = p_big ? hashmod_big(p_sp0, key, p_bits) : (uint64_t)hashmod_small(p_sp0, key, (uint32_t)p_bits);
+            const uint64_t idx = p_big ? hashmod_big(kc, p_sp0, key, p_bits) : (uint64_t)hashmod_small(kc, p_sp0, key, (uint32_t)p_bits);
             if ((c32[p_off32 + (idx >> 5)] >> (idx & 31)) & 1u) {
                 const uint32_t pos = atomicAdd(&s.count, 1u);
                 if (pos < TAIL_MAX_KEYS) s.keys[0][pos] = key;
@@ -544,7 +547,7 @@ __global__ void __launch_bounds__(TAIL_THREADS)
         const uint64_t* kin = s.keys[cur];
         uint64_t* kout = s.keys[cur ^ 1];
         for (uint32_t i = tid; i < k; i += TAIL_THREADS) {
-            const uint32_t idx = hashmod_small(sp0, kin[i], bits);
+            const uint32_t idx = hashmod_small(kc, sp0, kin[i], bits);
             const uint32_t m = 1u << (idx & 31);
             const uint32_t old = atomicOr(&s.a[idx >> 5], m);
             if (old & m) atomicOr(&s.c[idx >> 5], m);
@@ -565,7 +568,7 @@ __global__ void __launch_bounds__(TAIL_THREADS)
         }
         for (uint32_t i = tid; i < k; i += TAIL_THREADS) {
             const uint64_t key = kin[i];
-            const uint32_t idx = hashmod_small(sp0, key, bits);
+            const uint32_t idx = hashmod_small(kc, sp0, key, bits);
             if ((s.c[idx >> 5] >> (idx & 31)) & 1u) kout[atomicAdd(&s.count, 1u)] = key;
         }
         __syncthreads();

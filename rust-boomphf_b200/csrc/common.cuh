@@ -83,6 +83,7 @@ struct BuildState {
     uint32_t chunk_mode, chunk_has_max;
     uint32_t switch_level;     // first level built with gamma 1.7 (NO_LEVEL: not reached yet)
     uint32_t pad2_;
+    KeyCfg kc;                 // how the keys' Hash impl feeds the hasher (u64 unless built through bphf_build_keys)
     double shard_frac;         // this shard's share of the keys (n_local / n_global; 1 unsharded): sizes bucket regions
     LevelDesc lv[BPHF_MAX_LEVELS + 1];
 };
@@ -172,8 +173,8 @@ __host__ __device__ inline void make_level(BuildState* st, uint32_t level, uint6
     d.word_off = st->words_used;
     d.k_in = k;
     d.k_loc = (st->shard_world > 1 && level > 0) ? 0 : k;  // sharded: known once this shard's filter has run
-    d.sp0 = seed_xor_p0(st->seed0 + level);
-    d.sp0_query = seed_xor_p0(level);
+    d.sp0 = level_spx(st->kc, st->seed0 + level);
+    d.sp0_query = level_spx(st->kc, level);
     d.b_shift = 0;
     d.b_range = d.b_count = d.b_cap = 0;
     d.pad_ = 0;

@@ -23,13 +23,13 @@ constexpr int QUERY_THREADS = 256;
 //   + popcount of the bits of the final word strictly below idx (skipped when idx % 64 == 0)
 // With level offsets that are multiples of 512 bits, "idx/512 within the level" and "arena bit / 512"
 // select the same rank entry and the same words.
-__device__ __forceinline__ uint64_t lookup_one(const QLevel* __restrict__ lv, uint32_t n_levels,
+__device__ __forceinline__ uint64_t lookup_one(const KeyCfg& kc, const QLevel* __restrict__ lv, uint32_t n_levels,
                                                const uint64_t* __restrict__ words,
                                                const uint64_t* __restrict__ ranks, uint64_t key) {
     for (uint32_t l = 0; l < n_levels; l++) {
         const uint64_t bits = lv[l].bits;
-        const uint64_t idx = (bits >> 32) ? hashmod_big(lv[l].sp0, key, bits)
-                                          : (uint64_t)hashmod_small(lv[l].sp0, key, (uint32_t)bits);
+        const uint64_t idx = (bits >> 32) ? hashmod_big(kc, lv[l].sp0, key, bits)
+                                          : (uint64_t)hashmod_small(kc, lv[l].sp0, key, (uint32_t)bits);
         const uint64_t g = lv[l].bit_off + idx;
         const uint64_t wi = g >> 6;
         const uint64_t w = __ldg(words + wi);
@@ -97,10 +97,10 @@ __global__ void __launch_bounds__(256)
     }
 }
 
-__device__ __forceinline__ uint64_t lookup_packed(const QLevelP* __restrict__ lv, uint32_t n_levels,
+__device__ __forceinline__ uint64_t lookup_packed(const KeyCfg& kc, const QLevelP* __restrict__ lv, uint32_t n_levels,
                                                   const uint4* __restrict__ q, uint64_t key) {
     for (uint32_t l = 0; l < n_levels; l++) {
-        const uint32_t idx = hashmod_small(lv[l].sp0, key, lv[l].bits);
+        const uint32_t idx = hashmod_small(kc, lv[l].sp0, key, lv[l].bits);
         const uint32_t g = __umulhi(idx >> 5, 0x55555556u);  // (idx / 32) / 3, exact below 2^31
         const uint32_t bit = idx - g * GRAN_BITS;            // 0..95
         const uint4 v = __ldg(q + lv[l].gran_off + g);
@@ -121,8 +121,8 @@ __device__ __forceinline__ uint64_t lookup_packed(const QLevelP* __restrict__ lv
 struct PackedProbe {
     uint32_t g, bit;
 };
-__device__ __forceinline__ PackedProbe packed_slot(const QLevelP& lv, uint64_t key) {
-    const uint32_t idx = hashmod_small(lv.sp0, key, lv.bits);
+__device__ __forceinline__ PackedProbe packed_slot(const KeyCfg& kc, const QLevelP& lv, uint64_t key) {
+    const uint32_t idx = hashmod_small(kc, lv.sp0, key, lv.bits);
     PackedProbe p;
     p.g = __umulhi(idx >> 5, 0x55555556u);
     p.bit = idx - p.g * GRAN_BITS;
@@ -147,6 +147,7 @@ struct QView {
     const uint64_t* ranks;
     const uint4* packed;
     uint32_t n_levels;
+    KeyCfg kc;
 };
 
 // level table in shared memory + the lookup of either layout
@@ -159,7 +160,7 @@ struct LevelTab<false> {
         for (uint32_t i = threadIdx.x; i < v.n_levels; i += blockDim.x) lv[i] = v.lv[i];
     }
     __device__ __forceinline__ uint64_t lookup(const QView& v, uint64_t key) const {
-        return lookup_one(lv, v.n_levels, v.words, v.ranks, key);
+        return lookup_one(v.kc, lv, v.n_levels, v.words, v.ranks, key);
     }
 };
 template <>
@@ -169,7 +170,7 @@ struct LevelTab<true> {
         for (uint32_t i = threadIdx.x; i < v.n_levels; i += blockDim.x) lv[i] = v.lvp[i];
     }
     __device__ __forceinline__ uint64_t lookup(const QView& v, uint64_t key) const {
-        return lookup_packed(lv, v.n_levels, v.packed, key);
+        return lookup_packed(v.kc, lv, v.n_levels, v.packed, key);
     }
 };
 
@@ -221,6 +222,7 @@ __global__ void __launch_bounds__(QS_THREADS, 8)
     __syncthreads();
     uint64_t* __restrict__ res = res_all[warp];
     const uint4* __restrict__ q = v.packed;
+    const KeyCfg kc = v.kc;
     const uint32_t n_levels = v.n_levels;
     const uint64_t n_tiles = (n + QS_WTILE - 1) / QS_WTILE;
     const uint64_t w_stride = (uint64_t)gridDim.x * QS_WARPS;
@@ -241,7 +243,7 @@ __global__ void __launch_bounds__(QS_THREADS, 8)
             }
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                pp[j] = packed_slot(lv[0], key[j]);
+                pp[j] = packed_slot(kc, lv[0], key[j]);
                 g[j] = __ldg(q + lv[0].gran_off + pp[j].g);
             }
 #pragma unroll
@@ -275,7 +277,7 @@ __global__ void __launch_bounds__(QS_THREADS, 8)
                         live[j] = t < n_q;
                         i[j] = live[j] ? qin[t] : 0;
                         key[j] = res[i[j]];
-                        pp[j] = packed_slot(L, key[j]);
+                        pp[j] = packed_slot(kc, L, key[j]);
                         g[j] = __ldg(q + L.gran_off + pp[j].g);
                     }
                 }
@@ -297,7 +299,7 @@ __global__ void __launch_bounds__(QS_THREADS, 8)
             const uint64_t key = res[i];
             uint64_t rank = BPHF_NONE;
             for (uint32_t l = r; l < n_levels; l++) {
-                const PackedProbe pp = packed_slot(lv[l], key);
+                const PackedProbe pp = packed_slot(kc, lv[l], key);
                 const uint4 g = __ldg(q + lv[l].gran_off + pp.g);
                 uint64_t rk;
                 if (packed_hit(lv[l], g, pp.bit, &rk)) {
@@ -356,6 +358,20 @@ __global__ void __launch_bounds__(QUERY_THREADS)
         const bool found = pos < n_map && __ldg(map_keys + pos) == q;
         values_out[i] = found ? (map_values ? __ldg(map_values + pos) : pos) : 0;
         found_out[i] = found ? 1 : 0;
+    }
+}
+
+// packed keys of `width` bytes (u32 / u16 / u8 values, [u8; N]) -> tail words, hash.cuh: key_tail_word
+__global__ void key_words_kernel(const uint8_t* __restrict__ in, uint32_t width, uint64_t n, uint64_t* __restrict__ out) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint64_t k = 0;
+        if (width == 4) {
+            k = reinterpret_cast<const uint32_t*>(in)[i];
+        } else {
+            for (uint32_t b = 0; b < width; b++) k |= (uint64_t)in[i * width + b] << (8 * b);
+        }
+        out[i] = key_tail_word(k, width);
     }
 }
 

@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(TAIL_THREADS)
         const uint64_t* src = (level == 1) ? user_keys : (((level - 1) & 1) ? buf1 : buf0);
         for (uint64_t i = tid; i < k_src; i += TAIL_THREADS) {
             const uint64_t key = src[i];
-            const uint64_t idx = p_big ? hashmod_big(p_sp0, key, p_bits) : (uint64_t)hashmod_small(p_sp0, key, (uint32_t)p_bits);
+            const uint64_t idx = p_big ? hashmod_big(st->kc, p_sp0, key, p_bits) : (uint64_t)hashmod_small(st->kc, p_sp0, key, (uint32_t)p_bits);
             if ((c32[p_off32 + (idx >> 5)] >> (idx & 31)) & 1u) {
                 const uint32_t pos = atomicAdd(&count, 1u);
                 if (pos < TAIL_MAX_KEYS) xk[8 + pos] = key;

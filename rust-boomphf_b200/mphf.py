@@ -29,6 +29,40 @@ def _is_torch_cuda(x):
     return hasattr(x, "is_cuda") and hasattr(x, "data_ptr") and bool(x.is_cuda)
 
 
+KEY_U64, KEY_UINT, KEY_BYTES = 0, 1, 2
+
+
+def _kind_of(dtype_itemsize, ndim, shape, is_uint8):
+    """(kind, width) by element size / shape: 8-byte ints -> u64; 4/2/1-byte ints -> UINT; (n, N<=8) uint8 -> [u8; N]"""
+    if ndim == 2:
+        if not is_uint8 or not 1 <= shape[1] <= 8:
+            raise TypeError("byte-array keys must be uint8 of shape (n, N <= 8)")
+        return KEY_BYTES, int(shape[1])
+    if dtype_itemsize == 8:
+        return KEY_U64, 8
+    if dtype_itemsize in (1, 2, 4):
+        return KEY_UINT, int(dtype_itemsize)
+    raise TypeError("unsupported key type")
+
+
+def _as_any_keys(keys):
+    """keys of any supported kind -> (pointer, n, mem, device_or_None, keepalive, kind, width)"""
+    if _is_torch_cuda(keys):
+        k = keys.contiguous()
+        kind, width = _kind_of(k.element_size(), k.dim(), tuple(k.shape), str(k.dtype) == "torch.uint8")
+        n = k.shape[0] if k.dim() == 2 else k.numel()
+        return C.c_void_p(k.data_ptr()), n, N.MEM_DEVICE, k.device.index or 0, k, kind, width
+    if hasattr(keys, "is_cuda") and hasattr(keys, "numpy"):
+        keys = keys.contiguous().numpy()
+    a = keys if isinstance(keys, np.ndarray) else np.asarray(keys, dtype=np.uint64)
+    if a.dtype.kind not in "iu":
+        raise TypeError("keys must be integers")
+    a = np.ascontiguousarray(a)
+    kind, width = _kind_of(a.dtype.itemsize, a.ndim, a.shape, a.dtype == np.uint8)
+    n = a.shape[0] if a.ndim == 2 else a.size
+    return C.c_void_p(a.ctypes.data), n, N.MEM_HOST, None, a, kind, width
+
+
 def _as_keys(keys):
     """-> (pointer, n, mem, device_or_None, keepalive)"""
     if _is_torch_cuda(keys):
@@ -75,13 +109,18 @@ class Mphf:
     # ---- constructors ---------------------------------------------------------------------
     @classmethod
     def _build(cls, gamma, objects, starting_seed, device, stream):
-        ptr, n, mem, dev, keep = _as_keys(objects)
+        ptr, n, mem, dev, keep, kind, width = _as_any_keys(objects)
         if dev is not None:
             device = dev
         out = C.c_void_p()
-        rc = N.lib().bphf_build_u64(ptr, n, float(gamma), 0 if starting_seed is None else 1,
-                                    0 if starting_seed is None else int(starting_seed), int(device), mem,
-                                    _stream_ptr(stream), C.byref(out))
+        if kind == KEY_U64:
+            rc = N.lib().bphf_build_u64(ptr, n, float(gamma), 0 if starting_seed is None else 1,
+                                        0 if starting_seed is None else int(starting_seed), int(device), mem,
+                                        _stream_ptr(stream), C.byref(out))
+        else:  # Mphf<u32>, Mphf<[u8; N]>, ...: SURVEY 8f row 4
+            rc = N.lib().bphf_build_keys(ptr, n, kind, width, float(gamma), 0 if starting_seed is None else 1,
+                                         0 if starting_seed is None else int(starting_seed), int(device), mem,
+                                         C.byref(out))
         del keep
         _check(rc)
         return cls(out.value, int(device))
@@ -128,8 +167,9 @@ class Mphf:
         return cls._build_chunked(gamma, list(objects), n, True, max_iters, device)
 
     @classmethod
-    def from_levels(cls, levels, device=0):
-        """Upload a deserialised Mphf: levels = [(bits, words u64[], ranks u64[]), ...]."""
+    def from_levels(cls, levels, device=0, key_kind=KEY_U64, key_width=8):
+        """Upload a deserialised Mphf<T>: levels = [(bits, words u64[], ranks u64[]), ...]; key_kind / key_width say
+        what T is (default u64)."""
         n = len(levels)
         bits = np.array([l[0] for l in levels], dtype=np.uint64)
         words = [np.ascontiguousarray(l[1], dtype=np.uint64) for l in levels]
@@ -140,8 +180,15 @@ class Mphf:
         wp = (C.c_void_p * max(n, 1))(*[w.ctypes.data for w in words])
         rp = (C.c_void_p * max(n, 1))(*[r.ctypes.data for r in ranks])
         out = C.c_void_p()
-        _check(N.lib().bphf_from_levels(n, C.c_void_p(bits.ctypes.data), wp, rp, int(device), C.byref(out)))
+        _check(N.lib().bphf_from_levels_keys(n, C.c_void_p(bits.ctypes.data), wp, rp, int(key_kind), int(key_width),
+                                             int(device), C.byref(out)))
         return cls(out.value, int(device))
+
+    @property
+    def key_kind(self):
+        k, w = C.c_int(), C.c_int()
+        _check(N.lib().bphf_key_kind(self._h, C.byref(k), C.byref(w)))
+        return int(k.value), int(w.value)
 
     # ---- data model -------------------------------------------------------------------------
     @property
@@ -204,25 +251,35 @@ class Mphf:
     def hash_batch(self, keys, out=None, stream=None):
         """try_hash over a batch; entries equal to NONE (u64::MAX) are `None`.
         numpy in -> numpy out; CUDA tensor in -> CUDA tensor out (int64 view of the u64 values)."""
-        ptr, n, mem, dev, keep = _as_keys(keys)
+        ptr, n, mem, dev, keep, kind, width = _as_any_keys(keys)
+        if (kind, width) != self.key_kind:
+            raise TypeError("keys are not of the type this Mphf was built for")
+        fn = N.lib().bphf_hash_batch_u64 if kind == KEY_U64 else N.lib().bphf_hash_batch_keys
         if mem == N.MEM_DEVICE:
             import torch
             if dev != self.device:
                 raise ValueError("keys live on another device than the Mphf")
             if out is None:
-                out = torch.empty(n, dtype=keep.dtype, device=keep.device)
+                out = torch.empty(n, dtype=torch.int64, device=keep.device)
             if stream is None:
                 stream = torch.cuda.current_stream(keep.device)
-            _check(N.lib().bphf_hash_batch_u64(self._h, ptr, n, C.c_void_p(out.data_ptr()), mem, _stream_ptr(stream)))
+            _check(fn(self._h, ptr, n, C.c_void_p(out.data_ptr()), mem, _stream_ptr(stream)))
             return out
         if out is None:
             out = np.empty(n, dtype=np.uint64)
-        _check(N.lib().bphf_hash_batch_u64(self._h, ptr, n, C.c_void_p(out.ctypes.data), mem, _stream_ptr(stream)))
+        _check(fn(self._h, ptr, n, C.c_void_p(out.ctypes.data), mem, _stream_ptr(stream)))
         return out
 
     def try_hash(self, item):
         """Mphf::try_hash (src/lib.rs:340): Some(rank) or None"""
-        v = int(self.hash_batch(np.array([item], dtype=np.uint64))[0])
+        kind, width = self.key_kind
+        if kind == KEY_BYTES:
+            q = np.frombuffer(bytes(item), dtype=np.uint8).reshape(1, width)
+        elif kind == KEY_UINT:
+            q = np.array([int(item) & ((1 << (8 * width)) - 1)], dtype=np.dtype("u%d" % width))
+        else:
+            q = np.array([int(item) & (2 ** 64 - 1)], dtype=np.uint64)
+        v = int(self.hash_batch(q)[0])
         return None if v == N.NONE else v
 
     def hash(self, item):

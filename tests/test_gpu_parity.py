@@ -407,3 +407,61 @@ def test_from_chunked_iterator_device_chunks(pkg, oracle):
     assert_same_levels(m.levels(), oracle.OracleMphf.from_chunked_iterator_parallel(2.0, [keys], None, len(keys)).levels())
     one = pkg.Mphf.from_chunked_iterator(1.7, [torch.from_numpy(keys.view(np.int64)).cuda()], len(keys))
     assert_same_levels(one.levels(), oracle.OracleMphf.new(1.7, keys).levels())
+
+
+# ---- key types other than u64 (the reference's check_u32 / check_isize / check_vec_u8) ------
+def _distinct(rng, dtype, n):
+    info = np.iinfo(dtype)
+    span = int(info.max) - int(info.min) + 1
+    n = min(n, span)
+    if span <= 1 << 20:
+        vals = rng.permutation(span)[:n] + int(info.min)
+    else:
+        vals = np.unique(rng.integers(info.min, info.max, size=2 * n, dtype=np.int64))[:n]
+    return vals.astype(dtype)
+
+
+@pytest.mark.parametrize("dtype", [np.uint32, np.int32, np.uint16, np.int16, np.uint8, np.int8, np.int64])
+@pytest.mark.parametrize("n", [200, 5000, 300_000])
+def test_integer_key_types_parity(pkg, oracle, dtype, n):
+    keys = _distinct(np.random.default_rng(n), dtype, n)
+    m = pkg.Mphf.new(1.7, keys)
+    ref = oracle.OracleMphf.new(1.7, keys)
+    assert_same_levels(m.levels(), ref.levels())
+    assert_same_levels(pkg.Mphf.new_parallel(1.7, keys, None).levels(), ref.levels())
+    h = m.hash_batch(keys)
+    assert np.array_equal(h, ref.hash_batch(keys))
+    assert np.array_equal(np.sort(h), np.arange(len(keys), dtype=np.uint64))
+    assert m.try_hash(int(keys[0])) == int(h[0])
+
+
+@pytest.mark.parametrize("width", [1, 2, 3, 4, 5, 6, 7, 8])
+def test_byte_array_keys_parity(pkg, oracle, width):
+    rng = np.random.default_rng(width)
+    keys = np.unique(rng.integers(0, 256, size=(60_000, width), dtype=np.uint8), axis=0)
+    keys = keys[rng.permutation(len(keys))]
+    m = pkg.Mphf.new_parallel(1.7, keys, None)
+    ref = oracle.OracleMphf.new_parallel(1.7, keys)
+    assert_same_levels(m.levels(), ref.levels())
+    h = m.hash_batch(keys)
+    assert np.array_equal(h, ref.hash_batch(keys))
+    assert np.array_equal(np.sort(h), np.arange(len(keys), dtype=np.uint64))
+    assert m.key_kind == (2, width)
+    assert m.try_hash(bytes(keys[5])) == int(h[5])
+    # upload of the exported levels keeps the key type; a u64 view of the same levels hashes differently
+    m2 = pkg.Mphf.from_levels(m.levels(), key_kind=2, key_width=width)
+    assert np.array_equal(m2.hash_batch(keys), h)
+    with pytest.raises(TypeError):
+        m.hash_batch(np.arange(10, dtype=np.uint64))
+
+
+def test_u32_device_keys_and_absent_keys(pkg, oracle):
+    import torch
+    keys = _distinct(np.random.default_rng(7), np.uint32, 1_000_000)
+    dk = torch.from_numpy(keys.view(np.int32)).cuda()
+    m = pkg.Mphf.new_parallel(2.0, dk, None)
+    ref = oracle.OracleMphf.new_parallel(2.0, keys)
+    assert_same_levels(m.levels(), ref.levels())
+    absent = _distinct(np.random.default_rng(8), np.uint32, 100_000)
+    got = m.hash_batch(torch.from_numpy(absent.view(np.int32)).cuda()).cpu().numpy().view(np.uint64)
+    assert np.array_equal(got, ref.hash_batch(absent))

@@ -268,3 +268,40 @@ def test_chunked_parallel_quirks(oracle):
     # n must match
     with pytest.raises(oracle.OracleError):
         oracle.OracleMphf.from_chunked_iterator_parallel(1.7, [keys], None, len(keys) - 1)
+
+
+# ---- key types other than u64 -------------------------------------------------------------
+def test_key_kind_hash_matches_the_byte_stream_definition(oracle):
+    # bo_set_key_kind must hash exactly the byte stream Rust's Hash impls write: ints = their native-endian bytes,
+    # [u8; N] = usize length prefix + bytes; rebuilt here from the bare core / finish functions
+    L = oracle.lib()
+    try:
+        for kind, width, key in [(0, 8, 0x0123456789abcdef), (1, 4, 0xdeadbeef), (1, 2, 0xbeef), (1, 1, 0x7f),
+                                 (2, 1, 0x09), (2, 3, 0x030201), (2, 5, 0x0504030201), (2, 8, 0x0807060504030201)]:
+            L.bo_set_key_kind(kind, width)
+            for it in (0, 1, 5, 31, 32, 33):
+                want = oracle.hash_key_bytes(it, key.to_bytes(8, "little")[:width], kind == 2)
+                assert L.bo_hash_with_seed(it, key) == want, (kind, width, it)
+    finally:
+        L.bo_set_key_kind(0, 8)
+    # a 3-byte write goes through read_rest's (rd16 << 8) | byte case: the README vector wyhash(&[0,1,2], 3) pins it
+    assert oracle.wyhash_bytes(bytes([0, 1, 2]), 3) == 0xb0f941520b1ad95d
+
+
+@pytest.mark.parametrize("dtype", [np.uint32, np.int32, np.uint16, np.uint8])
+def test_mphf_property_other_integer_keys(oracle, dtype):
+    # the reference's check_u32 / check_isize style property (src/lib.rs:857-879): hashes are a permutation of 0..n
+    info = np.iinfo(dtype)
+    n = min(20_000, int(info.max) - int(info.min) + 1)
+    keys = (np.random.default_rng(3).permutation(max(n, 70_000))[:n] % (int(info.max) - int(info.min) + 1) + int(info.min))
+    keys = np.unique(keys).astype(dtype)
+    for build in (oracle.OracleMphf.new, oracle.OracleMphf.new_parallel):
+        m = build(1.7, keys)
+        assert np.array_equal(np.sort(m.hash_batch(keys)), np.arange(len(keys), dtype=np.uint64))
+
+
+def test_mphf_property_byte_array_keys(oracle):
+    keys = np.unique(np.random.default_rng(4).integers(0, 256, size=(30_000, 6), dtype=np.uint8), axis=0)
+    a, b = oracle.OracleMphf.new(1.7, keys), oracle.OracleMphf.new_parallel(1.7, keys)
+    assert oracle.fingerprint(a.levels()) == oracle.fingerprint(b.levels())
+    assert np.array_equal(np.sort(a.hash_batch(keys)), np.arange(len(keys), dtype=np.uint64))
