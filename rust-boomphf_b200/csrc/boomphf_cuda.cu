@@ -1533,42 +1533,47 @@ BPHF_API int bphf_hash_batch_u64(const bphf_mphf* m, const uint64_t* keys, uint6
     }
     // host buffers: H2D -> kernel -> D2H pipelined in chunks over two streams
     const uint64_t chunk = 8ull << 20;  // 8 Mi keys = 64 MiB each way
-    const int NBUF = 3;
+    constexpr int NBUF = 3;
     const uint64_t cap = std::min(n, chunk);
-    uint64_t* d_in[NBUF];
-    uint64_t* d_out[NBUF];
     cudaStream_t cs = own_stream(m->device, true);
-    cudaEvent_t in_ready[NBUF], out_done[NBUF], kernel_done[NBUF];
+    // staging buffers and events; released on every exit path (an exception must not leak device memory)
+    struct Pipe {
+        cudaStream_t s;
+        uint64_t* d_in[NBUF] = {};
+        uint64_t* d_out[NBUF] = {};
+        cudaEvent_t in_ready[NBUF] = {}, out_done[NBUF] = {};
+        explicit Pipe(cudaStream_t st) : s(st) {}
+        ~Pipe() {
+            for (int i = 0; i < NBUF; i++) {
+                if (d_in[i]) cudaFreeAsync(d_in[i], s);
+                if (d_out[i]) cudaFreeAsync(d_out[i], s);
+                if (in_ready[i]) cudaEventDestroy(in_ready[i]);
+                if (out_done[i]) cudaEventDestroy(out_done[i]);
+            }
+        }
+    } p(s);
     for (int i = 0; i < NBUF; i++) {
-        CK(cudaMallocAsync((void**)&d_in[i], cap * 8, s));
-        CK(cudaMallocAsync((void**)&d_out[i], cap * 8, s));
-        CK(cudaEventCreateWithFlags(&in_ready[i], cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&out_done[i], cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&kernel_done[i], cudaEventDisableTiming));
+        CK(cudaMallocAsync((void**)&p.d_in[i], cap * 8, s));
+        CK(cudaMallocAsync((void**)&p.d_out[i], cap * 8, s));
+        CK(cudaEventCreateWithFlags(&p.in_ready[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&p.out_done[i], cudaEventDisableTiming));
     }
-    CK(cudaEventRecord(out_done[0], s));
-    CK(cudaStreamWaitEvent(cs, out_done[0], 0));  // buffers exist before the copy stream touches them
+    CK(cudaEventRecord(p.out_done[0], s));
+    CK(cudaStreamWaitEvent(cs, p.out_done[0], 0));  // buffers exist before the copy stream touches them
     uint64_t c = 0;
     for (uint64_t lo = 0; lo < n; lo += chunk, c++) {
         const int bi = (int)(c % NBUF);
         const uint64_t cnt = std::min(chunk, n - lo);
-        if (c >= (uint64_t)NBUF) CK(cudaStreamWaitEvent(cs, out_done[bi], 0));  // buffer free again
-        CK(cudaMemcpyAsync(d_in[bi], keys + lo, cnt * 8, cudaMemcpyHostToDevice, cs));
-        CK(cudaEventRecord(in_ready[bi], cs));
-        CK(cudaStreamWaitEvent(s, in_ready[bi], 0));
-        launch_query(m, info, d_in[bi], cnt, d_out[bi], s);
-        CK(cudaMemcpyAsync(out + lo, d_out[bi], cnt * 8, cudaMemcpyDeviceToHost, s));
-        CK(cudaEventRecord(out_done[bi], s));
+        if (c >= (uint64_t)NBUF) CK(cudaStreamWaitEvent(cs, p.out_done[bi], 0));  // buffer free again
+        CK(cudaMemcpyAsync(p.d_in[bi], keys + lo, cnt * 8, cudaMemcpyHostToDevice, cs));
+        CK(cudaEventRecord(p.in_ready[bi], cs));
+        CK(cudaStreamWaitEvent(s, p.in_ready[bi], 0));
+        launch_query(m, info, p.d_in[bi], cnt, p.d_out[bi], s);
+        CK(cudaMemcpyAsync(out + lo, p.d_out[bi], cnt * 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaEventRecord(p.out_done[bi], s));
     }
-    CK(cudaStreamSynchronize(s));
     CK(cudaStreamSynchronize(cs));
-    for (int i = 0; i < NBUF; i++) {
-        CK(cudaFreeAsync(d_in[i], s));
-        CK(cudaFreeAsync(d_out[i], s));
-        cudaEventDestroy(in_ready[i]);
-        cudaEventDestroy(out_done[i]);
-        cudaEventDestroy(kernel_done[i]);
-    }
+    CK(cudaStreamSynchronize(s));
     return BPHF_OK;
     API_END
 }
