@@ -203,6 +203,11 @@ BPHF_API int bphf_set_profile(int level);
  *   mode 2           = large levels are built in shared memory after grouping the keys by bit range ("bucketed"),
  *                      levels with fewer than bucket_min_keys keys (0 = default 2^20) by the mode-1 kernels. */
 BPHF_API int bphf_set_build_mode(int mode, uint64_t bucket_min_keys);
+/* hybrid level 0 of build mode 0 (measurement / tests; identical results): `frac` of the level's bit range is built
+ * in shared memory, the rest with L2 atomics, in the same pass; levels below min_bits bits stay all-atomic.
+ * Off by default (frac = 0: it measured no faster than the all-atomic level 0); out-of-range
+ * values restore the defaults (off, 2^26). */
+BPHF_API int bphf_set_hybrid(double frac, uint64_t min_bits);
 /* lookup strategy (measurement only; identical results): 0 (default) = level-synchronous kernel over the packed
  * lookup structure, 1 = one thread per key over the same structure */
 BPHF_API int bphf_set_query_mode(int mode);

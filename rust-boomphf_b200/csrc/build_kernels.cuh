@@ -342,6 +342,8 @@ __device__ __forceinline__ void finalize_body(BuildState* __restrict__ st, uint3
     __shared__ bool is_last;
     const uint64_t word_off = __ldcg(&st->lv[level].word_off);
     const uint64_t n_pairs = round_up8(__ldcg(&st->lv[level].n_words)) / 2;  // multiple of 4
+    // hybrid level: the words below h_split were finalized (and popcounted) by bucket_mark_kernel
+    const uint64_t first_pair = __ldcg(&st->lv[level].h_split) / 128;
     const int lane = threadIdx.x & 31;
     ulonglong2* __restrict__ a2 = reinterpret_cast<ulonglong2*>(words + word_off);
     const ulonglong2* __restrict__ c2 = reinterpret_cast<const ulonglong2*>(coll + word_off);
@@ -349,7 +351,7 @@ __device__ __forceinline__ void finalize_body(BuildState* __restrict__ st, uint3
 
     uint64_t uniq = 0;
     const uint64_t stride = (uint64_t)gridDim.x * FIN_THREADS;
-    for (uint64_t p0 = (uint64_t)blockIdx.x * FIN_THREADS + (threadIdx.x & ~31u); p0 < n_pairs; p0 += stride) {
+    for (uint64_t p0 = first_pair + (uint64_t)blockIdx.x * FIN_THREADS + (threadIdx.x & ~31u); p0 < n_pairs; p0 += stride) {
         const uint64_t p = p0 + lane;
         uint32_t pc = 0;
         if (p < n_pairs) {

@@ -465,3 +465,45 @@ def test_u32_device_keys_and_absent_keys(pkg, oracle):
     absent = _distinct(np.random.default_rng(8), np.uint32, 100_000)
     got = m.hash_batch(torch.from_numpy(absent.view(np.int32)).cuda()).cpu().numpy().view(np.uint64)
     assert np.array_equal(got, ref.hash_batch(absent))
+
+
+# ---- hybrid level 0: part of the bit range in shared memory, the rest with L2 atomics ------------------------------
+@pytest.fixture
+def small_hybrid(pkg):
+    pkg.lib().bphf_set_hybrid(0.45, 1 << 14)
+    yield
+    pkg.lib().bphf_set_hybrid(-1.0, 0)
+
+
+@pytest.mark.parametrize("n", [10_000, 65_537, 300_001, 3_000_000, 20_000_000])
+@pytest.mark.parametrize("frac", [0.1, 0.45, 0.9])
+def test_hybrid_level0_parity(pkg, oracle, small_hybrid, n, frac):
+    pkg.lib().bphf_set_hybrid(frac, 1 << 14)
+    keys = oracle.keygen(n, seed=n + 23, kind=0)
+    m = pkg.Mphf.new_parallel(1.7, keys, None)
+    assert_same_levels(m.levels(), oracle.OracleMphf.new_parallel(1.7, keys).levels())
+
+
+@pytest.mark.parametrize("gamma", [1.02, 2.0, 5.0, 17.5])
+def test_hybrid_level0_gammas_and_host_chunks(pkg, oracle, small_hybrid, gamma):
+    keys = oracle.keygen(1_500_000, seed=31, kind=1)
+    assert_same_levels(pkg.Mphf.new_parallel(gamma, keys, 7).levels(), oracle.OracleMphf.new_parallel(gamma, keys, 7).levels())
+
+
+def test_hybrid_level0_duplicates_fall_back(pkg, small_hybrid):
+    base = np.arange(50_000, dtype=np.uint64) * 3 + 5
+    with pytest.raises(pkg.MphfPanic) as e:
+        pkg.Mphf.new_parallel(1.7, np.tile(base, 40), None)   # bucket regions overflow -> plain rebuild -> MAX_ITERS
+    assert e.value.code == -3
+
+
+def test_hybrid_switch_gives_identical_structures(pkg, oracle):
+    keys = oracle.keygen(50_000_000, seed=6, kind=0)
+    try:
+        pkg.lib().bphf_set_hybrid(0.0, 0)           # the default: all-atomic level 0
+        a = pkg.Mphf.new_parallel(1.7, keys, None)
+        pkg.lib().bphf_set_hybrid(0.45, 0)          # hybrid for levels >= 2^26 bits
+        b = pkg.Mphf.new_parallel(1.7, keys, None)
+    finally:
+        pkg.lib().bphf_set_hybrid(-1.0, 0)
+    assert oracle.fingerprint(a.levels()) == oracle.fingerprint(b.levels())
