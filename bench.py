@@ -47,13 +47,18 @@ class ClockSampler:
     """SM clock and throttle reasons sampled DURING the timed region, in-process through NVML (an nvidia-smi
     subprocess per sample stalls the driver for tens of ms and would perturb a 3 ms step)."""
 
-    def __init__(self, torch_index):
+    def __init__(self, torch_index, enabled=True, period=0.5):
+        # NVML queries take a driver-wide lock: at 10 Hz from every rank they stalled kernel launches of ALL ranks for
+        # milliseconds at a time (a 4-GPU sharded step was seen at 33 ms instead of 5 ms).  One sampling rank, 2 Hz.
+        self.period = period
         self.samples = []
         self._stop = threading.Event()
         self._t = None
         self._h = None
         self._nv = None
         try:
+            if not enabled:
+                raise RuntimeError("clock sampling is done by rank 0 only")
             import pynvml as nv
             nv.nvmlInit()
             self._nv = nv
@@ -94,7 +99,7 @@ class ClockSampler:
     def _run(self):
         while not self._stop.is_set():
             self._sample()
-            self._stop.wait(0.1)
+            self._stop.wait(self.period)
 
     def __enter__(self):
         if self._nv is not None:
@@ -260,7 +265,7 @@ def main():
     cascade_ms = 0.0
     launches = 0
     barrier()
-    with ClockSampler(local_rank) as clocks:
+    with ClockSampler(local_rank, enabled=(rank == 0)) as clocks:
         e0.record(stream)
         t0 = time.perf_counter()
         for _ in range(args.steps):

@@ -424,7 +424,19 @@ struct Builder {
         if (ev_end) cudaEventDestroy(ev_end);
     }
 
-    int max_grid() const { return info.sm_count * 8; }
+    // persistent grids: exactly the CTAs that are resident at once (a grid of 8 per SM with 6 resident runs a second,
+    // two-thirds empty wave: 41 tiles per CTA either way)
+    int resident_grid(const void* fn, int threads) const {
+        static std::mutex mu;
+        static std::vector<std::pair<const void*, int>> cache;
+        std::lock_guard<std::mutex> lock(mu);
+        for (auto& e : cache)
+            if (e.first == fn) return info.sm_count * e.second;
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
+        cache.emplace_back(fn, per_sm);
+        return info.sm_count * per_sm;
+    }
     uint32_t slots() const { return (uint32_t)info.sm_count * 2; }
 
     size_t begin_event(int kind, uint32_t level) {
@@ -510,7 +522,8 @@ struct Builder {
         const uint64_t cnt = level == 0 ? end - begin : k_up;
         if (cnt == 0) return;
         const uint64_t tiles = (cnt + PASS_TILE - 1) / PASS_TILE;
-        const int grid = (int)std::min<uint64_t>(tiles, (uint64_t)max_grid());
+        const void* fn = maybe_big ? (const void*)mark_list_kernel<true> : (const void*)mark_list_kernel<false>;
+        const int grid = (int)std::min<uint64_t>(tiles, (uint64_t)resident_grid(fn, PASS_THREADS));
         if (maybe_big)
             mark_list_kernel<true><<<grid, PASS_THREADS, 0, s>>>(d_state, level, d_keys, begin, end, d_buf[0], d_buf[1], a32(), c32(), list_cursor(level));
         else
@@ -520,7 +533,8 @@ struct Builder {
     }
     void launch_pass(uint32_t level, uint64_t k_src_up) {
         const uint64_t tiles = std::max<uint64_t>(1, (k_src_up + PASS_TILE - 1) / PASS_TILE);
-        const int grid = (int)std::min<uint64_t>(tiles, (uint64_t)max_grid());
+        const void* fn = maybe_big ? (const void*)pass_kernel<true> : (const void*)pass_kernel<false>;
+        const int grid = (int)std::min<uint64_t>(tiles, (uint64_t)resident_grid(fn, PASS_THREADS));
         if (maybe_big)
             pass_kernel<true><<<grid, PASS_THREADS, 0, s>>>(d_state, level, d_keys, d_buf[0], d_buf[1], a32(), c32());
         else
@@ -532,7 +546,7 @@ struct Builder {
         const uint64_t bits = level_size(hst.gamma, k_up);
         const uint64_t pairs = round_up8((bits + 63) / 64) / 2;
         const int grid = (int)std::min<uint64_t>(std::max<uint64_t>(1, (pairs + FIN_THREADS - 1) / FIN_THREADS),
-                                                 (uint64_t)max_grid());
+                                                 (uint64_t)resident_grid((const void*)finalize_kernel, FIN_THREADS));
         finalize_kernel<<<grid, FIN_THREADS, 0, s>>>(d_state, level, d_words, d_coll, d_blockpop);
         CK(cudaGetLastError());
         launches++;
@@ -548,7 +562,8 @@ struct Builder {
     void launch_gather(uint32_t level, uint64_t k_src_up, uint64_t k_up) {
         const size_t e0 = begin_event(0, level);
         const uint64_t tiles = std::max<uint64_t>(1, (k_src_up + PASS_TILE - 1) / PASS_TILE);
-        const int grid = (int)std::min<uint64_t>(tiles, (uint64_t)max_grid());
+        const void* gfn = maybe_big ? (const void*)shard_gather_kernel<true> : (const void*)shard_gather_kernel<false>;
+        const int grid = (int)std::min<uint64_t>(tiles, (uint64_t)resident_grid(gfn, PASS_THREADS));
         uint64_t* xk = comm->dev.xkeys[comm->rank];
         if (maybe_big) shard_gather_kernel<true><<<grid, PASS_THREADS, 0, s>>>(d_state, level, d_keys, d_buf[0], d_buf[1], c32(), xk);
         else shard_gather_kernel<false><<<grid, PASS_THREADS, 0, s>>>(d_state, level, d_keys, d_buf[0], d_buf[1], c32(), xk);
