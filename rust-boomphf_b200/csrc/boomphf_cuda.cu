@@ -109,7 +109,7 @@ static const DeviceInfo& device_info(int dev) {
                 (const void*)scatter0_kernel, (const void*)scatter_kernel, (const void*)bucket_mark_kernel,
                 (const void*)hybrid0_kernel,
                 (const void*)query_kernel<false>, (const void*)query_kernel<true>, (const void*)map_permute_kernel<false>,
-                (const void*)map_permute_kernel<true>, (const void*)map_get_kernel<false>, (const void*)map_get_kernel<true>,
+                (const void*)map_get_kernel<false>, (const void*)map_scatter_kernel, (const void*)map_gather_kernel,
                 (const void*)pack_query_kernel, (const void*)set_base_rank_kernel, (const void*)query_sync_kernel,
                 (const void*)key_words_kernel, (const void*)keygen_kernel, (const void*)check_perm_kernel, (const void*)checksum_kernel,
                 (const void*)shard_barrier_kernel, (const void*)or_collide_merge_kernel, (const void*)tail_gather_kernel,
@@ -1704,8 +1704,19 @@ BPHF_API int bphf_map_permute_u64(const bphf_mphf* m, const uint64_t* keys, cons
     }
     unsigned long long* d_bad = st.scratch<unsigned long long>(1);
     CK(cudaMemsetAsync(d_bad, 0, 8, s));
-    if (m->d_lvp) map_permute_kernel<true><<<query_grid(info, n), QUERY_THREADS, 0, s>>>(query_view(m), dk, dv, n, dko, dvo, d_bad);
-    else map_permute_kernel<false><<<query_grid(info, n), QUERY_THREADS, 0, s>>>(query_view(m), dk, dv, n, dko, dvo, d_bad);
+    if (m->d_lvp) {
+        // ranks with the batched lookup kernel (warp-synchronous walk), then a plain scatter; 64 Mi keys at a time
+        const uint64_t chunk = std::min<uint64_t>(n, 64ull << 20);
+        uint64_t* d_pos = st.scratch<uint64_t>(chunk);
+        for (uint64_t lo = 0; lo < n; lo += chunk) {
+            const uint64_t cnt = std::min(chunk, n - lo);
+            launch_query(m, info, dk + lo, cnt, d_pos, s);
+            const int grid = (int)std::min<uint64_t>((cnt + 255) / 256, (uint64_t)info.sm_count * 16);
+            map_scatter_kernel<<<grid, 256, 0, s>>>(d_pos, dk + lo, dv ? dv + lo : nullptr, cnt, n, dko, dvo, d_bad);
+        }
+    } else {
+        map_permute_kernel<false><<<query_grid(info, n), QUERY_THREADS, 0, s>>>(query_view(m), dk, dv, n, dko, dvo, d_bad);
+    }
     CK(cudaGetLastError());
     unsigned long long bad = 0;
     CK(cudaMemcpyAsync(&bad, d_bad, 8, cudaMemcpyDeviceToHost, s));
@@ -1741,8 +1752,18 @@ BPHF_API int bphf_map_get_batch_u64(const bphf_mphf* m, const uint64_t* map_keys
         dvo = st.scratch<uint64_t>(nq);
         dfo = st.scratch<uint8_t>(nq);
     }
-    if (m->d_lvp) map_get_kernel<true><<<query_grid(info, nq), QUERY_THREADS, 0, s>>>(query_view(m), dmk, dmv, n_map, dq, nq, dvo, dfo);
-    else map_get_kernel<false><<<query_grid(info, nq), QUERY_THREADS, 0, s>>>(query_view(m), dmk, dmv, n_map, dq, nq, dvo, dfo);
+    if (m->d_lvp) {
+        const uint64_t chunk = std::min<uint64_t>(nq, 64ull << 20);
+        uint64_t* d_pos = st.scratch<uint64_t>(chunk);
+        for (uint64_t lo = 0; lo < nq; lo += chunk) {
+            const uint64_t cnt = std::min(chunk, nq - lo);
+            launch_query(m, info, dq + lo, cnt, d_pos, s);
+            const int grid = (int)std::min<uint64_t>((cnt + 255) / 256, (uint64_t)info.sm_count * 16);
+            map_gather_kernel<<<grid, 256, 0, s>>>(d_pos, dmk, dmv, n_map, dq + lo, cnt, dvo + lo, dfo + lo);
+        }
+    } else {
+        map_get_kernel<false><<<query_grid(info, nq), QUERY_THREADS, 0, s>>>(query_view(m), dmk, dmv, n_map, dq, nq, dvo, dfo);
+    }
     CK(cudaGetLastError());
     if (mem == BPHF_MEM_HOST) {
         CK(cudaMemcpyAsync(values_out, dvo, nq * 8, cudaMemcpyDeviceToHost, s));

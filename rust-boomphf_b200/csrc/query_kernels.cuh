@@ -361,6 +361,35 @@ __global__ void __launch_bounds__(QUERY_THREADS)
     }
 }
 
+// second half of create_map / get once the ranks are known (first half: the batched lookup kernel)
+__global__ void __launch_bounds__(256)
+    map_scatter_kernel(const uint64_t* __restrict__ pos, const uint64_t* __restrict__ keys, const uint64_t* __restrict__ values,
+                       uint64_t n, uint64_t n_total, uint64_t* __restrict__ keys_out, uint64_t* __restrict__ values_out,
+                       unsigned long long* __restrict__ bad) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint64_t p = pos[i];
+        if (p >= n_total) {
+            atomicAdd(bad, 1ULL);
+            continue;
+        }
+        keys_out[p] = keys[i];
+        if (values) values_out[p] = values[i];
+    }
+}
+__global__ void __launch_bounds__(256)
+    map_gather_kernel(const uint64_t* __restrict__ pos, const uint64_t* __restrict__ map_keys,
+                      const uint64_t* __restrict__ map_values, uint64_t n_map, const uint64_t* __restrict__ queries,
+                      uint64_t nq, uint64_t* __restrict__ values_out, uint8_t* __restrict__ found_out) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += stride) {
+        const uint64_t p = pos[i];
+        const bool found = p < n_map && __ldg(map_keys + p) == queries[i];
+        values_out[i] = found ? (map_values ? __ldg(map_values + p) : p) : 0;
+        found_out[i] = found ? 1 : 0;
+    }
+}
+
 // packed keys of `width` bytes (u32 / u16 / u8 values, [u8; N]) -> tail words, hash.cuh: key_tail_word
 __global__ void key_words_kernel(const uint8_t* __restrict__ in, uint32_t width, uint64_t n, uint64_t* __restrict__ out) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;

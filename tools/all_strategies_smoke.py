@@ -1,4 +1,4 @@
-"""compute-sanitizer target: small builds / lookups through every construction strategy + a sharded build."""
+"""Quick smoke over every construction strategy (L2-atomic cascade, per-level, bucketed, chunked, sharded) against the oracle."""
 import os, sys, importlib
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
