@@ -81,3 +81,20 @@ def test_product_package_never_touches_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
                 text = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "boomphf_oracle" not in text and "oracle/" not in text, f
+
+
+@pytest.mark.skipif(_have_gpu(), reason="checks the no-GPU failure mode")
+def test_every_compute_entry_point_fails_loudly_without_a_gpu(pkg):
+    import importlib
+    sh = importlib.import_module(pkg.__name__ + ".sharded")
+    keys = np.arange(100, dtype=np.uint64)
+    for build in (lambda: pkg.Mphf.new_parallel(1.7, keys, None),
+                  lambda: pkg.Mphf.new(1.7, keys.astype(np.uint32)),
+                  lambda: pkg.Mphf.from_chunked_iterator(1.7, [keys[:50], keys[50:]], 100),
+                  lambda: pkg.Mphf.from_chunked_iterator_parallel(1.7, [keys], None, 100),
+                  lambda: pkg.Mphf.from_levels([(255, np.zeros(4, np.uint64), np.zeros(1, np.uint64))]),
+                  lambda: sh.ShardComm.create(0, 0, 2, 1000),
+                  lambda: pkg.BoomHashMap.new(keys, keys)):
+        with pytest.raises(pkg.MphfPanic) as e:
+            build()
+        assert e.value.code == -4, str(e.value)   # BPHF_ERR_CUDA: there is no CPU path to fall back to
