@@ -67,6 +67,31 @@ def main():
     ms.append(mphf_entry("rand_100k_g1.7_seed5", o.keygen(100000, 1, 0), 1.7, seed=5))
     ms.append(mphf_entry("rand_100k_g1.7_seed30", o.keygen(100000, 1, 0), 1.7, seed=30))
     g["mphf"] = ms
+    # key kinds and the chunked-parallel constructor (8f row 3): fingerprints of whole structures
+    def kind_keys(name):
+        rng = np.random.default_rng(2026)
+        if name == "u32":
+            return np.unique(rng.integers(0, 2**32, size=60000, dtype=np.uint64)).astype(np.uint32)[:50000]
+        if name == "i32":
+            return (np.unique(rng.integers(0, 2**32, size=60000, dtype=np.uint64)).astype(np.uint32)[:50000]).view(np.int32)
+        if name == "u16":
+            return rng.permutation(65536)[:40000].astype(np.uint16)
+        if name == "u8":
+            return rng.permutation(256)[:200].astype(np.uint8)
+        w = int(name[5:])
+        b = np.unique(rng.integers(0, 256, size=(30000, w), dtype=np.uint8), axis=0)
+        return b[:20000] if w > 1 else b
+    ks = []
+    for name in ["u32", "i32", "u16", "u8", "bytes1", "bytes3", "bytes5", "bytes8"]:
+        k = kind_keys(name)
+        m = o.OracleMphf.new(1.7, k)
+        ks.append({"name": name, "n": int(len(k)), "gamma": 1.7, "bits": [int(l[0]) for l in m.levels()],
+                   "sha256": o.fingerprint(m.levels()), "hash_first": [int(v) for v in m.hash_batch(k[:4])]})
+    g["key_kinds"] = ks
+    ck = o.keygen(200000, 6, 0)
+    cm = o.OracleMphf.from_chunked_iterator_parallel(2.0, np.array_split(ck, 5), None, len(ck))
+    g["chunked_parallel"] = {"n": 200000, "keygen_seed": 6, "gamma": 2.0, "bits": [int(l[0]) for l in cm.levels()],
+                             "sha256": o.fingerprint(cm.levels())}
     g["keygen"] = {"kind0_seed1_first4": ["%016x" % int(v) for v in o.keygen(4, 1, 0)],
                    "kind1_seed5_first4": ["%016x" % int(v) for v in o.keygen(4, 5, 1)]}
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "vectors.json")

@@ -507,3 +507,19 @@ def test_hybrid_switch_gives_identical_structures(pkg, oracle):
     finally:
         pkg.lib().bphf_set_hybrid(-1.0, 0)
     assert oracle.fingerprint(a.levels()) == oracle.fingerprint(b.levels())
+
+
+@pytest.mark.parametrize("entry", GOLDEN["key_kinds"], ids=[e["name"] for e in GOLDEN["key_kinds"]])
+def test_key_kind_golden_fingerprints_gpu(pkg, oracle, entry):
+    from test_oracle import _golden_kind_keys
+    keys = _golden_kind_keys(entry["name"])
+    m = pkg.Mphf.new_parallel(entry["gamma"], keys, None)
+    assert [l[0] for l in m.levels()] == entry["bits"] and oracle.fingerprint(m.levels()) == entry["sha256"]
+    assert [int(v) for v in m.hash_batch(keys[:4])] == entry["hash_first"]
+
+
+def test_chunked_parallel_golden_fingerprint_gpu(pkg, oracle):
+    e = GOLDEN["chunked_parallel"]
+    keys = oracle.keygen(e["n"], e["keygen_seed"], 0)
+    m = pkg.Mphf.from_chunked_iterator_parallel(e["gamma"], np.array_split(keys, 7), None, e["n"])
+    assert [l[0] for l in m.levels()] == e["bits"] and oracle.fingerprint(m.levels()) == e["sha256"]

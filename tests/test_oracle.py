@@ -305,3 +305,35 @@ def test_mphf_property_byte_array_keys(oracle):
     a, b = oracle.OracleMphf.new(1.7, keys), oracle.OracleMphf.new_parallel(1.7, keys)
     assert oracle.fingerprint(a.levels()) == oracle.fingerprint(b.levels())
     assert np.array_equal(np.sort(a.hash_batch(keys)), np.arange(len(keys), dtype=np.uint64))
+
+
+def _golden_kind_keys(name):
+    # must match tests/golden/make_golden.py::kind_keys
+    rng = np.random.default_rng(2026)
+    if name == "u32":
+        return np.unique(rng.integers(0, 2**32, size=60000, dtype=np.uint64)).astype(np.uint32)[:50000]
+    if name == "i32":
+        return (np.unique(rng.integers(0, 2**32, size=60000, dtype=np.uint64)).astype(np.uint32)[:50000]).view(np.int32)
+    if name == "u16":
+        return rng.permutation(65536)[:40000].astype(np.uint16)
+    if name == "u8":
+        return rng.permutation(256)[:200].astype(np.uint8)
+    w = int(name[5:])
+    b = np.unique(rng.integers(0, 256, size=(30000, w), dtype=np.uint8), axis=0)
+    return b[:20000] if w > 1 else b
+
+
+@pytest.mark.parametrize("entry", GOLDEN["key_kinds"], ids=[e["name"] for e in GOLDEN["key_kinds"]])
+def test_key_kind_golden_fingerprints(oracle, entry):
+    keys = _golden_kind_keys(entry["name"])
+    assert len(keys) == entry["n"]
+    m = oracle.OracleMphf.new_parallel(entry["gamma"], keys)
+    assert [l[0] for l in m.levels()] == entry["bits"] and oracle.fingerprint(m.levels()) == entry["sha256"]
+    assert [int(v) for v in m.hash_batch(keys[:4])] == entry["hash_first"]
+
+
+def test_chunked_parallel_golden_fingerprint(oracle):
+    e = GOLDEN["chunked_parallel"]
+    keys = oracle.keygen(e["n"], e["keygen_seed"], 0)
+    m = oracle.OracleMphf.from_chunked_iterator_parallel(e["gamma"], np.array_split(keys, 3), None, e["n"])
+    assert [l[0] for l in m.levels()] == e["bits"] and oracle.fingerprint(m.levels()) == e["sha256"]
