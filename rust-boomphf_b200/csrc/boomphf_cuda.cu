@@ -93,6 +93,14 @@ static const DeviceInfo& device_info(int dev) {
         uint64_t thresh = UINT64_MAX;
         CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
         CK(cudaFuncSetAttribute(tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TailSmem)));
+        // the level kernels keep 32 KB of TMA ring per CTA; leave the L1 room for their random probes in flight
+        // (with the carve-out maxed for occupancy the probes starve: measured 2x slower)
+        {
+            const void* ring_kernels[] = {(const void*)pass_kernel<false>, (const void*)pass_kernel<true>,
+                                          (const void*)cascade_kernel<false>, (const void*)cascade_kernel<true>,
+                                          (const void*)shard_gather_kernel<false>, (const void*)shard_gather_kernel<true>};
+            for (const void* k : ring_kernels) CK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 60));
+        }
         CK(cudaFuncSetAttribute(scatter0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CK(cudaFuncSetAttribute(scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CK(cudaFuncSetAttribute(bucket_mark_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -434,6 +442,9 @@ struct Builder {
             if (e.first == fn) return info.sm_count * e.second;
         int per_sm = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
+        cudaFuncAttributes fa;
+        if (cudaFuncGetAttributes(&fa, fn) == cudaSuccess && fa.sharedSizeBytes >= 32 * 1024)
+            per_sm = std::min(per_sm, 4);  // TMA-ring kernels: 4 x 32 KB of shared memory, the rest stays L1
         cache.emplace_back(fn, per_sm);
         return info.sm_count * per_sm;
     }

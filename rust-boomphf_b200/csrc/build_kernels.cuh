@@ -41,6 +41,37 @@ __device__ __forceinline__ void red_or_u32(uint32_t* p, uint32_t v) {
     asm volatile("red.global.or.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// ---- TMA (bulk async copy) + mbarrier helpers: key tiles are prefetched global -> shared by the copy engine, two
+// tiles ahead of the tile being processed, so the key stream costs neither LSU slots nor exposed DRAM latency
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_inval(uint64_t* bar) {
+    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@!p bra WAIT_%=;\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
 // level bookkeeping shared by the finalize kernel (last CTA), the tail kernel and the host
 // (resume after growing a buffer).  Level `level` gets k keys; returns false (status set) when a
 // buffer must grow first.
@@ -218,7 +249,10 @@ __device__ __forceinline__ void pass_body(BuildState* __restrict__ st, uint32_t 
                                           uint64_t* __restrict__ buf0, uint64_t* __restrict__ buf1,
                                           uint32_t* __restrict__ a32, uint32_t* __restrict__ c32,
                                           uint64_t* __restrict__ gather_dst = nullptr) {
-    __shared__ uint64_t stage[PASS_TILE];
+    // ring[b]: TMA destination of a key tile, and -- once every thread holds its keys in registers -- the
+    // compaction stage of that same tile
+    __shared__ __align__(128) uint64_t ring[2][PASS_TILE];
+    __shared__ __align__(8) uint64_t mbar[2];
     __shared__ uint32_t warp_tot[PASS_THREADS / 32];
     __shared__ uint64_t sh_base;
 
@@ -237,14 +271,43 @@ __device__ __forceinline__ void pass_body(BuildState* __restrict__ st, uint32_t 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
     const uint64_t n_tiles = (k_src + PASS_TILE - 1) / PASS_TILE;
-    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    // full tiles of a 16-byte aligned source come through the TMA ring; a partial last tile (or an unaligned
+    // caller buffer) through plain loads
+    const bool tma_ok = (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+    auto issue = [&](uint64_t t, int b) {
+        if (tma_ok && t < n_tiles && (t + 1) * PASS_TILE <= k_src) {
+            mbar_expect_tx(&mbar[b], PASS_TILE * 8);
+            bulk_load(ring[b], src + t * PASS_TILE, PASS_TILE * 8, &mbar[b]);
+        }
+    };
+    if (threadIdx.x == 0) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        fence_mbar_init();
+        fence_proxy_async();
+        issue(blockIdx.x, 0);
+        issue((uint64_t)blockIdx.x + gridDim.x, 1);
+    }
+    __syncthreads();
+    uint32_t phase = 0;  // bit b: parity of mbar[b]'s next completion
+    uint32_t it = 0;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
+        const int rb = it & 1;
+        uint64_t* __restrict__ stage = ring[rb];
         const uint64_t base = tile * PASS_TILE + threadIdx.x;
         uint64_t key[PASS_KPT];
         uint32_t cw[PASS_KPT], sh[PASS_KPT];
+        if (tma_ok && (tile + 1) * PASS_TILE <= k_src) {
+            mbar_wait(&mbar[rb], (phase >> rb) & 1u);
+            phase ^= 1u << rb;
 #pragma unroll
-        for (int j = 0; j < PASS_KPT; j++) {
-            const uint64_t i = base + (uint64_t)j * PASS_THREADS;
-            key[j] = (i < k_src) ? ld_stream_u64(src + i) : 0;
+            for (int j = 0; j < PASS_KPT; j++) key[j] = stage[threadIdx.x + j * PASS_THREADS];
+        } else {
+#pragma unroll
+            for (int j = 0; j < PASS_KPT; j++) {
+                const uint64_t i = base + (uint64_t)j * PASS_THREADS;
+                key[j] = (i < k_src) ? ld_stream_u64(src + i) : 0;
+            }
         }
         // Context::filter (src/lib.rs:443-452): does this key's level-(l-1) slot collide?
 #pragma unroll
@@ -287,7 +350,11 @@ __device__ __forceinline__ void pass_body(BuildState* __restrict__ st, uint32_t 
         // an unsharded build knows k(level) before this kernel runs and sized the list for it; a shard of a
         // sharded build only has an estimate of its own share
         if (out + total > dst_cap) {
-            if (threadIdx.x == 0) st->status = ST_ERR_LIST_OVERFLOW;
+            if (threadIdx.x == 0) {
+                st->status = ST_ERR_LIST_OVERFLOW;
+                fence_proxy_async();
+                issue(tile + 2 * (uint64_t)gridDim.x, rb);  // keep the ring protocol intact on the error path
+            }
             __syncthreads();
             continue;
         }
@@ -320,7 +387,18 @@ __device__ __forceinline__ void pass_body(BuildState* __restrict__ st, uint32_t 
                 if (old[j] & m[j]) red_or_u32(c32 + w[j], m[j]);
         }
         __syncthreads();
+        // ring[rb] is free again: fetch the tile this CTA handles after the next one
+        if (threadIdx.x == 0) {
+            fence_proxy_async();
+            issue(tile + 2 * (uint64_t)gridDim.x, rb);
+        }
     }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_inval(&mbar[0]);
+        mbar_inval(&mbar[1]);
+    }
+    __syncthreads();
 }
 
 template <bool MAYBE_BIG>
