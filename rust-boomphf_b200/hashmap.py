@@ -117,3 +117,88 @@ class NoKeyBoomHashMap:
         out = np.zeros(len(pos), dtype=np.uint64)
         out[ok] = self.values[pos[ok].astype(np.int64)]
         return out, ok
+
+
+class BoomHashMap2:
+    """BoomHashMap2<u64, u64, u64> (src/hashmap.rs:222-394): keys plus two value arrays in MPHF order.
+    create_map (:277-302) swaps all three arrays along the same permutation; here two out-of-place scatters."""
+
+    GAMMA = 1.7  # src/hashmap.rs:306, :425
+
+    def __init__(self, mphf, keys, values, aux_values):
+        self.mphf, self.keys, self.values, self.aux_values = mphf, keys, values, aux_values
+
+    @classmethod
+    def _create_map(cls, keys, values, aux_values, mphf):
+        keys, values, aux = _u64(keys), _u64(values), _u64(aux_values)
+        if not (len(keys) == len(values) == len(aux)):
+            raise ValueError("keys, values and aux_values differ in length")
+        a = BoomHashMap._create_map(keys, values, mphf)
+        b = BoomHashMap._create_map(keys, aux, mphf)
+        return cls(mphf, a.keys, a.values, b.values)
+
+    @classmethod
+    def new(cls, keys, values, aux_values, device=0):
+        """BoomHashMap2::new (src/hashmap.rs:305-308)"""
+        return cls._create_map(keys, values, aux_values, Mphf.new(cls.GAMMA, _u64(keys), device=device))
+
+    @classmethod
+    def new_parallel(cls, keys, values, aux_values, device=0):
+        """BoomHashMap2::new_parallel (src/hashmap.rs:424-427)"""
+        return cls._create_map(keys, values, aux_values, Mphf.new_parallel(cls.GAMMA, _u64(keys), None, device=device))
+
+    def get_batch(self, queries):
+        """BoomHashMap2::get over a batch (src/hashmap.rs:310-328) -> (values, aux_values, found mask)"""
+        one = BoomHashMap(self.mphf, self.keys, self.values)
+        two = BoomHashMap(self.mphf, self.keys, self.aux_values)
+        v, f = one.get_batch(queries)
+        a, _ = two.get_batch(queries)
+        return v, a, f
+
+    def get(self, key):
+        v, a, f = self.get_batch([key])
+        return (int(v[0]), int(a[0])) if f[0] else None
+
+    def get_key_id(self, key):
+        """src/hashmap.rs:351-368"""
+        return BoomHashMap(self.mphf, self.keys, self.values).get_key_id(key)
+
+    def __len__(self):
+        return len(self.keys)
+
+    def is_empty(self):
+        return len(self.keys) == 0
+
+    def iter(self):
+        return zip(self.keys.tolist(), self.values.tolist(), self.aux_values.tolist())
+
+
+class NoKeyBoomHashMap2:
+    """NoKeyBoomHashMap2<u64, u64, u64> (src/hashmap.rs:530-641): two value arrays, no key check on get."""
+
+    def __init__(self, mphf, values, aux_values):
+        self.mphf, self.values, self.aux_values = mphf, values, aux_values
+
+    @classmethod
+    def new_parallel(cls, keys, values, aux_values, device=0):
+        """src/hashmap.rs:600-605"""
+        m = BoomHashMap2.new_parallel(keys, values, aux_values, device=device)
+        return cls(m.mphf, m.values, m.aux_values)
+
+    new = new_parallel
+
+    @classmethod
+    def new_with_mphf(cls, mphf, values, aux_values):
+        """src/hashmap.rs:608-614 -- arrays must already be in MPHF order"""
+        return cls(mphf, _u64(values), _u64(aux_values))
+
+    def get_batch(self, queries):
+        """src/hashmap.rs:617-627: Some((values[pos], aux_values[pos])) whenever try_hash is Some"""
+        pos = self.mphf.hash_batch(_u64(queries))
+        ok = pos < np.uint64(len(self.values))
+        v = np.zeros(len(pos), dtype=np.uint64)
+        a = np.zeros(len(pos), dtype=np.uint64)
+        idx = pos[ok].astype(np.int64)
+        v[ok] = self.values[idx]
+        a[ok] = self.aux_values[idx]
+        return v, a, ok

@@ -523,3 +523,24 @@ def test_chunked_parallel_golden_fingerprint_gpu(pkg, oracle):
     keys = oracle.keygen(e["n"], e["keygen_seed"], 0)
     m = pkg.Mphf.from_chunked_iterator_parallel(e["gamma"], np.array_split(keys, 7), None, e["n"])
     assert [l[0] for l in m.levels()] == e["bits"] and oracle.fingerprint(m.levels()) == e["sha256"]
+
+
+def test_boomhashmap2_and_nokey2_parity(pkg, oracle):
+    # BoomHashMap2 / NoKeyBoomHashMap2 (src/hashmap.rs:222-427, 530-641): three arrays along one permutation
+    keys = oracle.keygen(200_000, seed=41, kind=1)
+    vals = np.arange(len(keys), dtype=np.uint64) * 3 + 1
+    aux = np.arange(len(keys), dtype=np.uint64) ^ np.uint64(0xABCDEF)
+    m = pkg.BoomHashMap2.new_parallel(keys, vals, aux)
+    ref = oracle.OracleMphf.new_parallel(1.7, keys)
+    k1, v1 = ref.create_map(keys, vals)
+    k2, a1 = ref.create_map(keys, aux)
+    assert np.array_equal(m.keys, k1) and np.array_equal(m.values, v1) and np.array_equal(m.aux_values, a1)
+    absent = oracle.keygen(1000, seed=42, kind=1)
+    q = np.concatenate([keys[:1000], absent])
+    v, a, f = m.get_batch(q)
+    assert f[:1000].all() and np.array_equal(v[:1000], vals[:1000]) and np.array_equal(a[:1000], aux[:1000])
+    assert not f[1000:][~np.isin(absent, keys)].any()
+    assert m.get(int(keys[7])) == (int(vals[7]), int(aux[7])) and len(m) == len(keys)
+    nk = pkg.NoKeyBoomHashMap2.new_parallel(keys, vals, aux)
+    v, a, ok = nk.get_batch(keys[:500])
+    assert ok.all() and np.array_equal(v, vals[:500]) and np.array_equal(a, aux[:500])
