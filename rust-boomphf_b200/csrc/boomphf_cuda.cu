@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -594,18 +595,29 @@ struct Builder {
         launch_finalize(level, k_up);
     }
     void launch_cascade() {
-        static int per_sm[2] = {0, 0};
+        static std::atomic<int> per_sm[2];  // CTAs per SM that a cooperative launch accepts (0: not probed yet)
         const int v = maybe_big ? 1 : 0;
-        if (!per_sm[v]) {
+        const void* fn = maybe_big ? (const void*)cascade_kernel<true> : (const void*)cascade_kernel<false>;
+        int want = per_sm[v].load();
+        if (!want) {
             int n = 0;
-            if (maybe_big) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, cascade_kernel<true>, PASS_THREADS, 0));
-            else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, cascade_kernel<false>, PASS_THREADS, 0));
-            per_sm[v] = std::max(1, std::min(n, 8));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, PASS_THREADS, 0));
+            want = std::max(1, std::min(n, 4));  // 4 x 32 KB of TMA ring per SM; the rest of the array stays L1
         }
         const size_t ev = begin_event(5, 0);
         void* args[] = {(void*)&d_state, (void*)&d_keys, (void*)&d_buf[0], (void*)&d_buf[1], (void*)&d_words, (void*)&d_coll, (void*)&d_blockpop};
-        const void* fn = maybe_big ? (const void*)cascade_kernel<true> : (const void*)cascade_kernel<false>;
-        CK(cudaLaunchCooperativeKernel(fn, dim3(info.sm_count * per_sm[v]), dim3(PASS_THREADS), args, 0, s));
+        for (;;) {
+            const cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(info.sm_count * want), dim3(PASS_THREADS), args, 0, s);
+            if (e == cudaSuccess) break;
+            // the occupancy query and the launch can disagree (shared-memory carve-out): every CTA must be resident
+            if (e == cudaErrorCooperativeLaunchTooLarge && want > 1) {
+                cudaGetLastError();
+                want--;
+                continue;
+            }
+            CK(e);
+        }
+        per_sm[v].store(want);
         end_event(ev);
         launches++;
     }
