@@ -1374,7 +1374,8 @@ BPHF_API int bphf_build_sharded_u64(bphf_comm* c, const uint64_t* keys, uint64_t
     API_END
 }
 
-static_assert(BPHF_KIND_U64 == BPHF_KEY_U64 && BPHF_KIND_UINT == BPHF_KEY_UINT && BPHF_KIND_BYTES == BPHF_KEY_BYTES,
+static_assert((int)BPHF_KIND_U64 == (int)BPHF_KEY_U64 && (int)BPHF_KIND_UINT == (int)BPHF_KEY_UINT &&
+                  (int)BPHF_KIND_BYTES == (int)BPHF_KEY_BYTES,
               "key kinds of hash.cuh and of the public header must agree");
 static bool valid_key_kind(int kind, int width) {
     if (kind == BPHF_KIND_U64) return true;
