@@ -417,7 +417,6 @@ def main():
             "gpu_launches": launches + args.steps, "wall_ms_per_step": wall / args.steps * 1e3,
             "clocks": clocks.summary(),
         }
-        print(json.dumps(line), flush=True)
     if comm is not None:
         del m
         torch.cuda.synchronize()
@@ -425,6 +424,14 @@ def main():
         comm.close()
     if world > 1:
         dist.destroy_process_group()
+    if rank == 0:
+        # the JSON line must be the LAST thing on stdout: libraries that write through C stdio (NCCL's version
+        # banner) sit in a buffer that is otherwise flushed at exit, i.e. after Python's own output
+        try:
+            C.CDLL(None).fflush(None)
+        except Exception:
+            pass
+        print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":
