@@ -35,3 +35,22 @@ def test_our_arm_refuses_to_run_without_a_gpu():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True,
                          timeout=300)
     assert out.returncode != 0 and "no CPU fallback" in (out.stderr + out.stdout)
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.gpu
+def test_bench_line_on_the_gpu_has_every_contract_key():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--keys", "4000000", "--steps", "3", "--warmup", "3",
+                          "--cpu-baseline-keys", "4000000"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])   # the JSON line is the last line of stdout
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "e2e", "roofline", "cpu_baseline", "gpu_launches", "clocks"):
+        assert k in line, k
+    assert line["n_gpus"] == 1 and line["value"] > 0 and line["gpu_launches"] > 0 and line["dtype"] == "u64"
+    assert line["e2e"]["h2d_bytes_per_step"] == 8 * 4000000 and line["e2e"]["d2h_bytes_per_step"] > 0
+    assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(line["roofline"])
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["bit_exact_vs_gpu"] is True
+    assert line["lookup"]["permutation_ok"] is True
