@@ -71,9 +71,21 @@ def build_native(force=False, verbose=False):
         if os.path.getmtime(LIB_PATH) >= newest:
             return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [
-        "-o", LIB_PATH, os.path.join(_CSRC, "boomphf_cuda.cu")]
-    subprocess.check_call(cmd)
+    # several ranks of one torchrun may get here at once: build under a lock, into a temporary, then rename
+    import fcntl
+    with open(LIB_PATH + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and os.path.exists(LIB_PATH) and \
+                    os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(p) for p in _sources()):
+                return LIB_PATH  # another process built it while we waited
+            tmp = LIB_PATH + ".tmp.%d" % os.getpid()
+            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [
+                "-o", tmp, os.path.join(_CSRC, "boomphf_cuda.cu")]
+            subprocess.check_call(cmd)
+            os.replace(tmp, LIB_PATH)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB_PATH
 
 
