@@ -162,3 +162,33 @@ def test_sharded_bucketed_unbalanced_shards_fail_cleanly_or_match(pkg, oracle, s
     finally:
         for c in comms:
             c.close()
+
+
+def test_wrong_global_count_is_an_error_on_every_shard_not_a_hang(pkg, oracle):
+    # the first barrier of level 0 carries each shard's key count: a sum that differs from n_global stops the build
+    # with an error status on all shards (no timeout, no hang, no wrong structure)
+    import threading
+    import time
+    sh = _sharded(pkg)
+    keys = oracle.keygen(100_000, seed=77, kind=0)
+    comms = sh.ShardComm.local_group([0, 0], 200_000, 1.7)
+    errs = [None, None]
+
+    def run(r):
+        try:
+            comms[r].build(1.7, keys[r * 50_000:(r + 1) * 50_000], 120_000)   # shards hold 100 000 keys in total
+        except pkg.MphfPanic as e:
+            errs[r] = e
+
+    t0 = time.time()
+    ts = [threading.Thread(target=run, args=(r,)) for r in range(2)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    try:
+        assert all(e is not None for e in errs) and time.time() - t0 < 3.0
+        assert all(e.code in (-6, -4) for e in errs)
+    finally:
+        for c in comms:
+            c.close()
