@@ -1,7 +1,7 @@
 """Quick smoke over every construction strategy (L2-atomic cascade, per-level, bucketed, chunked, sharded) against the oracle."""
 import os, sys, importlib
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # repo root
 import numpy as np
 import __graft_entry__ as ge
 pkg = ge.load_package(); orc = ge.load_oracle(); L = pkg.lib()

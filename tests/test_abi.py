@@ -98,3 +98,16 @@ def test_every_compute_entry_point_fails_loudly_without_a_gpu(pkg):
         with pytest.raises(pkg.MphfPanic) as e:
             build()
         assert e.value.code == -4, str(e.value)   # BPHF_ERR_CUDA: there is no CPU path to fall back to
+
+
+def test_only_tests_smoke_and_bench_use_the_oracle():
+    # oracle/ is test infrastructure: nothing outside tests/, __graft_entry__.smoke()/build() and bench.py may touch it
+    offenders = []
+    for d in ("tools", "rust-boomphf_b200", "include", "profiles"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, d)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h", ".c", ".cpp")):
+                    text = open(os.path.join(dirpath, f), errors="replace").read()
+                    if "load_oracle" in text or "boomphf_oracle" in text:
+                        offenders.append(os.path.join(dirpath, f))
+    assert not offenders, offenders

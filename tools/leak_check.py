@@ -4,9 +4,9 @@ os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import __graft_entry__ as ge
-pkg = ge.load_package(); orc = ge.load_oracle(); L = pkg.lib()
+pkg = ge.load_package(); L = pkg.lib()
 sh = importlib.import_module(pkg.__name__ + ".sharded")
-keys = orc.keygen(2_000_000, seed=1)
+keys = np.unique(np.random.default_rng(7).integers(0, 2**63, 2_100_000, dtype=np.uint64))[:2_000_000]
 k32 = np.unique(np.random.default_rng(1).integers(0, 2**32, 500_000, dtype=np.uint64)).astype(np.uint32)
 def cycle():
     for mode in (0, 1, 2):
