@@ -91,7 +91,7 @@ BPHF_API int bphf_build_u64(const uint64_t *keys, uint64_t n, double gamma, int 
  *   BPHF_KEY_UINT  width 1 | 2 | 4  u8/i8, u16/i16, u32/i32           -- one write of `width` bytes
  *   BPHF_KEY_BYTES width 1..8       [u8; N], &[u8], Vec<u8> of length N -- write_usize(N), then N bytes
  * keys: n keys packed back to back, `width` bytes each.  Lookups take keys of the handle's kind. */
-enum { BPHF_KEY_U64 = 0, BPHF_KEY_UINT = 1, BPHF_KEY_BYTES = 2 };
+enum { BPHF_KEY_U64 = 0, BPHF_KEY_UINT = 1, BPHF_KEY_BYTES = 2, BPHF_KEY_STREAM = 3 };
 BPHF_API int bphf_build_keys(const void *keys, uint64_t n, int key_kind, int key_width, double gamma, int has_seed,
                              uint64_t seed, int device, int keys_mem, bphf_mphf **out);
 BPHF_API int bphf_hash_batch_keys(const bphf_mphf *m, const void *keys, uint64_t n, uint64_t *out, int mem,
@@ -100,6 +100,28 @@ BPHF_API int bphf_from_levels_keys(uint32_t n_levels, const uint64_t *bits, cons
                                    const uint64_t *const *ranks, int key_kind, int key_width, int device,
                                    bphf_mphf **out);
 BPHF_API int bphf_key_kind(const bphf_mphf *m, int *key_kind, int *key_width);
+
+/* ---- any other T: Hash -- stream keys (BPHF_KEY_STREAM) ------------------------------------
+ * hash_with_seed (src/lib.rs:60-65) feeds `T::hash` to a wyhash Hasher; the hasher only ever sees a sequence of
+ * `write(&[u8])` calls (u128: one 16-byte write; Vec<u8> / &[u8] / [u8; N]: write_usize(len) then one write of the
+ * bytes; String / &str: write(bytes) then write_u8(0xff); Vec<String>: write_usize(len) then that per element; tuples:
+ * their fields in order; ...).  The Rust shim records those calls with a recording `Hasher` and hands them over:
+ *   bytes[n_bytes]       all writes of all keys back to back
+ *   seg_ends[n_segs]     end offset (exclusive) of write j in `bytes`; write j starts where write j-1 ends
+ *   key_segs[n_keys+1]   key i made writes [key_segs[i], key_segs[i+1]);  key_segs[0] = 0, key_segs[n_keys] = n_segs
+ * The device runs the wyhash v1 core once per write, carrying the state, and finish(total bytes of the key) -- what
+ * the crate's Hasher does -- so this covers the remaining quickcheck types of the reference (Vec<String>, Vec<u8>,
+ * src/lib.rs:851-879) and every other Hash impl.  A zero-length write leaves the state unchanged.
+ * All three tables live in `mem` (host or device).  Malformed tables -> BPHF_ERR_ARG.  Duplicate keys end in
+ * BPHF_ERR_MAX_ITERS like any other kind.  bphf_from_levels_keys(..., BPHF_KEY_STREAM, 0, ...) re-creates a handle;
+ * the data model and the level / rank export are the same as for u64 keys. */
+BPHF_API int bphf_build_stream(const uint8_t *bytes, uint64_t n_bytes, const uint64_t *seg_ends, uint64_t n_segs,
+                               const uint64_t *key_segs, uint64_t n_keys, double gamma, int has_seed, uint64_t seed,
+                               int device, int mem, bphf_mphf **out);
+/* Mphf::try_hash over a batch of stream keys: out[i] = index of key i or BPHF_NONE */
+BPHF_API int bphf_hash_batch_stream(const bphf_mphf *m, const uint8_t *bytes, uint64_t n_bytes, const uint64_t *seg_ends,
+                                    uint64_t n_segs, const uint64_t *key_segs, uint64_t n_keys, uint64_t *out, int mem,
+                                    void *stream);
 
 /* ---- chunked construction ---------------------------------------------
  * Mphf::from_chunked_iterator(gamma, &chunks, n)                       src/lib.rs:112   (parallel_variant = 0)

@@ -128,8 +128,18 @@ BO_API uint64_t bo_wyrng(uint64_t *seed) {
  *   kind 1: u8 / u16 / u32 (and signed) -> write_u8 / _u16 / _u32     = one write of `width` bytes
  *   kind 2: [u8; N], &[u8], Vec<u8>     -> impl Hash for [T]: write_usize(N) (8 bytes), then one write of N bytes
  * The wyhash Hasher runs the core once per write, carrying h, and finish() mixes in the total byte count.
- * Process-wide setting (test infrastructure; set before building / hashing). */
+ * Process-wide setting (test infrastructure; set before building / hashing).
+ *   kind 3: any other T: Hash ("stream keys") -- the recorded sequence of Hasher::write calls of every key
+ *           (bytes, end offset of every write, writes per key; bo_set_key_stream); the u64 "key" handed to the
+ *           functions of this file is then the key's INDEX into those tables.
+ * A zero-length write leaves the hasher alone (the crate's write() loops over bytes.chunks(..), which yields nothing
+ * for an empty slice): BO_WY_EMPTY_WRITE_IS_NOOP, same switch as BPHF_WY_EMPTY_WRITE_IS_NOOP on the CUDA side. */
+#ifndef BO_WY_EMPTY_WRITE_IS_NOOP
+#define BO_WY_EMPTY_WRITE_IS_NOOP 1
+#endif
 static int g_key_kind = 0, g_key_width = 8;
+static const uint8_t *g_s_bytes = NULL;
+static const uint64_t *g_s_seg_ends = NULL, *g_s_key_segs = NULL;
 BO_API int bo_set_key_kind(int kind, int width) {
     if (kind == 0) width = 8;
     if (kind < 0 || kind > 2 || width < 1 || width > 8) return BO_ERR_ARG_EARLY;
@@ -137,10 +147,33 @@ BO_API int bo_set_key_kind(int kind, int width) {
     g_key_width = width;
     return 0;
 }
+BO_API int bo_set_key_stream(const uint8_t *bytes, const uint64_t *seg_ends, const uint64_t *key_segs) {
+    if (!key_segs) return BO_ERR_ARG_EARLY;
+    g_key_kind = 3;
+    g_key_width = 0;
+    g_s_bytes = bytes;
+    g_s_seg_ends = seg_ends;
+    g_s_key_segs = key_segs;
+    return 0;
+}
 BO_API uint64_t bo_hash_with_seed(uint64_t iter, uint64_t key) {
     uint64_t h = 1ULL << ((iter + iter) & 63);
     uint64_t size = 0;
     uint8_t b[8];
+    if (g_key_kind == 3) { /* one core per recorded write, state carried; finish(total bytes) */
+        const uint64_t s0 = g_s_key_segs[key], s1 = g_s_key_segs[key + 1];
+        uint64_t pos = s0 ? g_s_seg_ends[s0 - 1] : 0;
+        for (uint64_t sg = s0; sg < s1; sg++) {
+            const uint64_t end = g_s_seg_ends[sg];
+#if BO_WY_EMPTY_WRITE_IS_NOOP
+            if (end != pos)
+#endif
+                h = wyhash_core(g_s_bytes + pos, (size_t)(end - pos), h);
+            size += end - pos;
+            pos = end;
+        }
+        return wyhash_finish(size, h);
+    }
     if (g_key_kind == 2) { /* length prefix: usize N, native endian */
         const uint64_t len = (uint64_t)g_key_width;
         for (int i = 0; i < 8; i++) b[i] = (uint8_t)(len >> (8 * i));

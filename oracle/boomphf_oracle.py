@@ -41,6 +41,8 @@ def lib():
     L.bo_wyrng.argtypes = [C.POINTER(u64)]
     L.bo_set_key_kind.restype = i32
     L.bo_set_key_kind.argtypes = [i32, i32]
+    L.bo_set_key_stream.restype = i32
+    L.bo_set_key_stream.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.bo_hash_with_seed.restype = u64
     L.bo_hash_with_seed.argtypes = [u64, u64]
     L.bo_hashmod.restype = u64
@@ -91,7 +93,26 @@ def _ptr(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
-KIND_U64, KIND_UINT, KIND_BYTES = 0, 1, 2
+KIND_U64, KIND_UINT, KIND_BYTES, KIND_STREAM = 0, 1, 2, 3
+
+
+class Stream:
+    """Stream keys (kind 3): the recorded Hasher::write calls of n keys -- `data` all writes back to back (uint8),
+    `seg_ends[j]` the end offset of write j, `key_segs[i]..key_segs[i+1]` the writes of key i."""
+
+    def __init__(self, data, seg_ends, key_segs):
+        self.data = np.ascontiguousarray(data, dtype=np.uint8)
+        self.seg_ends = np.ascontiguousarray(seg_ends, dtype=np.uint64)
+        self.key_segs = np.ascontiguousarray(key_segs, dtype=np.uint64)
+
+    def __len__(self):
+        return len(self.key_segs) - 1
+
+    def use(self):
+        lib().bo_set_key_stream(_ptr(self.data), _ptr(self.seg_ends), _ptr(self.key_segs))
+
+    def indices(self):
+        return np.arange(len(self), dtype=np.uint64)
 
 
 def key_kind(keys):
@@ -142,7 +163,38 @@ class OracleMphf:
         self.kind = kind
 
     def _use_kind(self):
+        if self.kind[0] == KIND_STREAM:
+            raise TypeError("stream-key Mphf: use hash_batch_stream")
         lib().bo_set_key_kind(*self.kind)
+
+    @classmethod
+    def new_stream(cls, gamma, stream, parallel=False, starting_seed=None, nthreads=0):
+        """Mphf::new / new_parallel for keys given as their Hash byte streams (`Stream`)"""
+        idx = stream.indices()
+        stream.use()
+        out = C.c_void_p()
+        try:
+            if parallel:
+                rc = lib().bo_build_parallel(_ptr(idx), len(idx), float(gamma), 0 if starting_seed is None else 1,
+                                             0 if starting_seed is None else int(starting_seed), int(nthreads), C.byref(out))
+            else:
+                rc = lib().bo_build_serial(_ptr(idx), len(idx), float(gamma), C.byref(out))
+        finally:
+            lib().bo_set_key_kind(KIND_U64, 8)
+        if rc != BO_OK:
+            raise OracleError(rc)
+        return cls(out.value, (KIND_STREAM, 0))
+
+    def hash_batch_stream(self, stream, nthreads=1):
+        """try_hash of every key of `stream` (NONE = no level matched)"""
+        idx = stream.indices()
+        out = np.empty(len(idx), dtype=np.uint64)
+        stream.use()
+        try:
+            lib().bo_hash_batch(self._h, _ptr(idx), len(idx), _ptr(out), int(nthreads))
+        finally:
+            lib().bo_set_key_kind(KIND_U64, 8)
+        return out
 
     def __del__(self):
         try:
@@ -342,6 +394,15 @@ def keygen(n, seed=1, kind=0, start=0):
     out = np.empty(n, dtype=np.uint64)
     lib().bo_keygen(_ptr(out), int(start), int(n), int(seed), int(kind))
     return out
+
+
+def hash_stream_with_seed(it, stream, i=0):
+    """hash_with_seed(it, &key_i) for a stream key"""
+    stream.use()
+    try:
+        return int(lib().bo_hash_with_seed(int(it), int(i)))
+    finally:
+        lib().bo_set_key_kind(KIND_U64, 8)
 
 
 def hash_with_seed(it, key):

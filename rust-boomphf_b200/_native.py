@@ -35,6 +35,7 @@ SYMBOLS = [
     "bphf_comm_create", "bphf_comm_ipc_handle", "bphf_comm_connect_ipc", "bphf_comm_connect_local",
     "bphf_comm_destroy", "bphf_build_sharded_u64", "bphf_build_chunked_u64",
     "bphf_build_keys", "bphf_hash_batch_keys", "bphf_from_levels_keys", "bphf_key_kind",
+    "bphf_build_stream", "bphf_hash_batch_stream",
 ]
 
 
@@ -166,6 +167,10 @@ def lib():
     L.bphf_hash_batch_keys.argtypes = [vp, vp, u64, vp, i32, vp]
     L.bphf_from_levels_keys.restype = i32
     L.bphf_from_levels_keys.argtypes = [u32, vp, vp, vp, i32, i32, i32, C.POINTER(vp)]
+    L.bphf_build_stream.restype = i32
+    L.bphf_build_stream.argtypes = [vp, u64, vp, u64, vp, u64, dbl, i32, u64, i32, i32, C.POINTER(vp)]
+    L.bphf_hash_batch_stream.restype = i32
+    L.bphf_hash_batch_stream.argtypes = [vp, vp, u64, vp, u64, vp, u64, vp, i32, vp]
     L.bphf_key_kind.restype = i32
     L.bphf_key_kind.argtypes = [vp, C.POINTER(i32), C.POINTER(i32)]
     L.bphf_build_chunked_u64.restype = i32

@@ -93,11 +93,13 @@ static const DeviceInfo& device_info(int dev) {
         CK(cudaDeviceGetDefaultMemPool(&pool, dev));
         uint64_t thresh = UINT64_MAX;
         CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
-        CK(cudaFuncSetAttribute(tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TailSmem)));
+        CK(cudaFuncSetAttribute(tail_kernel<KeyCfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TailSmem)));
+        CK(cudaFuncSetAttribute(tail_kernel<StreamCfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TailSmem)));
         // the level kernels keep 32 KB of TMA ring per CTA; leave the L1 room for their random probes in flight
         // (with the carve-out maxed for occupancy the probes starve: measured 2x slower)
         {
             const void* ring_kernels[] = {(const void*)pass_kernel<false>, (const void*)pass_kernel<true>,
+                                          (const void*)pass_kernel<true, StreamCfg>,
                                           (const void*)cascade_kernel<false>, (const void*)cascade_kernel<true>,
                                           (const void*)shard_gather_kernel<false>, (const void*)shard_gather_kernel<true>};
             for (const void* k : ring_kernels) CK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 60));
@@ -112,7 +114,10 @@ static const DeviceInfo& device_info(int dev) {
             cudaFuncAttributes fa;
             const void* all_kernels[] = {
                 (const void*)mark_list_kernel<false>, (const void*)mark_list_kernel<true>, (const void*)pass_kernel<false>,
-                (const void*)pass_kernel<true>, (const void*)finalize_kernel, (const void*)tail_kernel,
+                (const void*)pass_kernel<true>, (const void*)finalize_kernel, (const void*)tail_kernel<KeyCfg>,
+                (const void*)mark_list_kernel<true, StreamCfg>, (const void*)pass_kernel<true, StreamCfg>,
+                (const void*)tail_kernel<StreamCfg>, (const void*)query_kernel<false, StreamCfg>,
+                (const void*)query_kernel<true, StreamCfg>, (const void*)iota_kernel, (const void*)stream_check_kernel,
                 (const void*)cascade_kernel<false>, (const void*)cascade_kernel<true>,
                 (const void*)scan_sums_kernel, (const void*)scan_top_kernel, (const void*)scan_apply_kernel,
                 (const void*)scatter0_kernel, (const void*)scatter_kernel, (const void*)bucket_mark_kernel,
@@ -405,6 +410,7 @@ struct Builder {
     uint64_t phys_words = 0;  // words_cap + TAIL_RESERVE_WORDS
     uint64_t n = 0;
     bool maybe_big = false;
+    bool stream_keys = false;  // BPHF_KIND_STREAM: key lists hold key indices, StreamCfg kernel instantiations
     uint32_t launches = 0, syncs = 0;
     bphf_comm* comm = nullptr;  // sharded build: the arenas live in the comm's peer-visible allocation
     bool gathered = false;      // sharded build: the remaining keys were collected on every shard; unsharded from here
@@ -534,9 +540,12 @@ struct Builder {
         const uint64_t cnt = level == 0 ? end - begin : k_up;
         if (cnt == 0) return;
         const uint64_t tiles = (cnt + PASS_TILE - 1) / PASS_TILE;
-        const void* fn = maybe_big ? (const void*)mark_list_kernel<true> : (const void*)mark_list_kernel<false>;
+        const void* fn = stream_keys ? (const void*)mark_list_kernel<true, StreamCfg>
+                         : maybe_big ? (const void*)mark_list_kernel<true> : (const void*)mark_list_kernel<false>;
         const int grid = (int)std::min<uint64_t>(tiles, (uint64_t)resident_grid(fn, PASS_THREADS));
-        if (maybe_big)
+        if (stream_keys)
+            mark_list_kernel<true, StreamCfg><<<grid, PASS_THREADS, 0, s>>>(d_state, level, d_keys, begin, end, d_buf[0], d_buf[1], a32(), c32(), list_cursor(level));
+        else if (maybe_big)
             mark_list_kernel<true><<<grid, PASS_THREADS, 0, s>>>(d_state, level, d_keys, begin, end, d_buf[0], d_buf[1], a32(), c32(), list_cursor(level));
         else
             mark_list_kernel<false><<<grid, PASS_THREADS, 0, s>>>(d_state, level, d_keys, begin, end, d_buf[0], d_buf[1], a32(), c32(), list_cursor(level));
@@ -545,9 +554,12 @@ struct Builder {
     }
     void launch_pass(uint32_t level, uint64_t k_src_up) {
         const uint64_t tiles = std::max<uint64_t>(1, (k_src_up + PASS_TILE - 1) / PASS_TILE);
-        const void* fn = maybe_big ? (const void*)pass_kernel<true> : (const void*)pass_kernel<false>;
+        const void* fn = stream_keys ? (const void*)pass_kernel<true, StreamCfg>
+                         : maybe_big ? (const void*)pass_kernel<true> : (const void*)pass_kernel<false>;
         const int grid = (int)std::min<uint64_t>(tiles, (uint64_t)resident_grid(fn, PASS_THREADS));
-        if (maybe_big)
+        if (stream_keys)
+            pass_kernel<true, StreamCfg><<<grid, PASS_THREADS, 0, s>>>(d_state, level, d_keys, d_buf[0], d_buf[1], a32(), c32());
+        else if (maybe_big)
             pass_kernel<true><<<grid, PASS_THREADS, 0, s>>>(d_state, level, d_keys, d_buf[0], d_buf[1], a32(), c32());
         else
             pass_kernel<false><<<grid, PASS_THREADS, 0, s>>>(d_state, level, d_keys, d_buf[0], d_buf[1], a32(), c32());
@@ -566,7 +578,7 @@ struct Builder {
     // levels >= 1 of an unsharded L2-atomic build: one cooperative launch, every CTA resident
     bool use_cascade() const {
         static const bool no_coop = getenv("BPHF_NO_COOP") != nullptr;  // debugging aid
-        if (no_coop) return false;
+        if (no_coop || stream_keys) return false;  // stream keys: per-level kernels (their own instantiations)
         return comm ? (gathered && !comm->co_located) : g_build_mode == 0;
     }
     bool sharded_now() const { return comm && !gathered; }
@@ -632,7 +644,10 @@ struct Builder {
             launches++;
             launch_barrier(BAR_PLAIN, 0);
         }
-        tail_kernel<<<1, TAIL_THREADS, sizeof(TailSmem), s>>>(d_state, d_keys, d_buf[0], d_buf[1], a32(), c32(), d_blockpop, cd);
+        if (stream_keys)
+            tail_kernel<StreamCfg><<<1, TAIL_THREADS, sizeof(TailSmem), s>>>(d_state, d_keys, d_buf[0], d_buf[1], a32(), c32(), d_blockpop, cd);
+        else
+            tail_kernel<KeyCfg><<<1, TAIL_THREADS, sizeof(TailSmem), s>>>(d_state, d_keys, d_buf[0], d_buf[1], a32(), c32(), d_blockpop, cd);
         CK(cudaGetLastError());
         end_event(ev);
         launches++;
@@ -747,6 +762,8 @@ static int build_once(const uint64_t* keys, uint64_t n, double gamma, int has_se
     Builder b(device, info, s, g_profile);
     b.n = n;
     b.comm = comm;
+    b.stream_keys = chunk && chunk->kc.kind == BPHF_KIND_STREAM;
+    if (b.stream_keys && (comm || bucket_enable)) return fail(BPHF_ERR_INTERNAL, "stream keys take the plain unsharded path");
     const uint64_t n_global = comm ? n_global_arg : n;
     const double shard_frac = (comm && n_global) ? (double)n / (double)n_global : 1.0;
 
@@ -789,7 +806,7 @@ static int build_once(const uint64_t* keys, uint64_t n, double gamma, int has_se
     {
         const double frac = g_hybrid_frac;
         const uint64_t bits0 = level_size(gamma, n_global);
-        if (!comm && g_build_mode == 0 && !bucket_enable && rebuilds == 0 && frac > 0.0 && frac < 1.0 &&
+        if (!comm && !b.stream_keys && g_build_mode == 0 && !bucket_enable && rebuilds == 0 && frac > 0.0 && frac < 1.0 &&
             bits0 >= g_hybrid_min_bits && (bits0 >> 32) == 0) {
             uint32_t shift = BUCKET_SHIFT_MAX;
             while (shift > BUCKET_SHIFT_MIN && (bits0 >> shift) < 2ull * b.slots()) shift--;
@@ -995,6 +1012,9 @@ static int build_once(const uint64_t* keys, uint64_t n, double gamma, int has_se
     if (!m) return fail(BPHF_ERR_NOMEM, "host allocation failed");
     m->device = device;
     m->kc = st.kc;
+    m->kc.s_bytes = nullptr;  // the caller's segment tables were only borrowed for the build
+    m->kc.s_seg_ends = nullptr;
+    m->kc.s_key_segs = nullptr;
     m->n_levels = st.n_levels;
     m->words_used = st.words_used;
     m->lv.assign(st.lv, st.lv + st.n_levels);
@@ -1072,7 +1092,8 @@ static int build_impl(const uint64_t* keys, uint64_t n, double gamma, int has_se
     // mode 0: levels whose (a, collide) pair does not fit the L2 are built by the bucketed kernels
     bool bucket = g_build_mode == 2;
     uint64_t min_keys = g_bucket_min_keys;
-    if (g_build_mode == 0) {
+    if (chunk && chunk->kc.kind == BPHF_KIND_STREAM) bucket = false;  // the bucketed kernels exist for word keys only
+    else if (g_build_mode == 0) {
         const double fit_bits = bucket_fit_bits();
         bucket = (double)level_size(gamma, n) > fit_bits;
         min_keys = (uint64_t)(fit_bits / gamma);
@@ -1375,7 +1396,7 @@ BPHF_API int bphf_build_sharded_u64(bphf_comm* c, const uint64_t* keys, uint64_t
 }
 
 static_assert((int)BPHF_KIND_U64 == (int)BPHF_KEY_U64 && (int)BPHF_KIND_UINT == (int)BPHF_KEY_UINT &&
-                  (int)BPHF_KIND_BYTES == (int)BPHF_KEY_BYTES,
+                  (int)BPHF_KIND_BYTES == (int)BPHF_KEY_BYTES && (int)BPHF_KIND_STREAM == (int)BPHF_KEY_STREAM,
               "key kinds of hash.cuh and of the public header must agree");
 static bool valid_key_kind(int kind, int width) {
     if (kind == BPHF_KIND_U64) return true;
@@ -1411,6 +1432,7 @@ BPHF_API int bphf_build_keys(const void* keys, uint64_t n, int key_kind, int key
     API_BEGIN
     if (!out) return fail(BPHF_ERR_ARG, "out is null");
     *out = nullptr;
+    if (key_kind == BPHF_KIND_STREAM) return fail(BPHF_ERR_ARG, "stream keys are built by bphf_build_stream");
     if (!valid_key_kind(key_kind, key_width)) return fail(BPHF_ERR_ARG, "unsupported key kind / width");
     if (key_kind == BPHF_KIND_U64)
         return build_impl(static_cast<const uint64_t*>(keys), n, gamma, has_seed, seed, device, keys_mem, nullptr, out);
@@ -1427,6 +1449,72 @@ BPHF_API int bphf_build_keys(const void* keys, uint64_t n, int key_kind, int key
     try {
         const uint64_t* d_words = keys_to_words(keys, n, spec.kc, keys_mem, s, info, scratch);
         rc = build_impl(d_words, n, gamma, has_seed, seed, device, BPHF_MEM_DEVICE, s, out, &spec);
+    } catch (...) {
+        for (void* p : scratch) cudaFreeAsync(p, s);
+        throw;
+    }
+    for (void* p : scratch) cudaFreeAsync(p, s);
+    return rc;
+    API_END
+}
+
+// ---- stream keys: any T: Hash as the recorded sequence of Hasher::write calls (hash.cuh) -------------------
+// The caller's three tables on the device (copied when they live on the host), structurally checked.
+static KeyCfg stage_stream(const uint8_t* bytes, uint64_t n_bytes, const uint64_t* seg_ends, uint64_t n_segs,
+                           const uint64_t* key_segs, uint64_t n_keys, int mem, cudaStream_t s, const DeviceInfo& info,
+                           std::vector<void*>& scratch) {
+    if (!key_segs || (n_segs && !seg_ends) || (n_bytes && !bytes))
+        throw CudaFailure{BPHF_ERR_ARG, "stream keys: null table"};
+    if (mem != BPHF_MEM_HOST && mem != BPHF_MEM_DEVICE) throw CudaFailure{BPHF_ERR_ARG, "bad mem"};
+    KeyCfg kc = make_key_cfg(BPHF_KIND_STREAM, 0);
+    auto stage = [&](const void* src, size_t size) -> const void* {
+        if (mem == BPHF_MEM_DEVICE) return src;
+        void* d = nullptr;
+        CK(cudaMallocAsync(&d, std::max<size_t>(size, 8), s));
+        scratch.push_back(d);
+        if (size) CK(cudaMemcpyAsync(d, src, size, cudaMemcpyHostToDevice, s));
+        return d;
+    };
+    kc.s_bytes = static_cast<const uint8_t*>(stage(bytes, n_bytes));
+    kc.s_seg_ends = static_cast<const uint64_t*>(stage(seg_ends, n_segs * 8));
+    kc.s_key_segs = static_cast<const uint64_t*>(stage(key_segs, (n_keys + 1) * 8));
+    uint32_t* d_bad = nullptr;
+    CK(cudaMallocAsync((void**)&d_bad, 4, s));
+    scratch.push_back(d_bad);
+    CK(cudaMemsetAsync(d_bad, 0, 4, s));
+    const uint64_t work = std::max(n_segs, n_keys);
+    const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((work + 255) / 256, (uint64_t)info.sm_count * 8));
+    stream_check_kernel<<<grid, 256, 0, s>>>(kc.s_seg_ends, n_segs, kc.s_key_segs, n_keys, n_bytes, d_bad);
+    CK(cudaGetLastError());
+    uint32_t bad = 0;
+    CK(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (bad) throw CudaFailure{BPHF_ERR_ARG, "stream keys: segment tables are not monotonic / do not add up"};
+    return kc;
+}
+
+BPHF_API int bphf_build_stream(const uint8_t* bytes, uint64_t n_bytes, const uint64_t* seg_ends, uint64_t n_segs,
+                               const uint64_t* key_segs, uint64_t n_keys, double gamma, int has_seed, uint64_t seed,
+                               int device, int mem, bphf_mphf** out) {
+    API_BEGIN
+    if (!out) return fail(BPHF_ERR_ARG, "out is null");
+    *out = nullptr;
+    if (!(gamma > 1.01)) return fail(BPHF_ERR_GAMMA, "assertion failed: gamma > 1.01");
+    const DeviceInfo& info = device_info(device);
+    DeviceGuard guard(device);
+    cudaStream_t s = own_stream(device, false);
+    ChunkSpec spec;
+    std::vector<void*> scratch;
+    int rc;
+    try {
+        spec.kc = stage_stream(bytes, n_bytes, seg_ends, n_segs, key_segs, n_keys, mem, s, info, scratch);
+        uint64_t* d_index = nullptr;  // level 0's key list: every key's index
+        CK(cudaMallocAsync((void**)&d_index, std::max<uint64_t>(n_keys, 1) * 8, s));
+        scratch.push_back(d_index);
+        const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((n_keys + 255) / 256, (uint64_t)info.sm_count * 16));
+        iota_kernel<<<grid, 256, 0, s>>>(d_index, n_keys);
+        CK(cudaGetLastError());
+        rc = build_impl(d_index, n_keys, gamma, has_seed, seed, device, BPHF_MEM_DEVICE, s, out, &spec);
     } catch (...) {
         for (void* p : scratch) cudaFreeAsync(p, s);
         throw;
@@ -1520,7 +1608,8 @@ BPHF_API int bphf_from_levels(uint32_t n_levels, const uint64_t* bits, const uin
 BPHF_API int bphf_from_levels_keys(uint32_t n_levels, const uint64_t* bits, const uint64_t* const* words,
                                    const uint64_t* const* ranks, int key_kind, int key_width, int device, bphf_mphf** out) {
     API_BEGIN
-    if (!valid_key_kind(key_kind, key_width)) return fail(BPHF_ERR_ARG, "unsupported key kind / width");
+    if (key_kind != BPHF_KIND_STREAM && !valid_key_kind(key_kind, key_width))
+        return fail(BPHF_ERR_ARG, "unsupported key kind / width");
     return from_levels_impl(n_levels, bits, words, ranks, make_key_cfg((uint32_t)key_kind, (uint32_t)key_width), device, out);
     API_END
 }
@@ -1600,8 +1689,18 @@ static int query_grid(const DeviceInfo& info, uint64_t n) {
     return (int)std::max<uint64_t>(1, std::min<uint64_t>(blocks, (uint64_t)info.sm_count * 16));
 }
 
-static void launch_query(const bphf_mphf* m, const DeviceInfo& info, const uint64_t* keys, uint64_t n, uint64_t* out, cudaStream_t s) {
-    const QView v = query_view(m);
+// stream_kc: segment tables of the query batch for a BPHF_KIND_STREAM handle (keys == nullptr: key i is index i)
+static void launch_query(const bphf_mphf* m, const DeviceInfo& info, const uint64_t* keys, uint64_t n, uint64_t* out, cudaStream_t s,
+                         const KeyCfg* stream_kc = nullptr) {
+    QView v = query_view(m);
+    if (m->kc.kind == BPHF_KIND_STREAM) {
+        if (!stream_kc) throw CudaFailure{BPHF_ERR_ARG, "this handle hashes stream keys: use bphf_hash_batch_stream"};
+        v.kc = *stream_kc;
+        if (v.lvp) query_kernel<true, StreamCfg><<<query_grid(info, n), QUERY_THREADS, 0, s>>>(v, keys, n, out);
+        else query_kernel<false, StreamCfg><<<query_grid(info, n), QUERY_THREADS, 0, s>>>(v, keys, n, out);
+        CK(cudaGetLastError());
+        return;
+    }
     if (v.lvp && g_query_mode == 0) {
         const uint64_t tiles = (n + (uint64_t)QS_WTILE * QS_WARPS - 1) / ((uint64_t)QS_WTILE * QS_WARPS);
         // persistent CTAs: exactly one wave of resident CTAs, each walks tiles blockIdx, +gridDim, ...
@@ -1622,6 +1721,7 @@ BPHF_API int bphf_hash_batch_u64(const bphf_mphf* m, const uint64_t* keys, uint6
     if (!m) return fail(BPHF_ERR_ARG, "null handle");
     if (n == 0) return BPHF_OK;
     if (!keys || !out) return fail(BPHF_ERR_ARG, "null buffer");
+    if (m->kc.kind == BPHF_KIND_STREAM) return fail(BPHF_ERR_ARG, "this handle hashes stream keys: use bphf_hash_batch_stream");
     const DeviceInfo& info = device_info(m->device);
     DeviceGuard guard(m->device);
     cudaStream_t s = stream ? (cudaStream_t)stream : own_stream(m->device, false);
@@ -1681,6 +1781,7 @@ BPHF_API int bphf_hash_batch_keys(const bphf_mphf* m, const void* keys, uint64_t
     API_BEGIN
     if (!m) return fail(BPHF_ERR_ARG, "null handle");
     if (m->kc.kind == BPHF_KIND_U64) return bphf_hash_batch_u64(m, static_cast<const uint64_t*>(keys), n, out, mem, stream);
+    if (m->kc.kind == BPHF_KIND_STREAM) return fail(BPHF_ERR_ARG, "this handle hashes stream keys: use bphf_hash_batch_stream");
     if (n == 0) return BPHF_OK;
     if (!keys || !out) return fail(BPHF_ERR_ARG, "null buffer");
     const DeviceInfo& info = device_info(m->device);
@@ -1696,6 +1797,38 @@ BPHF_API int bphf_hash_batch_keys(const bphf_mphf* m, const void* keys, uint64_t
         }
         launch_query(m, info, d_words, n, d_out, s);
         if (mem == BPHF_MEM_HOST) CK(cudaMemcpyAsync(out, d_out, n * 8, cudaMemcpyDeviceToHost, s));
+        for (void* p : scratch) CK(cudaFreeAsync(p, s));
+        scratch.clear();
+        CK(cudaStreamSynchronize(s));
+    } catch (...) {
+        for (void* p : scratch) cudaFreeAsync(p, s);
+        throw;
+    }
+    return BPHF_OK;
+    API_END
+}
+
+BPHF_API int bphf_hash_batch_stream(const bphf_mphf* m, const uint8_t* bytes, uint64_t n_bytes, const uint64_t* seg_ends,
+                                    uint64_t n_segs, const uint64_t* key_segs, uint64_t n_keys, uint64_t* out, int mem,
+                                    void* stream) {
+    API_BEGIN
+    if (!m) return fail(BPHF_ERR_ARG, "null handle");
+    if (m->kc.kind != BPHF_KIND_STREAM) return fail(BPHF_ERR_ARG, "this handle does not hash stream keys");
+    if (n_keys == 0) return BPHF_OK;
+    if (!out) return fail(BPHF_ERR_ARG, "null buffer");
+    const DeviceInfo& info = device_info(m->device);
+    DeviceGuard guard(m->device);
+    cudaStream_t s = stream ? (cudaStream_t)stream : own_stream(m->device, false);
+    std::vector<void*> scratch;
+    try {
+        const KeyCfg kc = stage_stream(bytes, n_bytes, seg_ends, n_segs, key_segs, n_keys, mem, s, info, scratch);
+        uint64_t* d_out = out;
+        if (mem == BPHF_MEM_HOST) {
+            CK(cudaMallocAsync((void**)&d_out, n_keys * 8, s));
+            scratch.push_back(d_out);
+        }
+        launch_query(m, info, nullptr, n_keys, d_out, s, &kc);
+        if (mem == BPHF_MEM_HOST) CK(cudaMemcpyAsync(out, d_out, n_keys * 8, cudaMemcpyDeviceToHost, s));
         for (void* p : scratch) CK(cudaFreeAsync(p, s));
         scratch.clear();
         CK(cudaStreamSynchronize(s));

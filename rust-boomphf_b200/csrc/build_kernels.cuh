@@ -164,8 +164,8 @@ __device__ __forceinline__ void mark_bit(uint32_t* __restrict__ a32, uint32_t* _
     if (old & m) red_or_u32(c32 + w, m);
 }
 
-template <bool BIG>
-__device__ __forceinline__ uint64_t level_index(const KeyCfg& kc, uint64_t sp0, uint64_t key, uint64_t bits) {
+template <bool BIG, class KC>
+__device__ __forceinline__ uint64_t level_index(const KC& kc, uint64_t sp0, uint64_t key, uint64_t bits) {
     if (BIG) return hashmod_big(kc, sp0, key, bits);
     return hashmod_small(kc, sp0, key, (uint32_t)bits);
 }
@@ -174,7 +174,7 @@ __device__ __forceinline__ uint64_t level_index(const KeyCfg& kc, uint64_t sp0, 
 // mark_list_kernel: find_collisions only, over a contiguous key list.  level 0: the input keys
 // [key_begin, key_end); level >= 1 (first plain level after the bucketed prefix): the list in buf[level & 1]
 // ---------------------------------------------------------------------------------------------
-template <bool MAYBE_BIG>
+template <bool MAYBE_BIG, class KC = KeyCfg>
 __global__ void __launch_bounds__(PASS_THREADS)
     mark_list_kernel(BuildState* __restrict__ st, uint32_t level, const uint64_t* __restrict__ user_keys,
                      uint64_t key_begin, uint64_t key_end, const uint64_t* __restrict__ buf0,
@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(PASS_THREADS)
             if (blockIdx.x == 0 && threadIdx.x == 0) st->redo_count = key_end;
         }
     }
-    const KeyCfg kc = st->kc;
+    const KC kc(st->kc);
     const uint64_t bits = st->lv[level].bits;
     const uint64_t sp0 = st->lv[level].sp0;
     const uint64_t off32 = st->lv[level].word_off * 2;
@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(PASS_THREADS)
 // ---------------------------------------------------------------------------------------------
 // GATHER: only filter + compact, into `gather_dst` (a shard's exchange slot); level `level` is marked later from
 // the collected list
-template <bool MAYBE_BIG, bool GATHER = false>
+template <bool MAYBE_BIG, bool GATHER = false, class KC = KeyCfg>
 __device__ __forceinline__ void pass_body(BuildState* __restrict__ st, uint32_t level, const uint64_t* __restrict__ user_keys,
                                           uint64_t* __restrict__ buf0, uint64_t* __restrict__ buf1,
                                           uint32_t* __restrict__ a32, uint32_t* __restrict__ c32,
@@ -258,7 +258,7 @@ __device__ __forceinline__ void pass_body(BuildState* __restrict__ st, uint32_t 
 
     // level descriptors are written by another CTA earlier in the same launch when this runs inside the
     // persistent cascade kernel: read them through L2
-    const KeyCfg kc = st->kc;
+    const KC kc(st->kc);
     const LevelDesc* pv = &st->lv[level - 1];
     const LevelDesc* cu = &st->lv[level];
     const uint64_t p_bits = __ldcg(&pv->bits), p_sp0 = __ldcg(&pv->sp0), p_off32 = __ldcg(&pv->word_off) * 2, k_src = __ldcg(&pv->k_loc);
@@ -401,14 +401,14 @@ __device__ __forceinline__ void pass_body(BuildState* __restrict__ st, uint32_t 
     __syncthreads();
 }
 
-template <bool MAYBE_BIG>
+template <bool MAYBE_BIG, class KC = KeyCfg>
 __global__ void __launch_bounds__(PASS_THREADS)
     pass_kernel(BuildState* __restrict__ st, uint32_t level, const uint64_t* __restrict__ user_keys,
                 uint64_t* __restrict__ buf0, uint64_t* __restrict__ buf1, uint32_t* __restrict__ a32,
                 uint32_t* __restrict__ c32) {
     if (st->status != ST_RUNNING || st->n_levels != level || level >= st->tail_level) return;
     if (st->lv[level - 1].b_range != 0) return;  // bucketed predecessor: scatter_kernel filtered it already
-    pass_body<MAYBE_BIG>(st, level, user_keys, buf0, buf1, a32, c32);
+    pass_body<MAYBE_BIG, false, KC>(st, level, user_keys, buf0, buf1, a32, c32);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -562,6 +562,7 @@ struct TailSmem {
     uint32_t status;
 };
 
+template <class KC = KeyCfg>
 __global__ void __launch_bounds__(TAIL_THREADS)
     tail_kernel(BuildState* __restrict__ st, const uint64_t* __restrict__ user_keys, const uint64_t* __restrict__ buf0,
                 const uint64_t* __restrict__ buf1, uint32_t* __restrict__ words32, const uint32_t* __restrict__ c32,
@@ -570,7 +571,7 @@ __global__ void __launch_bounds__(TAIL_THREADS)
     TailSmem& s = *reinterpret_cast<TailSmem*>(tail_smem_raw);
     if (st->status != ST_RUNNING || st->tail_level == NO_TAIL || st->n_levels != st->tail_level) return;
     const uint32_t tid = threadIdx.x;
-    const KeyCfg kc = st->kc;
+    const KC kc(st->kc);
     uint32_t level = st->tail_level;
     uint32_t k = (uint32_t)st->lv[level].k_in;
     if (tid == 0) s.count = 0;

@@ -23,7 +23,8 @@ constexpr int QUERY_THREADS = 256;
 //   + popcount of the bits of the final word strictly below idx (skipped when idx % 64 == 0)
 // With level offsets that are multiples of 512 bits, "idx/512 within the level" and "arena bit / 512"
 // select the same rank entry and the same words.
-__device__ __forceinline__ uint64_t lookup_one(const KeyCfg& kc, const QLevel* __restrict__ lv, uint32_t n_levels,
+template <class KC>
+__device__ __forceinline__ uint64_t lookup_one(const KC& kc, const QLevel* __restrict__ lv, uint32_t n_levels,
                                                const uint64_t* __restrict__ words,
                                                const uint64_t* __restrict__ ranks, uint64_t key) {
     for (uint32_t l = 0; l < n_levels; l++) {
@@ -97,7 +98,8 @@ __global__ void __launch_bounds__(256)
     }
 }
 
-__device__ __forceinline__ uint64_t lookup_packed(const KeyCfg& kc, const QLevelP* __restrict__ lv, uint32_t n_levels,
+template <class KC>
+__device__ __forceinline__ uint64_t lookup_packed(const KC& kc, const QLevelP* __restrict__ lv, uint32_t n_levels,
                                                   const uint4* __restrict__ q, uint64_t key) {
     for (uint32_t l = 0; l < n_levels; l++) {
         const uint32_t idx = hashmod_small(kc, lv[l].sp0, key, lv[l].bits);
@@ -121,7 +123,8 @@ __device__ __forceinline__ uint64_t lookup_packed(const KeyCfg& kc, const QLevel
 struct PackedProbe {
     uint32_t g, bit;
 };
-__device__ __forceinline__ PackedProbe packed_slot(const KeyCfg& kc, const QLevelP& lv, uint64_t key) {
+template <class KC>
+__device__ __forceinline__ PackedProbe packed_slot(const KC& kc, const QLevelP& lv, uint64_t key) {
     const uint32_t idx = hashmod_small(kc, lv.sp0, key, lv.bits);
     PackedProbe p;
     p.g = __umulhi(idx >> 5, 0x55555556u);
@@ -159,8 +162,9 @@ struct LevelTab<false> {
     __device__ __forceinline__ void load(const QView& v) {
         for (uint32_t i = threadIdx.x; i < v.n_levels; i += blockDim.x) lv[i] = v.lv[i];
     }
-    __device__ __forceinline__ uint64_t lookup(const QView& v, uint64_t key) const {
-        return lookup_one(v.kc, lv, v.n_levels, v.words, v.ranks, key);
+    template <class KC>
+    __device__ __forceinline__ uint64_t lookup(const QView& v, const KC& kc, uint64_t key) const {
+        return lookup_one(kc, lv, v.n_levels, v.words, v.ranks, key);
     }
 };
 template <>
@@ -169,21 +173,24 @@ struct LevelTab<true> {
     __device__ __forceinline__ void load(const QView& v) {
         for (uint32_t i = threadIdx.x; i < v.n_levels; i += blockDim.x) lv[i] = v.lvp[i];
     }
-    __device__ __forceinline__ uint64_t lookup(const QView& v, uint64_t key) const {
-        return lookup_packed(v.kc, lv, v.n_levels, v.packed, key);
+    template <class KC>
+    __device__ __forceinline__ uint64_t lookup(const QView& v, const KC& kc, uint64_t key) const {
+        return lookup_packed(kc, lv, v.n_levels, v.packed, key);
     }
 };
 
 // Mphf::hash / try_hash over a batch (src/lib.rs:324-355)
-template <bool PACKED>
+// KC = StreamCfg: `keys` may be null, the keys are then the stream indices 0..n-1 themselves
+template <bool PACKED, class KC = KeyCfg>
 __global__ void __launch_bounds__(QUERY_THREADS)
     query_kernel(QView v, const uint64_t* __restrict__ keys, uint64_t n, uint64_t* __restrict__ out) {
     __shared__ LevelTab<PACKED> tab;
     tab.load(v);
     __syncthreads();
+    const KC kc(v.kc);
     const uint64_t stride = (uint64_t)gridDim.x * QUERY_THREADS;
     for (uint64_t i = (uint64_t)blockIdx.x * QUERY_THREADS + threadIdx.x; i < n; i += stride)
-        out[i] = tab.lookup(v, keys[i]);
+        out[i] = tab.lookup(v, kc, keys ? keys[i] : i);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -332,7 +339,7 @@ __global__ void __launch_bounds__(QUERY_THREADS)
     const uint64_t stride = (uint64_t)gridDim.x * QUERY_THREADS;
     for (uint64_t i = (uint64_t)blockIdx.x * QUERY_THREADS + threadIdx.x; i < n; i += stride) {
         const uint64_t k = keys[i];
-        const uint64_t pos = tab.lookup(v, k);
+        const uint64_t pos = tab.lookup(v, v.kc, k);
         if (pos >= n) {
             atomicAdd(bad, 1ULL);
             continue;
@@ -354,7 +361,7 @@ __global__ void __launch_bounds__(QUERY_THREADS)
     const uint64_t stride = (uint64_t)gridDim.x * QUERY_THREADS;
     for (uint64_t i = (uint64_t)blockIdx.x * QUERY_THREADS + threadIdx.x; i < nq; i += stride) {
         const uint64_t q = queries[i];
-        const uint64_t pos = tab.lookup(v, q);
+        const uint64_t pos = tab.lookup(v, v.kc, q);
         const bool found = pos < n_map && __ldg(map_keys + pos) == q;
         values_out[i] = found ? (map_values ? __ldg(map_values + pos) : pos) : 0;
         found_out[i] = found ? 1 : 0;
@@ -388,6 +395,27 @@ __global__ void __launch_bounds__(256)
         values_out[i] = found ? (map_values ? __ldg(map_values + p) : p) : 0;
         found_out[i] = found ? 1 : 0;
     }
+}
+
+// stream keys (hash.cuh): the level-0 key list is the index of every key; and a structural check of the caller's
+// segment tables before any kernel dereferences them (bad[0] = number of violations)
+__global__ void __launch_bounds__(256) iota_kernel(uint64_t* __restrict__ out, uint64_t n) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = i;
+}
+__global__ void __launch_bounds__(256)
+    stream_check_kernel(const uint64_t* __restrict__ seg_ends, uint64_t n_segs, const uint64_t* __restrict__ key_segs,
+                        uint64_t n_keys, uint64_t n_bytes, uint32_t* __restrict__ bad) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x, t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t v = 0;
+    for (uint64_t j = t; j < n_segs; j += stride) {
+        const uint64_t e = seg_ends[j];
+        if (e > n_bytes || (j && seg_ends[j - 1] > e)) v++;
+    }
+    for (uint64_t i = t; i < n_keys; i += stride)
+        if (key_segs[i] > key_segs[i + 1] || key_segs[i + 1] > n_segs) v++;
+    if (t == 0 && (key_segs[0] != 0 || key_segs[n_keys] != n_segs)) v++;
+    if (v) atomicAdd(bad, v);
 }
 
 // packed keys of `width` bytes (u32 / u16 / u8 values, [u8; N]) -> tail words, hash.cuh: key_tail_word

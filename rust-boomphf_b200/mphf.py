@@ -10,6 +10,7 @@ import ctypes as C
 import numpy as np
 
 from . import _native as N
+from .keys import StreamKeys, encode_keys, is_stream_like
 
 
 class MphfPanic(RuntimeError):
@@ -29,7 +30,19 @@ def _is_torch_cuda(x):
     return hasattr(x, "is_cuda") and hasattr(x, "data_ptr") and bool(x.is_cuda)
 
 
-KEY_U64, KEY_UINT, KEY_BYTES = 0, 1, 2
+KEY_U64, KEY_UINT, KEY_BYTES, KEY_STREAM = 0, 1, 2, 3
+
+
+def _as_stream(objects, rust_type=None):
+    """StreamKeys as they are; plain Python collections through the recorder stand-in (keys.encode_keys)"""
+    if isinstance(objects, StreamKeys):
+        return objects
+    return encode_keys(objects, rust_type)
+
+
+def _stream_args(sk):
+    return (C.c_void_p(sk.data.ctypes.data), int(sk.data.size), C.c_void_p(sk.seg_ends.ctypes.data),
+            int(sk.seg_ends.size), C.c_void_p(sk.key_segs.ctypes.data), len(sk))
 
 
 def _kind_of(dtype_itemsize, ndim, shape, is_uint8):
@@ -91,9 +104,10 @@ def _stream_ptr(stream):
 class Mphf:
     """A minimal perfect hash function over a set of u64 keys, resident on one B200."""
 
-    def __init__(self, handle, device):
+    def __init__(self, handle, device, rust_type=None):
         self._h = C.c_void_p(handle)
         self.device = device
+        self.rust_type = rust_type  # stream keys only: the T of Mphf<T>, used to encode single items
 
     def __del__(self):
         try:
@@ -108,7 +122,15 @@ class Mphf:
 
     # ---- constructors ---------------------------------------------------------------------
     @classmethod
-    def _build(cls, gamma, objects, starting_seed, device, stream):
+    def _build(cls, gamma, objects, starting_seed, device, stream, rust_type=None):
+        if rust_type is not None or is_stream_like(objects):
+            # Mphf<T> for any other T: Hash (Vec<u8>, String, Vec<String>, u128, tuples, ...): the recorded writes
+            sk = _as_stream(objects, rust_type)
+            out = C.c_void_p()
+            _check(N.lib().bphf_build_stream(*_stream_args(sk), float(gamma), 0 if starting_seed is None else 1,
+                                             0 if starting_seed is None else int(starting_seed), int(device),
+                                             N.MEM_HOST, C.byref(out)))
+            return cls(out.value, int(device), sk.rust_type)
         ptr, n, mem, dev, keep, kind, width = _as_any_keys(objects)
         if dev is not None:
             device = dev
@@ -126,14 +148,15 @@ class Mphf:
         return cls(out.value, int(device))
 
     @classmethod
-    def new(cls, gamma, objects, device=0, stream=None):
-        """Mphf::new(gamma, objects)  (src/lib.rs:235).  Same result as new_parallel (SURVEY 3.1)."""
-        return cls._build(gamma, objects, None, device, stream)
+    def new(cls, gamma, objects, device=0, stream=None, rust_type=None):
+        """Mphf::new(gamma, objects)  (src/lib.rs:235).  Same result as new_parallel (SURVEY 3.1).
+        rust_type (e.g. "Vec<String>", "u128", "(u32, String)") or a `StreamKeys` selects the any-T path."""
+        return cls._build(gamma, objects, None, device, stream, rust_type)
 
     @classmethod
-    def new_parallel(cls, gamma, objects, starting_seed=None, device=0, stream=None):
+    def new_parallel(cls, gamma, objects, starting_seed=None, device=0, stream=None, rust_type=None):
         """Mphf::new_parallel(gamma, objects, starting_seed)  (src/lib.rs:363)."""
-        return cls._build(gamma, objects, starting_seed, device, stream)
+        return cls._build(gamma, objects, starting_seed, device, stream, rust_type)
 
     @classmethod
     def _build_chunked(cls, gamma, objects, n, parallel, max_iters, device):
@@ -167,9 +190,11 @@ class Mphf:
         return cls._build_chunked(gamma, list(objects), n, True, max_iters, device)
 
     @classmethod
-    def from_levels(cls, levels, device=0, key_kind=KEY_U64, key_width=8):
+    def from_levels(cls, levels, device=0, key_kind=KEY_U64, key_width=8, rust_type=None):
         """Upload a deserialised Mphf<T>: levels = [(bits, words u64[], ranks u64[]), ...]; key_kind / key_width say
-        what T is (default u64)."""
+        what T is (default u64); rust_type names T for a stream-key Mphf (key_kind = KEY_STREAM)."""
+        if rust_type is not None:
+            key_kind, key_width = KEY_STREAM, 0
         n = len(levels)
         bits = np.array([l[0] for l in levels], dtype=np.uint64)
         words = [np.ascontiguousarray(l[1], dtype=np.uint64) for l in levels]
@@ -182,7 +207,7 @@ class Mphf:
         out = C.c_void_p()
         _check(N.lib().bphf_from_levels_keys(n, C.c_void_p(bits.ctypes.data), wp, rp, int(key_kind), int(key_width),
                                              int(device), C.byref(out)))
-        return cls(out.value, int(device))
+        return cls(out.value, int(device), rust_type)
 
     @property
     def key_kind(self):
@@ -250,7 +275,15 @@ class Mphf:
     # ---- lookups ----------------------------------------------------------------------------
     def hash_batch(self, keys, out=None, stream=None):
         """try_hash over a batch; entries equal to NONE (u64::MAX) are `None`.
-        numpy in -> numpy out; CUDA tensor in -> CUDA tensor out (int64 view of the u64 values)."""
+        numpy in -> numpy out; CUDA tensor in -> CUDA tensor out (int64 view of the u64 values).
+        A stream-key Mphf takes a `StreamKeys` or a collection of Python values of its rust_type."""
+        if self.key_kind[0] == KEY_STREAM:
+            sk = _as_stream(keys, self.rust_type)
+            if out is None:
+                out = np.empty(len(sk), dtype=np.uint64)
+            _check(N.lib().bphf_hash_batch_stream(self._h, *_stream_args(sk), C.c_void_p(out.ctypes.data), N.MEM_HOST,
+                                                  _stream_ptr(stream)))
+            return out
         ptr, n, mem, dev, keep, kind, width = _as_any_keys(keys)
         if (kind, width) != self.key_kind:
             raise TypeError("keys are not of the type this Mphf was built for")
@@ -273,7 +306,9 @@ class Mphf:
     def try_hash(self, item):
         """Mphf::try_hash (src/lib.rs:340): Some(rank) or None"""
         kind, width = self.key_kind
-        if kind == KEY_BYTES:
+        if kind == KEY_STREAM:
+            q = [item]
+        elif kind == KEY_BYTES:
             q = np.frombuffer(bytes(item), dtype=np.uint8).reshape(1, width)
         elif kind == KEY_UINT:
             q = np.array([int(item) & ((1 << (8 * width)) - 1)], dtype=np.dtype("u%d" % width))
