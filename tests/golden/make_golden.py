@@ -92,6 +92,33 @@ def main():
     cm = o.OracleMphf.from_chunked_iterator_parallel(2.0, np.array_split(ck, 5), None, len(ck))
     g["chunked_parallel"] = {"n": 200000, "keygen_seed": 6, "gamma": 2.0, "bits": [int(l[0]) for l in cm.levels()],
                              "sha256": o.fingerprint(cm.levels())}
+    # stream keys (any T: Hash as its recorded writes): raw hashes of hand-written write sequences, then whole
+    # structures for the seeded key sets of tests/stream_cases.py
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    sys.path.insert(0, ROOT)
+    import importlib
+    import __graft_entry__ as ge
+    from stream_cases import STREAM_TYPES, make_keys
+    K = importlib.import_module(ge.load_package().__name__ + ".keys")
+    raw = []
+    seqs = [[b"ab"], [b"", b"x"], [b"x", b""], [bytes(range(40))], [bytes(range(32))], [bytes(range(8)), b"\xff"],
+            [(2).to_bytes(8, "little"), b"ab", b"\xff", b"c", b"\xff"], [bytes(range(16))], [bytes(range(100)), bytes(range(7))]]
+    for w in seqs:
+        ends, pos = [], 0
+        for x in w:
+            pos += len(x)
+            ends.append(pos)
+        st = o.Stream(np.frombuffer(b"".join(w), dtype=np.uint8), ends, [0, len(w)])
+        raw.append({"writes": [x.hex() for x in w], "h": {str(it): "%016x" % o.hash_stream_with_seed(it, st) for it in (0, 1, 7, 33)}})
+    g["stream_hashes"] = raw
+    sk_entries = []
+    for t in STREAM_TYPES:
+        sk = K.encode_keys(make_keys(t, 3000, seed=1), t)
+        st = o.Stream(sk.data, sk.seg_ends, sk.key_segs)
+        m = o.OracleMphf.new_stream(1.7, st)
+        sk_entries.append({"rust_type": t, "n": 3000, "keys_seed": 1, "gamma": 1.7, "bits": [int(l[0]) for l in m.levels()],
+                           "sha256": o.fingerprint(m.levels()), "hash_first": [int(v) for v in m.hash_batch_stream(st)[:4]]})
+    g["stream_keys"] = sk_entries
     g["keygen"] = {"kind0_seed1_first4": ["%016x" % int(v) for v in o.keygen(4, 1, 0)],
                    "kind1_seed5_first4": ["%016x" % int(v) for v in o.keygen(4, 5, 1)]}
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "vectors.json")

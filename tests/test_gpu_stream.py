@@ -3,6 +3,8 @@ ABI against the oracle: bit-identical levels and ranks, identical hash values, t
 types (Vec<String>, Vec<u8>; /root/reference/src/lib.rs:851-879), the error paths, device-resident tables."""
 import ctypes as C
 import importlib
+import json
+import os
 
 import numpy as np
 import pytest
@@ -12,6 +14,7 @@ from stream_cases import STREAM_TYPES, make_keys
 from test_gpu_parity import assert_same_levels
 
 pytestmark = pytest.mark.gpu
+GOLDEN = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "vectors.json")))
 
 
 @pytest.fixture(scope="module")
@@ -185,3 +188,11 @@ def test_quickcheck_check_vec_u8_gpu(pkg, oracle, K, v):
     m = pkg.Mphf.new_parallel(1.7, sk, None)
     assert sorted(m.hash_batch(sk).tolist()) == list(range(len(vals)))
     assert_same_levels(m.levels(), oracle.OracleMphf.new_stream(1.7, ostream(oracle, sk), parallel=True).levels())
+
+
+@pytest.mark.parametrize("entry", GOLDEN["stream_keys"], ids=[e["rust_type"] for e in GOLDEN["stream_keys"]])
+def test_golden_stream_fingerprints_gpu(pkg, oracle, K, entry):
+    sk = K.encode_keys(make_keys(entry["rust_type"], entry["n"], seed=entry["keys_seed"]), entry["rust_type"])
+    m = pkg.Mphf.new(entry["gamma"], sk)
+    assert [l[0] for l in m.levels()] == entry["bits"] and oracle.fingerprint(m.levels()) == entry["sha256"]
+    assert [int(v) for v in m.hash_batch(sk)[:4]] == entry["hash_first"]

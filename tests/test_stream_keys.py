@@ -3,12 +3,16 @@
 single-word key kinds, a pure-Python restatement of the wyhash v1 core, and the MPHF permutation property for the
 reference's remaining quickcheck types (Vec<String>, Vec<u8>; /root/reference/src/lib.rs:851-879)."""
 import importlib
+import json
+import os
 
 import numpy as np
 import pytest
 from hypothesis import given, settings, strategies as st
 
 from stream_cases import STREAM_TYPES, make_keys
+
+GOLDEN = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "vectors.json")))
 
 
 @pytest.fixture(scope="module")
@@ -169,3 +173,23 @@ def test_quickcheck_check_vec_u8(oracle, K, v):
     s = ostream(oracle, K.encode_keys(vals, "Vec<u8>"))
     m = oracle.OracleMphf.new_stream(1.7, s)
     assert sorted(m.hash_batch_stream(s).tolist()) == list(range(len(vals)))
+
+
+# ---- committed golden vectors (tests/golden/make_golden.py) ------------------------------------------------
+def test_golden_stream_hashes(oracle):
+    for e in GOLDEN["stream_hashes"]:
+        w = [bytes.fromhex(x) for x in e["writes"]]
+        ends = np.cumsum([len(x) for x in w]).astype(np.uint64)
+        s = oracle.Stream(np.frombuffer(b"".join(w), dtype=np.uint8), ends, [0, len(w)])
+        for it, h in e["h"].items():
+            assert "%016x" % oracle.hash_stream_with_seed(int(it), s) == h
+            assert "%016x" % py_stream_hash(int(it), w) == h
+
+
+@pytest.mark.parametrize("entry", GOLDEN["stream_keys"], ids=[e["rust_type"] for e in GOLDEN["stream_keys"]])
+def test_golden_stream_fingerprints(oracle, K, entry):
+    sk = K.encode_keys(make_keys(entry["rust_type"], entry["n"], seed=entry["keys_seed"]), entry["rust_type"])
+    s = ostream(oracle, sk)
+    m = oracle.OracleMphf.new_stream(entry["gamma"], s, parallel=True)
+    assert [l[0] for l in m.levels()] == entry["bits"] and oracle.fingerprint(m.levels()) == entry["sha256"]
+    assert [int(v) for v in m.hash_batch_stream(s)[:4]] == entry["hash_first"]
