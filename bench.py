@@ -263,6 +263,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     pass_ms = [0.0, 0.0]
     cascade_ms = 0.0
+    merge0_ms = 0.0
     launches = 0
     barrier()
     with ClockSampler(local_rank, enabled=(rank == 0)) as clocks:
@@ -274,6 +275,7 @@ def main():
             pass_ms[0] += st["pass_ms"][0]
             pass_ms[1] += st["pass_ms"][1] if len(st["pass_ms"]) > 1 else 0.0
             cascade_ms += st["cascade_ms"]
+            merge0_ms += st["merge_ms"][0] if st["merge_ms"] else 0.0
             launches += st["kernel_launches"]
         e1.record(stream)
         barrier()
@@ -358,7 +360,14 @@ def main():
     # dominant kernel by time: the level-0 mark kernel, the persistent cascade kernel (N = 1: every level >= 1
     # in one launch) or, in a sharded build, the level-1 filter+mark kernel
     cands = [("mark_list_kernel (level-0 find_collisions)", pass_ms[0] / args.steps, per_pass[0])]
-    if cascade_ms > 0:
+    if world > 1 and stats["bucketed_levels"] > 0:
+        # sharded build whose full-width level-0 pair exceeds the L2: the level-0 entry step is the grouping kernel of
+        # the shared-memory mark path (reads the shard's keys, writes them into bucket regions)
+        cands = [("scatter0_kernel (level 0 of a sharded build: keys grouped by bit range for the shared-memory mark)",
+                  pass_ms[0] / args.steps, 2 * per_pass[0])]
+    if world > 1:
+        pass  # the cascade kernel of a sharded build only covers the levels after the key collection: not comparable
+    elif cascade_ms > 0:
         cands.append(("cascade_kernel (filter + compact + mark + finalize of every level >= 1, one launch)",
                       cascade_ms / args.steps, cascade_bytes))
     elif len(per_pass) > 1:
@@ -383,6 +392,14 @@ def main():
                    "achieved": (16.0 * n + 8.0 * (m.total_dims()[0] + m.total_dims()[1])) / (q_ms * 1e-3) / 1e9},
     }
     roofline["lookup"]["frac"] = roofline["lookup"]["achieved"] / peak
+    if world > 1 and merge0_ms > 0:
+        # the OR-collide fold of level 0 moves (G-1)/G * 16 W bytes into and out of every GPU
+        w0 = (stats["bits"][0] + 63) // 64
+        each_way = (world - 1) / world * 16 * w0
+        roofline["nvlink_level0"] = {"bytes_in_per_gpu": each_way, "bytes_out_per_gpu": each_way,
+                                     "ms": merge0_ms / args.steps, "what": "two device barriers + or_collide_merge_kernel",
+                                     "achieved_per_direction": each_way / (merge0_ms / args.steps * 1e-3) / 1e9,
+                                     "peak_per_direction": 900.0, "unit": "GB/s"}
 
     # ---- CPU baseline (oracle port of new_parallel on the host cores), rank 0 at N=1 only ------------------------
     cpu = None

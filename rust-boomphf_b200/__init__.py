@@ -7,4 +7,4 @@ include/boomphf_cuda.h); this package is the thin host-side mirror used by tests
 from ._native import LIB_PATH, NONE, SYMBOLS, build_native, lib  # noqa: F401
 from .mphf import Mphf, MphfPanic  # noqa: F401
 from .keys import StreamKeys, encode_keys  # noqa: F401
-from .hashmap import BoomHashMap, BoomHashMap2, NoKeyBoomHashMap, NoKeyBoomHashMap2  # noqa: F401
+from .hashmap import BoomHashMap, BoomHashMap2, BoomHashMapAny, NoKeyBoomHashMap, NoKeyBoomHashMap2  # noqa: F401

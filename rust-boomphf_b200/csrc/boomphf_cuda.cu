@@ -458,7 +458,7 @@ struct Builder {
     uint32_t slots() const { return (uint32_t)info.sm_count * 2; }
 
     size_t begin_event(int kind, uint32_t level) {
-        const bool want = profile >= 2 || (profile == 1 && ((kind <= 1 && level <= 1) || kind == 5));
+        const bool want = profile >= 2 || (profile == 1 && (((kind <= 1 || kind == 4) && level <= 1) || kind == 5));
         if (!want) return (size_t)-1;
         EventPair e;
         e.kind = kind;

@@ -202,3 +202,64 @@ class NoKeyBoomHashMap2:
         v[ok] = self.values[idx]
         a[ok] = self.aux_values[idx]
         return v, a, ok
+
+
+class BoomHashMapAny:
+    """BoomHashMap<K, D> for any other K: Hash (String, Vec<u8>, Vec<String>, u128, tuples, ... -- stream keys,
+    keys.py): the Mphf is built and queried on the GPU; keys and values are host-side Python lists held in MPHF order
+    (src/hashmap.rs:16-132).  `get` checks the stored key like the reference (:49-66)."""
+
+    GAMMA = 1.7  # src/hashmap.rs:44, :171
+
+    def __init__(self, mphf, keys, values):
+        self.mphf, self.keys, self.values = mphf, keys, values
+
+    @classmethod
+    def new(cls, keys, data, rust_type=None, device=0):
+        """BoomHashMap::new (src/hashmap.rs:43-46) / new_parallel (:170-173) -- the same structure either way"""
+        keys, data = list(keys), list(data)
+        if len(keys) != len(data):
+            raise ValueError("keys and values differ in length")
+        from .keys import encode_keys
+        sk = encode_keys(keys, rust_type)
+        mphf = Mphf.new(cls.GAMMA, sk, device=device)
+        pos = mphf.hash_batch(sk)
+        ko, vo = [None] * len(keys), [None] * len(keys)
+        for i, p in enumerate(pos.tolist()):  # create_map (:27-40): element i goes to slot hash(key i)
+            ko[p], vo[p] = keys[i], data[i]
+        return cls(mphf, ko, vo)
+
+    new_parallel = new
+
+    def get_key_id_batch(self, queries):
+        """positions of the queries that are keys of the map, None for the others (src/hashmap.rs:88-105)"""
+        queries = list(queries)
+        if not queries:
+            return []
+        pos = self.mphf.hash_batch(queries).tolist()
+        n = len(self.keys)
+        return [p if p < n and self.keys[p] == q else None for p, q in zip(pos, queries)]
+
+    def get_batch(self, queries):
+        return [None if p is None else self.values[p] for p in self.get_key_id_batch(queries)]
+
+    def get(self, key):
+        return self.get_batch([key])[0]
+
+    def get_key_id(self, key):
+        return self.get_key_id_batch([key])[0]
+
+    def get_key(self, id):
+        """src/hashmap.rs:117-124"""
+        if id > len(self.keys):
+            return None
+        return self.keys[id]
+
+    def __len__(self):
+        return len(self.keys)
+
+    def is_empty(self):
+        return len(self.keys) == 0
+
+    def iter(self):
+        return zip(self.keys, self.values)

@@ -196,3 +196,20 @@ def test_golden_stream_fingerprints_gpu(pkg, oracle, K, entry):
     m = pkg.Mphf.new(entry["gamma"], sk)
     assert [l[0] for l in m.levels()] == entry["bits"] and oracle.fingerprint(m.levels()) == entry["sha256"]
     assert [int(v) for v in m.hash_batch(sk)[:4]] == entry["hash_first"]
+
+
+def test_boomhashmap_with_string_keys(pkg):
+    """BoomHashMap<String, _> (src/hashmap.rs:16-132) over stream keys: every key finds its value, absent keys None"""
+    keys = make_keys("String", 5000, seed=12)
+    vals = [("v", i) for i in range(len(keys))]
+    m = pkg.BoomHashMapAny.new(keys, vals)
+    assert len(m) == len(keys) and not m.is_empty()
+    assert m.get_batch(keys) == vals
+    assert sorted(m.get_key_id_batch(keys)) == list(range(len(keys)))
+    absent = [k + "\x00absent" for k in keys[:200]]
+    assert m.get_batch(absent) == [None] * 200
+    assert m.get(keys[7]) == vals[7] and m.get("no such key, surely") is None
+    assert m.get_key(m.get_key_id(keys[3])) == keys[3]
+    assert dict(m.iter()) == dict(zip(keys, vals))
+    mb = pkg.BoomHashMapAny.new([b"a", b"bb", b""], [1, 2, 3], rust_type="Vec<u8>")
+    assert [mb.get(b"a"), mb.get(b"bb"), mb.get(b""), mb.get(b"c")] == [1, 2, 3, None]
