@@ -544,3 +544,35 @@ def test_boomhashmap2_and_nokey2_parity(pkg, oracle):
     nk = pkg.NoKeyBoomHashMap2.new_parallel(keys, vals, aux)
     v, a, ok = nk.get_batch(keys[:500])
     assert ok.all() and np.array_equal(v, vals[:500]) and np.array_equal(a, aux[:500])
+
+
+def test_concurrent_builds_and_lookups_from_host_threads(pkg, oracle):
+    """Mphf is Send + Sync and `hash` takes &self (src/lib.rs:324): one handle answers lookups from many host threads
+    at once, and independent builds may run concurrently (each thread gets its own streams inside the library)."""
+    import threading
+    shared_keys = oracle.keygen(400_000, seed=90, kind=0)
+    shared = pkg.Mphf.new_parallel(1.7, shared_keys, None)
+    want_shared = oracle.OracleMphf.new_parallel(1.7, shared_keys).hash_batch(shared_keys, nthreads=0)
+    n_threads, errors = 8, []
+
+    def worker(t):
+        try:
+            keys = oracle.keygen(150_000 + 1000 * t, seed=100 + t, kind=t % 2)
+            ref = oracle.OracleMphf.new(1.7, keys)
+            for rep in range(3):
+                m = pkg.Mphf.new_parallel(1.7, keys, None)
+                assert oracle.fingerprint(m.levels()) == oracle.fingerprint(ref.levels()), ("build", t, rep)
+                lo = (t * 50_000) % len(shared_keys)
+                got = shared.hash_batch(shared_keys[lo:lo + 50_000])
+                assert np.array_equal(got, want_shared[lo:lo + 50_000]), ("shared lookup", t, rep)
+                assert np.array_equal(m.hash_batch(keys), ref.hash_batch(keys)), ("own lookup", t, rep)
+        except BaseException as e:  # noqa: BLE001 -- reported in the main thread
+            errors.append((t, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(n_threads)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join(timeout=300)
+    assert not any(th.is_alive() for th in threads), "a worker thread hung"
+    assert not errors, errors
