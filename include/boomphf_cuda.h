@@ -213,6 +213,8 @@ typedef struct bphf_build_stats {
     uint32_t rebuilds;                     /* 1 when a bucket overflow forced an unbucketed rebuild */
     float merge_ms[BPHF_MAX_LEVELS + 1];   /* sharded build: barrier + OR-collide merge + barrier (profile 2) */
     float cascade_ms;                      /* persistent kernel that runs every level >= 1 (build mode 0)     */
+    uint32_t streamed_ingest;              /* 1: the host keys went through the device ring (bphf_set_ingest_mode) */
+    uint64_t peak_device_bytes;            /* high-water mark of the device's default memory pool after the build  */
 } bphf_build_stats;
 BPHF_API int bphf_get_build_stats(const bphf_mphf *m, bphf_build_stats *out);
 /* 0: no events; 1: CUDA events around the kernels of levels 0 and 1; 2: around every kernel.
@@ -225,6 +227,16 @@ BPHF_API int bphf_set_profile(int level);
  *   mode 2           = large levels are built in shared memory after grouping the keys by bit range ("bucketed"),
  *                      levels with fewer than bucket_min_keys keys (0 = default 2^20) by the mode-1 kernels. */
 BPHF_API int bphf_set_build_mode(int mode, uint64_t bucket_min_keys);
+/* ingest of HOST key sets (bphf_build_u64 and bphf_build_chunked_u64 with BPHF_MEM_HOST; identical results):
+ *   mode 0 (default) = automatic: a key set whose 8 n bytes plus the work buffers of an in-core build do not fit the
+ *                      device's free memory is STREAMED -- the host keys pass through a 3-slot device ring twice (mark of
+ *                      level 0; filter of level 0 + mark of level 1) and only the ~45 % that survive level 0 ever become
+ *                      device resident; everything else is copied whole, once, and built in core;
+ *   mode 1           = always streamed (tests, memory-constrained callers);  mode 2 = never.
+ * ring_keys = keys per ring slot (0 = default 16 Mi = 128 MiB).  This is the out-of-core side of
+ * Mphf::from_chunked_iterator[_parallel] (src/lib.rs:103-111: "the iterator is re-created once per level"): here the
+ * source is read twice in total, not once per level. */
+BPHF_API int bphf_set_ingest_mode(int mode, uint64_t ring_keys);
 /* hybrid level 0 of build mode 0 (measurement / tests; identical results): `frac` of the level's bit range is built
  * in shared memory, the rest with L2 atomics, in the same pass; levels below min_bits bits stay all-atomic.
  * Off by default (frac = 0: it measured no faster than the all-atomic level 0); out-of-range

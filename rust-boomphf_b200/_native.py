@@ -35,7 +35,7 @@ SYMBOLS = [
     "bphf_comm_create", "bphf_comm_ipc_handle", "bphf_comm_connect_ipc", "bphf_comm_connect_local",
     "bphf_comm_destroy", "bphf_build_sharded_u64", "bphf_build_chunked_u64",
     "bphf_build_keys", "bphf_hash_batch_keys", "bphf_from_levels_keys", "bphf_key_kind",
-    "bphf_build_stream", "bphf_hash_batch_stream",
+    "bphf_build_stream", "bphf_hash_batch_stream", "bphf_set_ingest_mode",
 ]
 
 
@@ -57,6 +57,8 @@ class BuildStats(C.Structure):
         ("rebuilds", C.c_uint32),
         ("merge_ms", C.c_float * (MAX_LEVELS + 1)),
         ("cascade_ms", C.c_float),
+        ("streamed_ingest", C.c_uint32),
+        ("peak_device_bytes", C.c_uint64),
     ]
 
 
@@ -167,6 +169,8 @@ def lib():
     L.bphf_hash_batch_keys.argtypes = [vp, vp, u64, vp, i32, vp]
     L.bphf_from_levels_keys.restype = i32
     L.bphf_from_levels_keys.argtypes = [u32, vp, vp, vp, i32, i32, i32, C.POINTER(vp)]
+    L.bphf_set_ingest_mode.restype = i32
+    L.bphf_set_ingest_mode.argtypes = [i32, u64]
     L.bphf_build_stream.restype = i32
     L.bphf_build_stream.argtypes = [vp, u64, vp, u64, vp, u64, dbl, i32, u64, i32, i32, C.POINTER(vp)]
     L.bphf_hash_batch_stream.restype = i32

@@ -100,6 +100,7 @@ static const DeviceInfo& device_info(int dev) {
         {
             const void* ring_kernels[] = {(const void*)pass_kernel<false>, (const void*)pass_kernel<true>,
                                           (const void*)pass_kernel<true, StreamCfg>,
+                                          (const void*)pass_chunk_kernel<false>, (const void*)pass_chunk_kernel<true>,
                                           (const void*)cascade_kernel<false>, (const void*)cascade_kernel<true>,
                                           (const void*)shard_gather_kernel<false>, (const void*)shard_gather_kernel<true>};
             for (const void* k : ring_kernels) CK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 60));
@@ -118,6 +119,7 @@ static const DeviceInfo& device_info(int dev) {
                 (const void*)mark_list_kernel<true, StreamCfg>, (const void*)pass_kernel<true, StreamCfg>,
                 (const void*)tail_kernel<StreamCfg>, (const void*)query_kernel<false, StreamCfg>,
                 (const void*)query_kernel<true, StreamCfg>, (const void*)iota_kernel, (const void*)stream_check_kernel,
+                (const void*)pass_chunk_kernel<false>, (const void*)pass_chunk_kernel<true>,
                 (const void*)cascade_kernel<false>, (const void*)cascade_kernel<true>,
                 (const void*)scan_sums_kernel, (const void*)scan_top_kernel, (const void*)scan_apply_kernel,
                 (const void*)scatter0_kernel, (const void*)scatter_kernel, (const void*)bucket_mark_kernel,
@@ -279,6 +281,13 @@ struct ChunkSpec {
     uint64_t thr = 0;        // (0.01f32 * n as f32) as u64
     int has_max = 0;
     uint64_t max_iters = 0;
+    // streamed ingest (ring_keys > 0): the level-0 keys stay in HOST memory as n_segs arrays and pass through a small
+    // device ring twice (mark of level 0, then filter of level 0 + mark of level 1); level 1's list is where the key
+    // set becomes device resident
+    const uint64_t* const* seg_ptr = nullptr;
+    const uint64_t* seg_len = nullptr;
+    uint64_t n_segs = 0;
+    uint64_t ring_keys = 0;
 };
 
 struct LevelPlan {
@@ -536,9 +545,10 @@ struct Builder {
     uint32_t* c32() const { return reinterpret_cast<uint32_t*>(d_coll); }
 
     // ---- plain (L2-atomic) kernels ----------------------------------------------------------------
-    void launch_mark_list(uint32_t level, uint64_t begin, uint64_t end, uint64_t k_up) {
+    void launch_mark_list(uint32_t level, uint64_t begin, uint64_t end, uint64_t k_up, const uint64_t* keys_override = nullptr) {
         const uint64_t cnt = level == 0 ? end - begin : k_up;
         if (cnt == 0) return;
+        const uint64_t* d_keys = keys_override ? keys_override : this->d_keys;
         const uint64_t tiles = (cnt + PASS_TILE - 1) / PASS_TILE;
         const void* fn = stream_keys ? (const void*)mark_list_kernel<true, StreamCfg>
                          : maybe_big ? (const void*)mark_list_kernel<true> : (const void*)mark_list_kernel<false>;
@@ -563,6 +573,17 @@ struct Builder {
             pass_kernel<true><<<grid, PASS_THREADS, 0, s>>>(d_state, level, d_keys, d_buf[0], d_buf[1], a32(), c32());
         else
             pass_kernel<false><<<grid, PASS_THREADS, 0, s>>>(d_state, level, d_keys, d_buf[0], d_buf[1], a32(), c32());
+        CK(cudaGetLastError());
+        launches++;
+    }
+    // streamed ingest: filter(0) + mark(1) over one chunk of the level-0 keys
+    void launch_pass_chunk(const uint64_t* chunk, uint64_t cnt) {
+        if (cnt == 0) return;
+        const uint64_t tiles = (cnt + PASS_TILE - 1) / PASS_TILE;
+        const void* fn = maybe_big ? (const void*)pass_chunk_kernel<true> : (const void*)pass_chunk_kernel<false>;
+        const int grid = (int)std::min<uint64_t>(tiles, (uint64_t)resident_grid(fn, PASS_THREADS));
+        if (maybe_big) pass_chunk_kernel<true><<<grid, PASS_THREADS, 0, s>>>(d_state, chunk, cnt, d_buf[0], d_buf[1], a32(), c32());
+        else pass_chunk_kernel<false><<<grid, PASS_THREADS, 0, s>>>(d_state, chunk, cnt, d_buf[0], d_buf[1], a32(), c32());
         CK(cudaGetLastError());
         launches++;
     }
@@ -711,9 +732,9 @@ struct Builder {
 
     // Everything level `level` might need, in dependency order; each kernel checks the device state and returns
     // at once when it is not the variant that applies.  level 0's entry step is issued by the caller (chunks).
-    void launch_level(uint32_t level, const LevelPlan* prev, const LevelPlan& cur) {
+    void launch_level(uint32_t level, const LevelPlan* prev, const LevelPlan& cur, bool entry_done = false) {
         const bool prev_maybe_b = level >= 1 && prev->maybe_bucket, prev_surely_b = level >= 1 && prev->surely_bucket;
-        if (level >= 1) {
+        if (level >= 1 && !entry_done) {
             const size_t e0 = begin_event(0, level);
             if (prev_maybe_b) launch_scatter(level, prev->range_max, prev->count_max, cur.maybe_bucket ? cur.count_max : 1);
             if (!cur.surely_bucket && prev_maybe_b) launch_mark_list(level, 0, 0, cur.k_up);
@@ -750,7 +771,23 @@ struct Builder {
 
 }  // namespace
 
-enum { BUILD_RETRY_PLAIN = 1000 };
+enum { BUILD_RETRY_PLAIN = 1000, BUILD_RETRY_INCORE = 1001 };
+
+// device ring of a streamed ingest; released on every exit path
+struct IngestRing {
+    static constexpr int SLOTS = 3;
+    cudaStream_t s;
+    uint64_t* buf[SLOTS] = {};
+    cudaEvent_t free_ev[SLOTS] = {};
+    bool used[SLOTS] = {};
+    explicit IngestRing(cudaStream_t st) : s(st) {}
+    ~IngestRing() {
+        for (int i = 0; i < SLOTS; i++) {
+            if (buf[i]) cudaFreeAsync(buf[i], s);
+            if (free_ev[i]) cudaEventDestroy(free_ev[i]);
+        }
+    }
+};
 
 // n = keys of this shard; comm == nullptr: unsharded (n_global == n)
 static int build_once(const uint64_t* keys, uint64_t n, double gamma, int has_seed, uint64_t seed, int device,
@@ -764,12 +801,21 @@ static int build_once(const uint64_t* keys, uint64_t n, double gamma, int has_se
     b.comm = comm;
     b.stream_keys = chunk && chunk->kc.kind == BPHF_KIND_STREAM;
     if (b.stream_keys && (comm || bucket_enable)) return fail(BPHF_ERR_INTERNAL, "stream keys take the plain unsharded path");
+    const bool ingest = chunk && chunk->ring_keys > 0;
+    if (ingest && (comm || bucket_enable || b.stream_keys || chunk->kc.kind != BPHF_KIND_U64))
+        return fail(BPHF_ERR_INTERNAL, "streamed ingest takes the plain unsharded u64 path");
     const uint64_t n_global = comm ? n_global_arg : n;
     const double shard_frac = (comm && n_global) ? (double)n / (double)n_global : 1.0;
 
     CK(cudaEventCreate(&b.ev_begin));
     CK(cudaEventCreate(&b.ev_end));
     CK(cudaEventRecord(b.ev_begin, s));
+    {
+        // statistics: high-water mark of the stream-ordered pool over this build
+        cudaMemPool_t pool;
+        uint64_t zero = 0;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrUsedMemHigh, &zero);
+    }
 
     Plan plan = make_plan(n_global, gamma, b.slots(), bucket_enable, min_keys, shard_frac, chunk);
     b.maybe_big = plan.maybe_big;
@@ -806,7 +852,7 @@ static int build_once(const uint64_t* keys, uint64_t n, double gamma, int has_se
     {
         const double frac = g_hybrid_frac;
         const uint64_t bits0 = level_size(gamma, n_global);
-        if (!comm && !b.stream_keys && g_build_mode == 0 && !bucket_enable && rebuilds == 0 && frac > 0.0 && frac < 1.0 &&
+        if (!comm && !b.stream_keys && !ingest && g_build_mode == 0 && !bucket_enable && rebuilds == 0 && frac > 0.0 && frac < 1.0 &&
             bits0 >= g_hybrid_min_bits && (bits0 >> 32) == 0) {
             uint32_t shift = BUCKET_SHIFT_MAX;
             while (shift > BUCKET_SHIFT_MIN && (bits0 >> shift) < 2ull * b.slots()) shift--;
@@ -826,6 +872,7 @@ static int build_once(const uint64_t* keys, uint64_t n, double gamma, int has_se
             }
         }
     }
+    if (ingest && plan.lv.size() < 2) return BUILD_RETRY_INCORE;  // level 1 may already belong to the tail kernel
     CK(cudaMallocAsync((void**)&b.d_state, sizeof(BuildState), s));
     b.alloc_arena(plan.words_cap);
     for (int i = 0; i < 2; i++) {
@@ -876,7 +923,75 @@ static int build_once(const uint64_t* keys, uint64_t n, double gamma, int has_se
         else if (hyb.on) b.launch_hybrid0(lo, hi, hyb.count);
         else b.launch_mark_list(0, lo, hi, 0);
     };
-    if (keys_mem == BPHF_MEM_HOST && n) {
+    // ST_NEED_WORDS / ST_NEED_LIST for level `level`: grow what is missing and redo the level set-up on the host until
+    // it fits, then hand the state back to the device (words_used still points at the end of the previous level)
+    auto grow_until_fits = [&](uint32_t level) {
+        const uint64_t k = st.lv[level].k_in;
+        for (;;) {
+            if (st.status == ST_NEED_WORDS) b.grow_arena(st.need);
+            else b.grow_list(level & 1, st.need);
+            st.status = ST_RUNNING;
+            if (try_make_level(&st, level, k)) break;
+        }
+        b.upload_state();
+    };
+    std::vector<LevelPlan> lps = plan.lv;
+    uint32_t first_level = 1;  // first level the common launch sequence below still has to run
+    IngestRing ring(s);
+    if (ingest) {
+        // ---- streamed ingest: two passes of the host keys through a 3-slot device ring ------------------------
+        cudaStream_t cs = own_stream(device, true);
+        for (int i = 0; i < IngestRing::SLOTS; i++) {
+            CK(cudaMallocAsync((void**)&ring.buf[i], chunk->ring_keys * 8, s));
+            CK(cudaEventCreateWithFlags(&ring.free_ev[i], cudaEventDisableTiming));
+        }
+        cudaEvent_t ready;
+        CK(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+        CK(cudaEventRecord(ready, s));  // allocations + state upload precede the copies
+        CK(cudaStreamWaitEvent(cs, ready, 0));
+        cudaEventDestroy(ready);
+        uint64_t slot = 0;
+        auto pass_over_host_keys = [&](auto&& consume) {
+            for (uint64_t g = 0; g < chunk->n_segs; g++) {
+                for (uint64_t off = 0; off < chunk->seg_len[g]; off += chunk->ring_keys, slot++) {
+                    const uint64_t cnt = std::min(chunk->ring_keys, chunk->seg_len[g] - off);
+                    const int i = (int)(slot % IngestRing::SLOTS);
+                    if (ring.used[i]) CK(cudaStreamWaitEvent(cs, ring.free_ev[i], 0));  // its last consumer is done
+                    CK(cudaMemcpyAsync(ring.buf[i], chunk->seg_ptr[g] + off, cnt * 8, cudaMemcpyHostToDevice, cs));
+                    cudaEvent_t landed;
+                    CK(cudaEventCreateWithFlags(&landed, cudaEventDisableTiming));
+                    CK(cudaEventRecord(landed, cs));
+                    CK(cudaStreamWaitEvent(s, landed, 0));
+                    cudaEventDestroy(landed);
+                    consume(ring.buf[i], cnt);
+                    CK(cudaEventRecord(ring.free_ev[i], s));
+                    ring.used[i] = true;
+                }
+            }
+        };
+        const size_t pe = b.begin_event(0, 0);
+        pass_over_host_keys([&](const uint64_t* p, uint64_t cnt) { b.launch_mark_list(0, 0, cnt, 0, p); });
+        b.end_event(pe);
+        LevelPlan lp0;
+        lp0.k_up = lp0.k_lo = n_global;
+        lps[0] = lp0;
+        b.launch_level(0, nullptr, lps[0]);
+        b.download_state();  // one extra host round trip, nothing next to a second pass over PCIe
+        if (st.status == ST_NEED_WORDS || st.status == ST_NEED_LIST) grow_until_fits(st.n_levels);
+        if (st.status == ST_RUNNING) {
+            if (st.tail_level <= 1) return BUILD_RETRY_INCORE;  // the tail kernel would want the level-0 keys resident
+            const size_t p1 = b.begin_event(0, 1);
+            pass_over_host_keys([&](const uint64_t* p, uint64_t cnt) { b.launch_pass_chunk(p, cnt); });
+            b.end_event(p1);
+            LevelPlan l1;
+            l1.k_up = l1.k_lo = st.lv[1].k_in;
+            lps[1] = l1;
+            b.launch_level(1, &lps[0], lps[1], true);
+            first_level = 2;
+        } else {
+            first_level = (uint32_t)lps.size();  // done or failed at level 0: the loop below reports it
+        }
+    } else if (keys_mem == BPHF_MEM_HOST && n) {
         CK(cudaMallocAsync((void**)&b.d_keys_owned, n * 8, s));
         b.d_keys = b.d_keys_owned;
         cudaStream_t cs = own_stream(device, true);
@@ -914,14 +1029,13 @@ static int build_once(const uint64_t* keys, uint64_t n, double gamma, int has_se
     lp0.count_max = level0_bucketed ? count0 : 1;
     lp0.hybrid_range = hyb.on ? (1u << hyb.shift) : 0;
     lp0.hybrid_count = hyb.on ? hyb.count : 0;
-    std::vector<LevelPlan> lps = plan.lv;
     if (lps.empty()) lps.push_back(lp0);
-    else lps[0] = lp0;
-    b.launch_level(0, nullptr, lps[0]);
+    else if (!ingest) lps[0] = lp0;
+    if (!ingest) b.launch_level(0, nullptr, lps[0]);
     {
         // the persistent cascade kernel takes over at the first level whose predecessor is surely plain; the
         // bucketed prefix (and the level right after it) is launched step by step
-        uint32_t l = 1;
+        uint32_t l = first_level;
         for (; l < lps.size(); l++) {
             if (comm && l == st.gather_level) {
                 b.launch_gather(l, lps[l - 1].k_up, lps[l].k_up);
@@ -964,16 +1078,7 @@ static int build_once(const uint64_t* keys, uint64_t n, double gamma, int has_se
         const uint32_t level = st.n_levels;  // the level that could not be set up / has not run yet
         if (level == 0 || level > BPHF_MAX_LEVELS) return fail(BPHF_ERR_INTERNAL, "bad resume level");
         if (st.status == ST_NEED_WORDS || st.status == ST_NEED_LIST) {
-            const uint64_t k = st.lv[level].k_in;
-            // words_used still points at the end of the previous level: grow what is missing and redo
-            // the level set-up on the host until it fits, then hand the state back to the device
-            for (;;) {
-                if (st.status == ST_NEED_WORDS) b.grow_arena(st.need);
-                else b.grow_list(level & 1, st.need);
-                st.status = ST_RUNNING;
-                if (try_make_level(&st, level, k)) break;
-            }
-            b.upload_state();
+            grow_until_fits(level);
         } else if (st.status != ST_RUNNING) {
             return fail(BPHF_ERR_INTERNAL, "unknown build status");
         }
@@ -1077,8 +1182,43 @@ static int build_once(const uint64_t* keys, uint64_t n, double gamma, int has_se
     for (uint32_t l = 0; l < st.n_levels; l++) nb += st.lv[l].b_range != 0;
     bs.bucketed_levels = nb;
     bs.rebuilds = rebuilds;
+    bs.streamed_ingest = ingest ? 1 : 0;
+    {
+        cudaMemPool_t pool;
+        uint64_t high = 0;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess &&
+            cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemHigh, &high) == cudaSuccess)
+            bs.peak_device_bytes = high;
+    }
     *out = m.release();
     return BPHF_OK;
+}
+
+// ---- ingest of HOST key sets ---------------------------------------------------------------------------------
+// 0 (default): a key set whose 8 n bytes plus the work buffers of an in-core build do not fit the device's free memory
+// is streamed through a device ring (two passes over PCIe; level 1's list is where it becomes resident), anything
+// else is copied whole (one pass); 1: always stream; 2: never.
+static int g_ingest_mode = 0;
+static uint64_t g_ingest_ring_keys = 16ull << 20;  // 128 MiB per ring slot
+
+static bool want_streamed_ingest(uint64_t n, double gamma, int device) {
+    if (g_ingest_mode == 2 || n == 0) return false;
+    if (g_ingest_mode == 1) return true;
+    DeviceGuard guard(device);
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return false;
+    cudaMemPool_t pool;
+    uint64_t reserved = 0, used = 0;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess &&
+        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
+        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess && reserved > used)
+        free_b += reserved - used;  // cached by the stream-ordered pool: available to the build
+    // in-core: the keys, the two key lists (bucket regions of level 0 and 1 when level 0 exceeds the L2: ~1.1 n and
+    // ~0.5 n keys; plain: ~0.45 n and ~0.2 n) and the (a, collide) arenas (~3.1 gamma/1.7 bits per key each)
+    const bool bucketed = g_build_mode == 2 || (g_build_mode == 0 && (double)level_size(gamma, n) > bucket_fit_bits());
+    const double lists = bucketed ? 1.6 : 0.65;
+    const double need = 8.0 * (double)n * (1.0 + lists) + 2.0 * (double)n * gamma * 1.85 / 8.0 + 512e6;
+    return need > 0.92 * (double)free_b;
 }
 
 static int build_impl(const uint64_t* keys, uint64_t n, double gamma, int has_seed, uint64_t seed, int device,
@@ -1089,6 +1229,16 @@ static int build_impl(const uint64_t* keys, uint64_t n, double gamma, int has_se
     if (keys_mem != BPHF_MEM_HOST && keys_mem != BPHF_MEM_DEVICE) return fail(BPHF_ERR_ARG, "bad keys_mem");
     // assert!(gamma > 1.01)  src/lib.rs:236,364  (NaN fails the assertion too)
     if (!(gamma > 1.01)) return fail(BPHF_ERR_GAMMA, "assertion failed: gamma > 1.01");
+    if (keys_mem == BPHF_MEM_HOST && (!chunk || (chunk->kc.kind == BPHF_KIND_U64 && chunk->ring_keys == 0)) &&
+        want_streamed_ingest(n, gamma, device)) {
+        ChunkSpec spec = chunk ? *chunk : ChunkSpec();
+        spec.seg_ptr = &keys;
+        spec.seg_len = &n;
+        spec.n_segs = 1;
+        spec.ring_keys = std::max<uint64_t>(g_ingest_ring_keys, 4096);
+        const int rc = build_once(nullptr, n, gamma, has_seed, seed, device, keys_mem, stream, false, 0, 0, out, nullptr, 0, &spec);
+        if (rc != BUILD_RETRY_INCORE) return rc;  // else: too few keys survive level 0 for the streamed schedule
+    }
     // mode 0: levels whose (a, collide) pair does not fit the L2 are built by the bucketed kernels
     bool bucket = g_build_mode == 2;
     uint64_t min_keys = g_bucket_min_keys;
@@ -1171,6 +1321,13 @@ BPHF_API int bphf_set_build_mode(int mode, uint64_t bucket_min_keys) {
     return BPHF_OK;
 }
 
+BPHF_API int bphf_set_ingest_mode(int mode, uint64_t ring_keys) {
+    if (mode < 0 || mode > 2) return fail(BPHF_ERR_ARG, "ingest mode is 0 (automatic), 1 (always streamed) or 2 (never)");
+    g_ingest_mode = mode;
+    g_ingest_ring_keys = ring_keys ? ring_keys : (16ull << 20);
+    return BPHF_OK;
+}
+
 BPHF_API int bphf_set_hybrid(double frac, uint64_t min_bits) {
     g_hybrid_frac = (frac >= 0.0 && frac < 1.0) ? frac : 0.0;
     g_hybrid_min_bits = min_bits ? min_bits : (1ull << 26);
@@ -1229,6 +1386,24 @@ BPHF_API int bphf_build_chunked_u64(const uint64_t* const* chunks, const uint64_
         *out = m.release();
         return BPHF_OK;
     }
+    ChunkSpec cs;
+    if (parallel_variant) {
+        cs.mode = 1;
+        cs.thr = (uint64_t)(0.01f * (float)n);  // f32 arithmetic as in src/lib.rs:556-557
+        cs.has_max = has_max_iters ? 1 : 0;
+        cs.max_iters = max_iters;
+    }
+    // host chunks that would not fit the device next to the work buffers: streamed, chunk by chunk, twice -- the
+    // reference's own reason for this constructor (it re-iterates the source once per level, src/lib.rs:103-111)
+    if (keys_mem == BPHF_MEM_HOST && want_streamed_ingest(n, gamma, device)) {
+        ChunkSpec spec = cs;
+        spec.seg_ptr = chunks;
+        spec.seg_len = chunk_lens;
+        spec.n_segs = n_chunks;
+        spec.ring_keys = std::max<uint64_t>(g_ingest_ring_keys, 4096);
+        const int rc = build_once(nullptr, n, gamma, 0, 0, device, keys_mem, s, false, 0, 0, out, nullptr, 0, &spec);
+        if (rc != BUILD_RETRY_INCORE) return rc;
+    }
     // gather: one contiguous device array (a single device chunk is used in place)
     const uint64_t* d_keys = nullptr;
     uint64_t* owned = nullptr;
@@ -1244,13 +1419,6 @@ BPHF_API int bphf_build_chunked_u64(const uint64_t* const* chunks, const uint64_
             off += chunk_lens[c];
         }
         d_keys = owned;
-    }
-    ChunkSpec cs;
-    if (parallel_variant) {
-        cs.mode = 1;
-        cs.thr = (uint64_t)(0.01f * (float)n);  // f32 arithmetic as in src/lib.rs:556-557
-        cs.has_max = has_max_iters ? 1 : 0;
-        cs.max_iters = max_iters;
     }
     int rc;
     try {

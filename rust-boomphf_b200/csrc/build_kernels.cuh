@@ -248,7 +248,8 @@ template <bool MAYBE_BIG, bool GATHER = false, class KC = KeyCfg>
 __device__ __forceinline__ void pass_body(BuildState* __restrict__ st, uint32_t level, const uint64_t* __restrict__ user_keys,
                                           uint64_t* __restrict__ buf0, uint64_t* __restrict__ buf1,
                                           uint32_t* __restrict__ a32, uint32_t* __restrict__ c32,
-                                          uint64_t* __restrict__ gather_dst = nullptr) {
+                                          uint64_t* __restrict__ gather_dst = nullptr,
+                                          const uint64_t* __restrict__ src_chunk = nullptr, uint64_t chunk_keys = 0) {
     // ring[b]: TMA destination of a key tile, and -- once every thread holds its keys in registers -- the
     // compaction stage of that same tile
     __shared__ __align__(128) uint64_t ring[2][PASS_TILE];
@@ -261,11 +262,13 @@ __device__ __forceinline__ void pass_body(BuildState* __restrict__ st, uint32_t 
     const KC kc(st->kc);
     const LevelDesc* pv = &st->lv[level - 1];
     const LevelDesc* cu = &st->lv[level];
-    const uint64_t p_bits = __ldcg(&pv->bits), p_sp0 = __ldcg(&pv->sp0), p_off32 = __ldcg(&pv->word_off) * 2, k_src = __ldcg(&pv->k_loc);
+    // src_chunk: one chunk of the previous level's keys (streamed ingest); otherwise the whole list
+    const uint64_t p_bits = __ldcg(&pv->bits), p_sp0 = __ldcg(&pv->sp0), p_off32 = __ldcg(&pv->word_off) * 2;
+    const uint64_t k_src = src_chunk ? chunk_keys : __ldcg(&pv->k_loc);
     const uint64_t c_bits = __ldcg(&cu->bits), c_sp0 = __ldcg(&cu->sp0), c_off32 = __ldcg(&cu->word_off) * 2;
     const bool p_big = MAYBE_BIG && (p_bits >> 32) != 0;
     const bool c_big = MAYBE_BIG && (c_bits >> 32) != 0;
-    const uint64_t* __restrict__ src = (level == 1) ? user_keys : (((level - 1) & 1) ? buf1 : buf0);
+    const uint64_t* __restrict__ src = src_chunk ? src_chunk : (level == 1) ? user_keys : (((level - 1) & 1) ? buf1 : buf0);
     uint64_t* __restrict__ dst = GATHER ? gather_dst : ((level & 1) ? buf1 : buf0);
     const uint64_t dst_cap = GATHER ? GATHER_MAX_KEYS : __ldcg(&st->list_cap[level & 1]);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -409,6 +412,18 @@ __global__ void __launch_bounds__(PASS_THREADS)
     if (st->status != ST_RUNNING || st->n_levels != level || level >= st->tail_level) return;
     if (st->lv[level - 1].b_range != 0) return;  // bucketed predecessor: scatter_kernel filtered it already
     pass_body<MAYBE_BIG, false, KC>(st, level, user_keys, buf0, buf1, a32, c32);
+}
+
+// streamed ingest (host key sets that stay out of HBM): filter(0) + compaction + mark(1) over ONE chunk of the level-0
+// keys; the survivors of all chunks accumulate in level 1's list, which is where the key set becomes device resident
+template <bool MAYBE_BIG>
+__global__ void __launch_bounds__(PASS_THREADS)
+    pass_chunk_kernel(BuildState* __restrict__ st, const uint64_t* __restrict__ chunk, uint64_t chunk_keys,
+                      uint64_t* __restrict__ buf0, uint64_t* __restrict__ buf1, uint32_t* __restrict__ a32,
+                      uint32_t* __restrict__ c32) {
+    if (st->status != ST_RUNNING || st->n_levels != 1 || 1 >= st->tail_level) return;
+    if (st->lv[0].b_range != 0) return;
+    pass_body<MAYBE_BIG>(st, 1, nullptr, buf0, buf1, a32, c32, nullptr, chunk, chunk_keys);
 }
 
 // ---------------------------------------------------------------------------------------------

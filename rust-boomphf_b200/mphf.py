@@ -270,6 +270,7 @@ class Mphf:
             "tail_ms": float(st.tail_ms), "ranks_ms": float(st.ranks_ms), "total_ms": float(st.total_ms),
             "bucketed_levels": int(st.bucketed_levels), "rebuilds": int(st.rebuilds),
             "merge_ms": [float(st.merge_ms[i]) for i in range(nl)], "cascade_ms": float(st.cascade_ms),
+            "streamed_ingest": int(st.streamed_ingest), "peak_device_bytes": int(st.peak_device_bytes),
         }
 
     # ---- lookups ----------------------------------------------------------------------------

@@ -576,3 +576,95 @@ def test_concurrent_builds_and_lookups_from_host_threads(pkg, oracle):
         th.join(timeout=300)
     assert not any(th.is_alive() for th in threads), "a worker thread hung"
     assert not errors, errors
+
+
+# ---- streamed ingest of host key sets (out-of-core side of SURVEY 8f row 3) -----------------------------------
+@pytest.fixture()
+def streamed_ingest(pkg):
+    """force every host key set through the device ring (3 slots of 10 000 keys) for the duration of a test"""
+    pkg.lib().bphf_set_ingest_mode(1, 10_000)
+    yield
+    pkg.lib().bphf_set_ingest_mode(0, 0)
+
+
+@pytest.mark.parametrize("n", [0, 1, 100, 4096, 9_999, 10_000, 10_001, 30_000, 123_457, 1_000_000, 3_000_000])
+def test_streamed_ingest_parity_sizes(pkg, oracle, streamed_ingest, n):
+    keys = oracle.keygen(n, seed=n + 7, kind=0)
+    m = pkg.Mphf.new_parallel(1.7, keys, None)
+    ref = oracle.OracleMphf.new_parallel(1.7, keys)
+    assert_same_levels(m.levels(), ref.levels())
+    if n:
+        assert np.array_equal(m.hash_batch(keys), ref.hash_batch(keys, nthreads=0))
+    # small sets (level 1 would already belong to the tail kernel) are handed to the in-core schedule
+    assert m.build_stats()["streamed_ingest"] == (1 if n >= 9_999 else 0)
+
+
+def test_streamed_ingest_keeps_the_keys_out_of_device_memory(pkg, oracle):
+    n = 4_000_000
+    keys = oracle.keygen(n, seed=77, kind=0)
+    peak = {}
+    for mode in (2, 1):
+        pkg.lib().bphf_set_ingest_mode(mode, 100_000)
+        try:
+            m = pkg.Mphf.new_parallel(1.7, keys, None)
+        finally:
+            pkg.lib().bphf_set_ingest_mode(0, 0)
+        st = m.build_stats()
+        assert st["streamed_ingest"] == (1 if mode == 1 else 0)
+        peak[mode] = st["peak_device_bytes"]
+        del m
+    # in core: the 32 MB of keys + lists + arenas; streamed: 3 ring slots of 0.8 MB instead of the keys
+    assert peak[2] >= 8 * n and peak[1] <= peak[2] - 8 * n * 0.9, peak
+
+
+@pytest.mark.parametrize("gamma", [1.02, 2.0, 5.0, 100.0, 3000.0])
+@pytest.mark.parametrize("seed", [None, 7])
+def test_streamed_ingest_gamma_and_seed(pkg, oracle, streamed_ingest, gamma, seed):
+    # gamma = 3000: almost nothing survives level 0 -> the streamed schedule hands over to the in-core one
+    keys = oracle.keygen(250_000, seed=3, kind=1)
+    m = pkg.Mphf.new_parallel(gamma, keys, seed)
+    ref = oracle.OracleMphf.new_parallel(gamma, keys, seed)
+    assert_same_levels(m.levels(), ref.levels())
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_streamed_ingest_is_independent_of_the_build_mode(pkg, oracle, streamed_ingest, mode):
+    keys = oracle.keygen(2_000_000, seed=21, kind=0)
+    ref = oracle.OracleMphf.new_parallel(1.7, keys)
+    try:
+        pkg.lib().bphf_set_build_mode(mode, 0)
+        m = pkg.Mphf.new_parallel(1.7, keys, None)
+    finally:
+        pkg.lib().bphf_set_build_mode(0, 0)
+    assert_same_levels(m.levels(), ref.levels())
+    st = m.build_stats()
+    assert st["bucketed_levels"] == 0  # the streamed schedule marks through the L2 whatever the mode says
+
+
+@pytest.mark.parametrize("parallel", [False, True])
+def test_streamed_ingest_of_host_chunks(pkg, oracle, streamed_ingest, parallel):
+    """from_chunked_iterator[_parallel] with chunks that never become device resident as a whole: ragged chunk
+    lengths around the ring size, empty chunks, the gamma switch of the parallel variant"""
+    keys = oracle.keygen(600_000, seed=31, kind=0)
+    cuts = [0, 0, 5, 9_999, 20_000, 20_000, 45_001, 300_000, 600_000]
+    chunks = [keys[a:b] for a, b in zip(cuts[:-1], cuts[1:])]
+    if parallel:
+        m = pkg.Mphf.from_chunked_iterator_parallel(2.5, chunks, None, len(keys))
+        ref = oracle.OracleMphf.from_chunked_iterator_parallel(2.5, chunks, None, len(keys))
+    else:
+        m = pkg.Mphf.from_chunked_iterator(2.5, chunks, len(keys))
+        ref = oracle.OracleMphf.from_chunked_iterator(2.5, chunks, len(keys))
+    assert_same_levels(m.levels(), ref.levels())
+    assert np.array_equal(m.hash_batch(keys), ref.hash_batch(keys, nthreads=0))
+
+
+def test_streamed_ingest_duplicates_and_regrowth(pkg, oracle, streamed_ingest):
+    keys = oracle.keygen(100_000, seed=5, kind=0)
+    dup = np.concatenate([keys, keys[:10]])
+    with pytest.raises(pkg.MphfPanic) as e:
+        pkg.Mphf.new_parallel(1.7, dup, None)
+    assert "counldn't find unique hashes" in str(e.value)
+    # heavily duplicated input makes level 1 much larger than planned: the lists / arena grow between the two passes
+    many = np.concatenate([keys[:50_000]] * 3 + [keys])
+    with pytest.raises(pkg.MphfPanic):
+        pkg.Mphf.new_parallel(1.7, many, None)
