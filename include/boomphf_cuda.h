@@ -214,7 +214,8 @@ typedef struct bphf_build_stats {
     float merge_ms[BPHF_MAX_LEVELS + 1];   /* sharded build: barrier + OR-collide merge + barrier (profile 2) */
     float cascade_ms;                      /* persistent kernel that runs every level >= 1 (build mode 0)     */
     uint32_t streamed_ingest;              /* 1: the host keys went through the device ring (bphf_set_ingest_mode) */
-    uint64_t peak_device_bytes;            /* high-water mark of the device's default memory pool after the build  */
+    uint64_t peak_device_bytes;            /* high-water mark of the device's default memory pool over the build
+                                              (streamed builds and profile 2; else 0)                             */
 } bphf_build_stats;
 BPHF_API int bphf_get_build_stats(const bphf_mphf *m, bphf_build_stats *out);
 /* 0: no events; 1: CUDA events around the kernels of levels 0 and 1; 2: around every kernel.

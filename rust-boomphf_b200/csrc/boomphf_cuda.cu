@@ -62,6 +62,7 @@ struct DeviceInfo {
     bool init = false;
     int sm_count = 0;
     int cc_major = 0;
+    uint64_t total_mem = 0;
 };
 static DeviceInfo g_dev[MAX_DEVICES];
 static std::mutex g_dev_mutex;
@@ -86,6 +87,11 @@ static const DeviceInfo& device_info(int dev) {
         CK(cudaSetDevice(dev));
         CK(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev));
         CK(cudaDeviceGetAttribute(&d.cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+        {
+            size_t free_b = 0, total_b = 0;
+            CK(cudaMemGetInfo(&free_b, &total_b));
+            d.total_mem = total_b;
+        }
         if (d.cc_major != 10)
             throw CudaFailure{BPHF_ERR_CUDA, "device is not sm_100 (Blackwell B200); kernels are built for sm_100a only"};
         // keep freed build scratch in the stream-ordered pool instead of returning it to the OS
@@ -810,7 +816,8 @@ static int build_once(const uint64_t* keys, uint64_t n, double gamma, int has_se
     CK(cudaEventCreate(&b.ev_begin));
     CK(cudaEventCreate(&b.ev_end));
     CK(cudaEventRecord(b.ev_begin, s));
-    {
+    const bool want_peak = (chunk && chunk->ring_keys > 0) || g_profile >= 2;
+    if (want_peak) {
         // statistics: high-water mark of the stream-ordered pool over this build
         cudaMemPool_t pool;
         uint64_t zero = 0;
@@ -1183,7 +1190,7 @@ static int build_once(const uint64_t* keys, uint64_t n, double gamma, int has_se
     bs.bucketed_levels = nb;
     bs.rebuilds = rebuilds;
     bs.streamed_ingest = ingest ? 1 : 0;
-    {
+    if (want_peak) {
         cudaMemPool_t pool;
         uint64_t high = 0;
         if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess &&
@@ -1204,6 +1211,12 @@ static uint64_t g_ingest_ring_keys = 16ull << 20;  // 128 MiB per ring slot
 static bool want_streamed_ingest(uint64_t n, double gamma, int device) {
     if (g_ingest_mode == 2 || n == 0) return false;
     if (g_ingest_mode == 1) return true;
+    // in-core: the keys, the two key lists (bucket regions of level 0 and 1 when level 0 exceeds the L2: ~1.1 n and
+    // ~0.5 n keys; plain: ~0.45 n and ~0.2 n) and the (a, collide) arenas (~3.1 gamma/1.7 bits per key each)
+    const bool bucketed = g_build_mode == 2 || (g_build_mode == 0 && (double)level_size(gamma, n) > bucket_fit_bits());
+    const double lists = bucketed ? 1.6 : 0.65;
+    const double need = 8.0 * (double)n * (1.0 + lists) + 2.0 * (double)n * gamma * 1.85 / 8.0 + 512e6;
+    if (need < 0.25 * (double)device_info(device).total_mem) return false;  // small next to the device: skip the query
     DeviceGuard guard(device);
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return false;
@@ -1213,11 +1226,6 @@ static bool want_streamed_ingest(uint64_t n, double gamma, int device) {
         cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
         cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess && reserved > used)
         free_b += reserved - used;  // cached by the stream-ordered pool: available to the build
-    // in-core: the keys, the two key lists (bucket regions of level 0 and 1 when level 0 exceeds the L2: ~1.1 n and
-    // ~0.5 n keys; plain: ~0.45 n and ~0.2 n) and the (a, collide) arenas (~3.1 gamma/1.7 bits per key each)
-    const bool bucketed = g_build_mode == 2 || (g_build_mode == 0 && (double)level_size(gamma, n) > bucket_fit_bits());
-    const double lists = bucketed ? 1.6 : 0.65;
-    const double need = 8.0 * (double)n * (1.0 + lists) + 2.0 * (double)n * gamma * 1.85 / 8.0 + 512e6;
     return need > 0.92 * (double)free_b;
 }
 

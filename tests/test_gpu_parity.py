@@ -605,10 +605,12 @@ def test_streamed_ingest_keeps_the_keys_out_of_device_memory(pkg, oracle):
     peak = {}
     for mode in (2, 1):
         pkg.lib().bphf_set_ingest_mode(mode, 100_000)
+        pkg.lib().bphf_set_profile(2)  # the in-core build only keeps the memory statistic when profiling
         try:
             m = pkg.Mphf.new_parallel(1.7, keys, None)
         finally:
             pkg.lib().bphf_set_ingest_mode(0, 0)
+            pkg.lib().bphf_set_profile(0)
         st = m.build_stats()
         assert st["streamed_ingest"] == (1 if mode == 1 else 0)
         peak[mode] = st["peak_device_bytes"]
