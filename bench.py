@@ -47,11 +47,15 @@ class ClockSampler:
     """SM clock and throttle reasons sampled DURING the timed region, in-process through NVML (an nvidia-smi
     subprocess per sample stalls the driver for tens of ms and would perturb a 3 ms step)."""
 
-    def __init__(self, torch_index, enabled=True, period=0.5):
-        # NVML queries take a driver-wide lock: at 10 Hz from every rank they stalled kernel launches of ALL ranks for
-        # milliseconds at a time (a 4-GPU sharded step was seen at 33 ms instead of 5 ms).  One sampling rank, 2 Hz.
+    def __init__(self, torch_index, enabled=True, period=0.05):
+        # Measured (tools/nvml_cost.py): the FIRST call of each NVML query initialises lazily and takes 2-3 ms with a
+        # driver-wide lock held -- issued from every rank at the start of the timed region that stalled the kernel
+        # launches of all ranks (a 4-GPU sharded step was seen at 33 ms instead of 5 ms; a single-GPU first step at
+        # 4-9 ms instead of 2.9).  Later calls cost microseconds and do not move the step time even every 2 ms.
+        # So: one sampling rank, the queries warmed up here (before the timed region), 20 Hz inside it.
         self.period = period
         self.samples = []
+        self._active = False
         self._stop = threading.Event()
         self._t = None
         self._h = None
@@ -81,6 +85,7 @@ class ClockSampler:
                 h = nv.nvmlDeviceGetHandleByIndex(idx)
             self._h = h
             self._max = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            self._sample()      # lazy initialisation of both queries happens here, outside the timed region
         except Exception:
             self._nv = None
 
@@ -92,7 +97,8 @@ class ClockSampler:
                 r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
             except Exception:
                 r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-            self.samples.append((sm, int(r)))
+            if self._active:
+                self.samples.append((sm, int(r)))
         except Exception:
             pass
 
@@ -101,17 +107,26 @@ class ClockSampler:
             self._sample()
             self._stop.wait(self.period)
 
-    def __enter__(self):
-        if self._nv is not None:
+    def start_thread(self):
+        """the sampling thread runs from here on (before the warm-up builds) and only RECORDS inside `with`:
+        nothing new -- no thread start, no first NVML call of a thread -- happens at the start of the timed region"""
+        if self._nv is not None and self._t is None and not os.environ.get("BENCH_NO_CLOCK_THREAD"):
             self._t = threading.Thread(target=self._run, daemon=True)
             self._t.start()
         return self
 
+    def __enter__(self):
+        self.start_thread()
+        self._active = True
+        return self
+
     def __exit__(self, *a):
+        if self._nv is not None:
+            self._sample()
+        self._active = False
         self._stop.set()
         if self._t is not None:
             self._t.join(timeout=2)
-            self._sample()
 
     def summary(self):
         if self._nv is None or not self.samples:
@@ -251,6 +266,10 @@ def main():
     # ---- warm-up ---------------------------------------------------------------------------------------------
     # clocks ramp from idle for a few hundred ms: spin untimed builds for ~1 s first, then the W warm-up steps
     L.bphf_set_profile(1)
+    # NVML is initialised (and its queries warmed up) here, BEFORE the warm-up builds: for a few milliseconds after
+    # nvmlInit the driver stalls kernel launches -- measured as a 4-11 ms first timed step when this sat right in
+    # front of the timed region (tools/nvml_cost.py)
+    clocks = ClockSampler(local_rank, enabled=(rank == 0)).start_thread()
     m = None
     t_spin = time.perf_counter()
     while time.perf_counter() - t_spin < 1.0:
@@ -265,21 +284,28 @@ def main():
     cascade_ms = 0.0
     merge0_ms = 0.0
     launches = 0
+    trace_steps = bool(os.environ.get("BENCH_TRACE_STEPS"))  # debugging aid: per-step wall times on stderr
     barrier()
-    with ClockSampler(local_rank, enabled=(rank == 0)) as clocks:
+    with clocks:
         e0.record(stream)
         t0 = time.perf_counter()
+        step_t = []
         for _ in range(args.steps):
+            if trace_steps:
+                step_t.append(time.perf_counter())
             m = build()
-            st = m.build_stats()
-            pass_ms[0] += st["pass_ms"][0]
-            pass_ms[1] += st["pass_ms"][1] if len(st["pass_ms"]) > 1 else 0.0
-            cascade_ms += st["cascade_ms"]
-            merge0_ms += st["merge_ms"][0] if st["merge_ms"] else 0.0
-            launches += st["kernel_launches"]
+            st = m.build_stats_raw()  # the struct, not the dict: no per-level Python loops inside the timed region
+            pass_ms[0] += st.pass_ms[0]
+            pass_ms[1] += st.pass_ms[1]
+            cascade_ms += st.cascade_ms
+            merge0_ms += st.merge_ms[0]
+            launches += st.kernel_launches
         e1.record(stream)
         barrier()
         wall = time.perf_counter() - t0
+        if trace_steps and rank == 0:
+            step_t.append(time.perf_counter())
+            sys.stderr.write("step wall us: " + " ".join("%.0f" % ((b - a) * 1e6) for a, b in zip(step_t[:-1], step_t[1:])) + "\n")
     dev_ms = e0.elapsed_time(e1)
     t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
     if world > 1:

@@ -12,6 +12,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <chrono>
 #include <vector>
 
 #include "build_kernels.cuh"
@@ -177,6 +178,49 @@ static cudaStream_t own_stream(int dev, bool copy) {
     return s;
 }
 
+// Memory that a handle keeps (arena words, ranks, lookup tables) is allocated AND freed on one process-wide stream per
+// device, whatever stream the build ran on and whichever thread frees the handle.  Measured reason: the stream-
+// ordered pool only recycles a block cheaply on the stream that freed it; handles allocated on a caller's stream and
+// freed on another (the freeing thread's) made every following build spend 2-90 ms in cudaMallocAsync, and the first
+// build after a device-wide synchronize 1-60 ms (tools/host_trace.py).
+static cudaStream_t g_handle_stream[MAX_DEVICES] = {};
+static std::mutex g_handle_stream_mutex;
+static cudaStream_t handle_stream(int dev) {
+    std::lock_guard<std::mutex> lock(g_handle_stream_mutex);
+    if (!g_handle_stream[dev]) CK(cudaStreamCreateWithFlags(&g_handle_stream[dev], cudaStreamNonBlocking));
+    return g_handle_stream[dev];
+}
+struct ThreadEvent {
+    cudaEvent_t e[MAX_DEVICES] = {};
+    ~ThreadEvent() {
+        for (auto x : e)
+            if (x) cudaEventDestroy(x);
+    }
+};
+static thread_local ThreadEvent g_order_event;
+// order stream `after` behind everything enqueued on `before` so far
+static void order_streams(int dev, cudaStream_t before, cudaStream_t after) {
+    if (before == after) return;
+    cudaEvent_t& e = g_order_event.e[dev];
+    if (!e) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CK(cudaEventRecord(e, before));
+    CK(cudaStreamWaitEvent(after, e, 0));
+}
+// handle-owned allocation, usable on stream `use` from here on
+template <typename T>
+static void handle_alloc(T** out, size_t bytes, int dev, cudaStream_t use) {
+    const cudaStream_t hs = handle_stream(dev);
+    CK(cudaMallocAsync((void**)out, bytes, hs));
+    order_streams(dev, hs, use);
+}
+// give handle-owned memory back once `last_use` has passed everything enqueued on it so far
+static void handle_free(void* p, int dev, cudaStream_t last_use) {
+    if (!p) return;
+    const cudaStream_t hs = handle_stream(dev);
+    order_streams(dev, last_use, hs);
+    CK(cudaFreeAsync(p, hs));
+}
+
 // ------------------------------------------------------------------------------------------------
 // the handle
 // ------------------------------------------------------------------------------------------------
@@ -235,7 +279,7 @@ static void upload_level_table(bphf_mphf* m, cudaStream_t s) {
         q[l].bit_off = m->lv[l].word_off * 64;
         q[l].sp0 = m->lv[l].sp0_query;
     }
-    CK(cudaMallocAsync((void**)&m->d_lv, q.size() * sizeof(QLevel), s));
+    handle_alloc(&m->d_lv, q.size() * sizeof(QLevel), m->device, s);
     CK(cudaMemcpyAsync(m->d_lv, q.data(), q.size() * sizeof(QLevel), cudaMemcpyHostToDevice, s));
     // packed lookup structure: needs the ranks (already enqueued on s) and 32-bit slot indices
     bool can_pack = m->n_levels > 0;
@@ -252,9 +296,9 @@ static void upload_level_table(bphf_mphf* m, cudaStream_t s) {
             off += qp[l].n_gran;
         }
         m->total_gran = off;
-        CK(cudaMallocAsync((void**)&m->d_lvp, qp.size() * sizeof(QLevelP), s));
+        handle_alloc(&m->d_lvp, qp.size() * sizeof(QLevelP), m->device, s);
         CK(cudaMemcpyAsync(m->d_lvp, qp.data(), qp.size() * sizeof(QLevelP), cudaMemcpyHostToDevice, s));
-        CK(cudaMallocAsync((void**)&m->d_packed, std::max<uint64_t>(off, 1) * sizeof(uint4), s));
+        handle_alloc(&m->d_packed, std::max<uint64_t>(off, 1) * sizeof(uint4), m->device, s);
         const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((off + 255) / 256, (uint64_t)g_dev[m->device].sm_count * 16));
         set_base_rank_kernel<<<1, 128, 0, s>>>(m->d_lvp, m->d_lv, m->n_levels, m->d_ranks);
         pack_query_kernel<<<grid, 256, 0, s>>>(m->d_lvp, m->d_lv, m->n_levels, m->d_words, m->d_ranks, off, m->d_packed);
@@ -439,7 +483,12 @@ struct Builder {
         // scratch goes back to the pool (stream ordered); the handle took ownership of what it keeps
         if (d_state) cudaFreeAsync(d_state, s);
         if (d_keys_owned) cudaFreeAsync(d_keys_owned, s);
-        if (d_words && !comm) cudaFreeAsync(d_words, s);
+        if (d_words && !comm) {
+            try {
+                handle_free(d_words, device, s);
+            } catch (...) {
+            }
+        }
         if (d_coll && !comm) cudaFreeAsync(d_coll, s);
         if (d_blockpop) cudaFreeAsync(d_blockpop, s);
         if (d_cursors) cudaFreeAsync(d_cursors, s);
@@ -496,7 +545,7 @@ struct Builder {
             d_words = comm->dev.words[comm->rank];
             d_coll = comm->dev.coll[comm->rank];
         } else {
-            CK(cudaMallocAsync((void**)&d_words, phys_words * 8, s));
+            handle_alloc(&d_words, phys_words * 8, device, s);  // the handle keeps the arena
             CK(cudaMallocAsync((void**)&d_coll, phys_words * 8, s));
         }
         CK(cudaMallocAsync((void**)&d_blockpop, (phys_words / 8) * 4, s));
@@ -518,7 +567,7 @@ struct Builder {
         const uint64_t new_phys = new_cap + TAIL_RESERVE_WORDS;
         uint64_t *nw = nullptr, *nc = nullptr;
         uint32_t* nb = nullptr;
-        CK(cudaMallocAsync((void**)&nw, new_phys * 8, s));
+        handle_alloc(&nw, new_phys * 8, device, s);
         CK(cudaMallocAsync((void**)&nc, new_phys * 8, s));
         CK(cudaMallocAsync((void**)&nb, (new_phys / 8) * 4, s));
         CK(cudaMemsetAsync(nw, 0, new_phys * 8, s));
@@ -527,7 +576,7 @@ struct Builder {
         CK(cudaMemcpyAsync(nw, d_words, used * 8, cudaMemcpyDeviceToDevice, s));
         CK(cudaMemcpyAsync(nc, d_coll, used * 8, cudaMemcpyDeviceToDevice, s));
         CK(cudaMemcpyAsync(nb, d_blockpop, (used / 8) * 4, cudaMemcpyDeviceToDevice, s));
-        CK(cudaFreeAsync(d_words, s));
+        handle_free(d_words, device, s);
         CK(cudaFreeAsync(d_coll, s));
         CK(cudaFreeAsync(d_blockpop, s));
         d_words = nw;
@@ -779,6 +828,28 @@ struct Builder {
 
 enum { BUILD_RETRY_PLAIN = 1000, BUILD_RETRY_INCORE = 1001 };
 
+// BPHF_HOST_TRACE=1: host-side timeline of every build on stderr (microseconds since the call started)
+struct HostTrace {
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    char line[512];
+    size_t len = 0;
+    HostTrace() : t0(std::chrono::steady_clock::now()) {
+        static const bool enabled = getenv("BPHF_HOST_TRACE") != nullptr;
+        on = enabled;
+        line[0] = 0;
+    }
+    void mark(const char* what) {
+        if (!on) return;
+        const double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+        len += (size_t)snprintf(line + len, len < sizeof line ? sizeof line - len : 0, " %s=%.0f", what, us);
+        if (len >= sizeof line) len = sizeof line - 1;
+    }
+    ~HostTrace() {
+        if (on) fprintf(stderr, "[bphf host trace, us]%s\n", line);
+    }
+};
+
 // device ring of a streamed ingest; released on every exit path
 struct IngestRing {
     static constexpr int SLOTS = 3;
@@ -799,6 +870,7 @@ struct IngestRing {
 static int build_once(const uint64_t* keys, uint64_t n, double gamma, int has_seed, uint64_t seed, int device,
                       int keys_mem, void* stream, bool bucket_enable, uint64_t min_keys, uint32_t rebuilds, bphf_mphf** out,
                       bphf_comm* comm = nullptr, uint64_t n_global_arg = 0, const ChunkSpec* chunk = nullptr) {
+    HostTrace trace;
     const DeviceInfo& info = device_info(device);
     DeviceGuard guard(device);
     cudaStream_t s = stream ? (cudaStream_t)stream : own_stream(device, false);
@@ -824,7 +896,9 @@ static int build_once(const uint64_t* keys, uint64_t n, double gamma, int has_se
         if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrUsedMemHigh, &zero);
     }
 
+    trace.mark("events");
     Plan plan = make_plan(n_global, gamma, b.slots(), bucket_enable, min_keys, shard_frac, chunk);
+    trace.mark("plan");
     b.maybe_big = plan.maybe_big;
     uint32_t gather_level = NO_LEVEL;
     if (comm) {
@@ -886,6 +960,7 @@ static int build_once(const uint64_t* keys, uint64_t n, double gamma, int has_se
         if (plan.list_cap[i]) CK(cudaMallocAsync((void**)&b.d_buf[i], plan.list_cap[i] * 8, s));
     }
 
+    trace.mark("alloc");
     BuildState& st = b.hst;
     st.kc = chunk ? chunk->kc : make_key_cfg(BPHF_KIND_U64, 8);
     st.status = ST_RUNNING;
@@ -921,6 +996,7 @@ static int build_once(const uint64_t* keys, uint64_t n, double gamma, int has_se
         hyb.on = false;
     }
     b.upload_state();
+    trace.mark("prologue");
     const bool level0_bucketed = st.lv[0].b_range != 0;
     const uint32_t count0 = st.lv[0].b_count;
 
@@ -1058,9 +1134,11 @@ static int build_once(const uint64_t* keys, uint64_t n, double gamma, int has_se
     if (lps.back().maybe_bucket)
         b.launch_scatter((uint32_t)lps.size(), lps.back().range_max, lps.back().count_max, 1);
 
+    trace.mark("enqueued");
     for (;;) {
         b.launch_tail();
         b.download_state();
+        trace.mark("state");
         if (st.status == ST_DONE) break;
         if (st.status == ST_BUCKET_OVERFLOW) return BUILD_RETRY_PLAIN;
         if (st.status == ST_ERR_MAX_ITERS) {
@@ -1131,7 +1209,7 @@ static int build_once(const uint64_t* keys, uint64_t n, double gamma, int has_se
     m->words_used = st.words_used;
     m->lv.assign(st.lv, st.lv + st.n_levels);
     const uint64_t n_blocks = st.words_used / 8;
-    CK(cudaMallocAsync((void**)&m->d_ranks, std::max<uint64_t>(n_blocks, 1) * 8, s));
+    handle_alloc(&m->d_ranks, std::max<uint64_t>(n_blocks, 1) * 8, device, s);
     {
         const uint64_t n_chunks = (n_blocks + SCAN_CHUNK - 1) / SCAN_CHUNK;
         uint64_t* d_sums = nullptr;
@@ -1149,7 +1227,7 @@ static int build_once(const uint64_t* keys, uint64_t n, double gamma, int has_se
     }
     if (comm) {
         // the arena belongs to the comm (peers write into it during the next build): the handle gets a copy
-        CK(cudaMallocAsync((void**)&m->d_words, std::max<uint64_t>(st.words_used, 8) * 8, s));
+        handle_alloc(&m->d_words, std::max<uint64_t>(st.words_used, 8) * 8, device, s);
         CK(cudaMemcpyAsync(m->d_words, b.d_words, st.words_used * 8, cudaMemcpyDeviceToDevice, s));
     } else {
         m->d_words = b.d_words;  // the handle keeps the arena (padded, <= planned capacity)
@@ -1157,7 +1235,9 @@ static int build_once(const uint64_t* keys, uint64_t n, double gamma, int has_se
     }
     upload_level_table(m.get(), s);  // level tables + packed lookup structure
     CK(cudaEventRecord(b.ev_end, s));
+    trace.mark("epilogue");
     CK(cudaStreamSynchronize(s));
+    trace.mark("synced");
     b.syncs++;
 
     // ---- statistics
@@ -1197,6 +1277,7 @@ static int build_once(const uint64_t* keys, uint64_t n, double gamma, int has_se
             cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemHigh, &high) == cudaSuccess)
             bs.peak_device_bytes = high;
     }
+    trace.mark("stats");
     *out = m.release();
     return BPHF_OK;
 }
@@ -1388,8 +1469,8 @@ BPHF_API int bphf_build_chunked_u64(const uint64_t* const* chunks, const uint64_
         // keys_remaining == 0 on entry: the loop breaks before the first level (src/lib.rs:580-582) -> no levels
         std::unique_ptr<bphf_mphf> m(new bphf_mphf());
         m->device = device;
-        CK(cudaMallocAsync((void**)&m->d_words, 64, s));
-        CK(cudaMallocAsync((void**)&m->d_ranks, 8, s));
+        handle_alloc(&m->d_words, 64, device, s);
+        handle_alloc(&m->d_ranks, 8, device, s);
         upload_level_table(m.get(), s);
         *out = m.release();
         return BPHF_OK;
@@ -1815,8 +1896,8 @@ static int from_levels_impl(uint32_t n_levels, const uint64_t* bits, const uint6
         if (d.n_words && (!words[l] || !ranks[l])) return fail(BPHF_ERR_ARG, "null level buffer");
     }
     m->words_used = off;
-    CK(cudaMallocAsync((void**)&m->d_words, std::max<uint64_t>(off, 8) * 8, s));
-    CK(cudaMallocAsync((void**)&m->d_ranks, std::max<uint64_t>(off / 8, 1) * 8, s));
+    handle_alloc(&m->d_words, std::max<uint64_t>(off, 8) * 8, device, s);
+    handle_alloc(&m->d_ranks, std::max<uint64_t>(off / 8, 1) * 8, device, s);
     CK(cudaMemsetAsync(m->d_words, 0, std::max<uint64_t>(off, 8) * 8, s));
     uint64_t n_keys = 0;
     for (uint32_t l = 0; l < n_levels; l++) {
@@ -1840,7 +1921,7 @@ BPHF_API void bphf_free(bphf_mphf* m) {
     if (cudaSetDevice(m->device) == cudaSuccess) {
         cudaStream_t s = nullptr;
         try {
-            s = own_stream(m->device, false);
+            s = handle_stream(m->device);
         } catch (...) {
         }
         if (m->d_words) cudaFreeAsync(m->d_words, s);

@@ -258,9 +258,14 @@ class Mphf:
         _check(N.lib().bphf_total_dims(self._h, C.byref(w), C.byref(r), C.byref(k)))
         return int(w.value), int(r.value), int(k.value)
 
-    def build_stats(self):
+    def build_stats_raw(self):
+        """the bphf_build_stats struct itself (cheap: for callers that read a few fields inside a timed loop)"""
         st = N.BuildStats()
         _check(N.lib().bphf_get_build_stats(self._h, C.byref(st)))
+        return st
+
+    def build_stats(self):
+        st = self.build_stats_raw()
         nl = int(st.n_levels)
         return {
             "n_levels": nl, "tail_level": int(st.tail_level),
