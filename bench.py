@@ -271,9 +271,16 @@ def main():
     # front of the timed region (tools/nvml_cost.py)
     clocks = ClockSampler(local_rank, enabled=(rank == 0)).start_thread()
     m = None
+    # (a sharded build is a collective: every rank must run the same number of them, so the ranks agree on when the
+    # second is over -- a per-rank clock check let one rank leave the loop a build earlier than its peers)
     t_spin = time.perf_counter()
-    while time.perf_counter() - t_spin < 1.0:
+    while True:
         m = build()
+        over = torch.tensor([1 if time.perf_counter() - t_spin >= 1.0 else 0], dtype=torch.int32, device=dev)
+        if world > 1:
+            dist.all_reduce(over, op=dist.ReduceOp.MAX)
+        if int(over.item()):
+            break
     for _ in range(max(args.warmup, 3)):
         m = build()
     stats = m.build_stats()
