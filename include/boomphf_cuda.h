@@ -177,6 +177,9 @@ BPHF_API int bphf_total_dims(const bphf_mphf *m, uint64_t *total_words, uint64_t
 /* upload a deserialised Mphf (host arrays) to `device` */
 BPHF_API int bphf_from_levels(uint32_t n_levels, const uint64_t *bits, const uint64_t *const *words,
                               const uint64_t *const *ranks, int device, bphf_mphf **out);
+/* Releases the handle and its device memory (stream-ordered on a library-owned stream).  Lookups that were launched
+ * on this handle with a caller-supplied stream and device buffers return before they finish: they must have
+ * completed (or that stream must have been synchronised) before the handle is freed. */
 BPHF_API void bphf_free(bphf_mphf *m);
 
 /* ---- lookup: Mphf::hash / try_hash over a batch ----------------------------------------

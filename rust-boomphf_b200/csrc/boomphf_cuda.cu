@@ -389,7 +389,7 @@ static Plan make_plan(uint64_t n, double gamma, uint32_t slots, bool bucket_enab
         lp.k_lo = k_lo;
         const bool prev_maybe = level == 0 || p.lv[level - 1].maybe_bucket;
         const bool prev_surely = level == 0 || p.lv[level - 1].surely_bucket;
-        BucketGeom gu, gl;
+        BucketGeom gu{}, gl{};
         const bool bu = bucket_enable && bucket_geometry(bits_up, k_up, slots, min_keys, frac, &gu);
         const bool bl = bucket_enable && bucket_geometry(bits_lo, k_lo, slots, min_keys, frac, &gl);
         lp.maybe_bucket = prev_maybe && (bu || bl);

@@ -108,6 +108,7 @@ class Mphf:
         self._h = C.c_void_p(handle)
         self.device = device
         self.rust_type = rust_type  # stream keys only: the T of Mphf<T>, used to encode single items
+        self._async_streams = []    # torch streams with possibly unfinished device-side lookups on this handle
 
     def __del__(self):
         try:
@@ -117,6 +118,13 @@ class Mphf:
 
     def close(self):
         if getattr(self, "_h", None):
+            # bphf_free must not overtake lookups still running on a caller's stream (include/boomphf_cuda.h)
+            for st in getattr(self, "_async_streams", ()):
+                try:
+                    st.synchronize()
+                except Exception:
+                    pass
+            self._async_streams = []
             N.lib().bphf_free(self._h)
             self._h = None
 
@@ -303,6 +311,8 @@ class Mphf:
             if stream is None:
                 stream = torch.cuda.current_stream(keep.device)
             _check(fn(self._h, ptr, n, C.c_void_p(out.data_ptr()), mem, _stream_ptr(stream)))
+            if hasattr(stream, "synchronize") and not any(st is stream or st == stream for st in self._async_streams):
+                self._async_streams.append(stream)
             return out
         if out is None:
             out = np.empty(n, dtype=np.uint64)
