@@ -145,6 +145,24 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self._max, "reasons": sorted(seen), "samples": len(sm)}
 
 
+def collective_spin(build, seconds, world, device):
+    """Call build() back to back for about `seconds`; EVERY rank makes the same number of calls (a sharded build is a
+    collective: a per-rank clock check would let one rank leave a build earlier than its peers, who then wait at a
+    device barrier for a shard that never comes).  Returns (last result, number of calls)."""
+    import torch
+    t0 = time.perf_counter()
+    m, calls = None, 0
+    while True:
+        m = build()
+        calls += 1
+        over = torch.tensor([1 if time.perf_counter() - t0 >= seconds else 0], dtype=torch.int32, device=device)
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(over, op=dist.ReduceOp.MAX)
+        if int(over.item()):
+            return m, calls
+
+
 def algorithmic_bytes(stats, world=1):
     """B_l = 16k + 8c + 41W per level (key read in mark and in filter, redo write, zeroing
     of a and collide, finalize read a/read collide/write a, ranks).  Returns total and per-kernel splits, PER GPU:
@@ -273,14 +291,7 @@ def main():
     m = None
     # (a sharded build is a collective: every rank must run the same number of them, so the ranks agree on when the
     # second is over -- a per-rank clock check let one rank leave the loop a build earlier than its peers)
-    t_spin = time.perf_counter()
-    while True:
-        m = build()
-        over = torch.tensor([1 if time.perf_counter() - t_spin >= 1.0 else 0], dtype=torch.int32, device=dev)
-        if world > 1:
-            dist.all_reduce(over, op=dist.ReduceOp.MAX)
-        if int(over.item()):
-            break
+    m, _ = collective_spin(build, 1.0, world, dev)
     for _ in range(max(args.warmup, 3)):
         m = build()
     stats = m.build_stats()

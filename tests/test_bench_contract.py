@@ -54,3 +54,40 @@ def test_bench_line_on_the_gpu_has_every_contract_key():
     assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(line["roofline"])
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["bit_exact_vs_gpu"] is True
     assert line["lookup"]["permutation_ok"] is True
+
+
+# ---- the warm-up second of a multi-rank run is a collective decision (gloo, world size 2, CPU) -----------------
+def _spin_worker(rank, world, port, q):
+    try:
+        import time
+        import torch.distributed as dist
+        os.environ["MASTER_ADDR"] = "127.0.0.1"
+        os.environ["MASTER_PORT"] = str(port)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        sys.path.insert(0, ROOT)
+        import bench
+        if rank == 0:
+            time.sleep(0.25)  # rank 0 starts late (it is the one that initialises NVML): its clock runs behind
+        _, calls = bench.collective_spin(lambda: time.sleep(0.01 * (1 + rank)), 0.4, world, "cpu")
+        q.put((rank, calls))
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception as e:  # noqa: BLE001
+        q.put((rank, repr(e)))
+
+
+def test_ranks_agree_on_the_number_of_warmup_builds():
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_spin_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert isinstance(got[0], int) and got[0] == got[1] and got[0] >= 2, got
