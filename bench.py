@@ -150,16 +150,21 @@ def collective_spin(build, seconds, world, device):
     collective: a per-rank clock check would let one rank leave a build earlier than its peers, who then wait at a
     device barrier for a shard that never comes).  Returns (last result, number of calls)."""
     import torch
+    # No torch allocation inside the loop: a cudaMalloc by torch's allocator between builds makes the first build after
+    # the next device-wide synchronize spend 20-480 ms in the stream-ordered pool (tools/pool_probe.py).
+    over = torch.zeros(1, dtype=torch.int32, device=device) if world > 1 else None
     t0 = time.perf_counter()
     m, calls = None, 0
     while True:
         m = build()
         calls += 1
-        over = torch.tensor([1 if time.perf_counter() - t0 >= seconds else 0], dtype=torch.int32, device=device)
+        done = time.perf_counter() - t0 >= seconds
         if world > 1:
             import torch.distributed as dist
+            over.fill_(1 if done else 0)
             dist.all_reduce(over, op=dist.ReduceOp.MAX)
-        if int(over.item()):
+            done = bool(int(over.item()))
+        if done:
             return m, calls
 
 
@@ -223,7 +228,9 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    # 200 steps = 0.6 s of timed builds: long enough that one host-side hiccup (the first build after the device-wide
+    # synchronize in front of the timed region occasionally waits ~10 ms for the memory pool) moves the mean by < 2 %
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--keys", type=int, default=100_000_000, help="keys per GPU (BASELINE configs[1]: 1e8)")

@@ -452,6 +452,23 @@ struct EventPair {
 
 constexpr size_t MAX_DYN_SMEM = 200 * 1024;
 
+// The two key-list buffers of a build (the only large scratch) are parked per thread and device between builds instead
+// of going back to the stream-ordered pool: measured (tools/pool_probe.py), the first LARGE cudaMallocAsync after a
+// device-wide synchronize takes 2 ms to 0.5 s (small and medium blocks come back in microseconds), i.e. a caller that
+// synchronises the device between two builds paid for it in the next one.  A parked buffer is idle: the build that
+// used it has returned, and builds end with a synchronisation of their stream.  At most SCRATCH_CACHE_BYTES per buffer.
+constexpr uint64_t SCRATCH_CACHE_BYTES = 2ull << 30;
+struct ScratchCache {
+    uint64_t* buf[MAX_DEVICES][2] = {};
+    uint64_t cap[MAX_DEVICES][2] = {};  // in keys
+    ~ScratchCache() {
+        for (int d = 0; d < MAX_DEVICES; d++)
+            for (int i = 0; i < 2; i++)
+                if (buf[d][i] && g_handle_stream[d]) cudaFreeAsync(buf[d][i], g_handle_stream[d]);
+    }
+};
+static thread_local ScratchCache g_scratch;
+
 struct Builder {
     int device;
     const DeviceInfo& info;
@@ -466,9 +483,11 @@ struct Builder {
     uint32_t* d_blockpop = nullptr;
     uint32_t* d_cursors = nullptr;  // [2][MAX_BUCKETS_ALLOC]
     uint64_t* d_buf[2] = {nullptr, nullptr};   // key lists / bucket key regions, level l in d_buf[l & 1]
+    uint64_t buf_cap[2] = {0, 0};               // allocated size of d_buf[] in keys (>= the planned list_cap)
     uint64_t phys_words = 0;  // words_cap + TAIL_RESERVE_WORDS
     uint64_t n = 0;
     bool maybe_big = false;
+    bool stream_idle = false;  // set once the build stream has been synchronised after the last use of the list buffers
     bool stream_keys = false;  // BPHF_KIND_STREAM: key lists hold key indices, StreamCfg kernel instantiations
     uint32_t launches = 0, syncs = 0;
     bphf_comm* comm = nullptr;  // sharded build: the arenas live in the comm's peer-visible allocation
@@ -493,7 +512,10 @@ struct Builder {
         if (d_blockpop) cudaFreeAsync(d_blockpop, s);
         if (d_cursors) cudaFreeAsync(d_cursors, s);
         for (int i = 0; i < 2; i++) {
-            if (d_buf[i]) cudaFreeAsync(d_buf[i], s);
+            try {
+                release_list(i);
+            } catch (...) {
+            }
         }
         for (auto& e : events) {
             if (e.a) cudaEventDestroy(e.a);
@@ -589,10 +611,43 @@ struct Builder {
     // holds nothing live at that point (level-2's keys are dead), so it is simply replaced.
     void grow_list(int which, uint64_t need) {
         const uint64_t cap = need + need / 8 + 1024;
-        if (d_buf[which]) CK(cudaFreeAsync(d_buf[which], s));
+        if (d_buf[which]) handle_free(d_buf[which], device, s);
         d_buf[which] = nullptr;
-        CK(cudaMallocAsync((void**)&d_buf[which], cap * 8, s));
+        buf_cap[which] = 0;
+        acquire_list(which, cap);
         hst.list_cap[which] = cap;
+    }
+    // list buffer `which` with room for `cap` keys: the parked one of this thread when it is large enough
+    void acquire_list(int which, uint64_t cap) {
+        uint64_t*& parked = g_scratch.buf[device][which];
+        uint64_t& parked_cap = g_scratch.cap[device][which];
+        if (parked && parked_cap >= cap) {
+            d_buf[which] = parked;
+            buf_cap[which] = parked_cap;
+            parked = nullptr;
+            parked_cap = 0;
+            return;
+        }
+        if (parked) {  // too small: give it back for good
+            handle_free(parked, device, s);
+            parked = nullptr;
+            parked_cap = 0;
+        }
+        handle_alloc(&d_buf[which], cap * 8, device, s);
+        buf_cap[which] = cap;
+    }
+    // end of the build (its stream is synchronised, or the build failed and the buffer is ordered behind the stream)
+    void release_list(int which) {
+        if (!d_buf[which]) return;
+        uint64_t*& parked = g_scratch.buf[device][which];
+        if (!parked && buf_cap[which] * 8 <= SCRATCH_CACHE_BYTES && stream_idle) {
+            parked = d_buf[which];
+            g_scratch.cap[device][which] = buf_cap[which];
+        } else {
+            handle_free(d_buf[which], device, s);
+        }
+        d_buf[which] = nullptr;
+        buf_cap[which] = 0;
     }
 
     const uint32_t* list_cursor(uint32_t level) const { return d_cursors + (size_t)(level & 1) * MAX_BUCKETS_ALLOC * CURSOR_STRIDE; }
@@ -955,9 +1010,11 @@ static int build_once(const uint64_t* keys, uint64_t n, double gamma, int has_se
     }
     if (ingest && plan.lv.size() < 2) return BUILD_RETRY_INCORE;  // level 1 may already belong to the tail kernel
     CK(cudaMallocAsync((void**)&b.d_state, sizeof(BuildState), s));
+    trace.mark("a_state");
     b.alloc_arena(plan.words_cap);
+    trace.mark("a_arena");
     for (int i = 0; i < 2; i++) {
-        if (plan.list_cap[i]) CK(cudaMallocAsync((void**)&b.d_buf[i], plan.list_cap[i] * 8, s));
+        if (plan.list_cap[i]) b.acquire_list(i, plan.list_cap[i]);
     }
 
     trace.mark("alloc");
@@ -1239,6 +1296,7 @@ static int build_once(const uint64_t* keys, uint64_t n, double gamma, int has_se
     CK(cudaStreamSynchronize(s));
     trace.mark("synced");
     b.syncs++;
+    b.stream_idle = true;  // nothing of this build is in flight any more: its list buffers may be parked
 
     // ---- statistics
     bphf_build_stats& bs = m->stats;
