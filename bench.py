@@ -197,7 +197,9 @@ def run_reference(args, rank, world):
         return
     orc = ge.load_oracle()
     orc.build_lib()
-    n = args.ref_keys
+    # bounded sample: the full 1e8-key config per step while K steps of it fit ~2 minutes of host time (K <= 50 at the
+    # ~46 Mkeys/s of a 16-core box), fewer keys per step beyond that; --ref-keys overrides
+    n = args.ref_keys if args.ref_keys else int(min(100_000_000, max(2_000_000, 5_000_000_000 // max(args.steps, 1))))
     keys = orc.keygen(n, seed=1, kind=0)
     threads = orc.max_threads()
     for _ in range(args.warmup):
@@ -234,7 +236,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--keys", type=int, default=100_000_000, help="keys per GPU (BASELINE configs[1]: 1e8)")
-    ap.add_argument("--ref-keys", type=int, default=100_000_000, help="keys per step of the CPU reference arm")
+    ap.add_argument("--ref-keys", type=int, default=0,
+                    help="keys per step of the CPU reference arm (0: 1e8, scaled down when --steps is large)")
     ap.add_argument("--cpu-baseline-keys", type=int, default=100_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
