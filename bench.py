@@ -25,8 +25,8 @@ sys.path.insert(0, ROOT)
 import __graft_entry__ as ge  # noqa: E402
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
-# (profiles/r01b_summary.md; n = 1e8, gamma = 1.7, one GPU -- only quoted for that workload)
-NCU_TRAFFIC_1E8 = {"mark_list_kernel": 0.8474e9 + 9.5e6, "cascade_kernel": 1.458e9 + 641.9e6}
+# (profiles/r01c_summary.md; n = 1e8, gamma = 1.7, one GPU -- only quoted for that workload)
+NCU_TRAFFIC_1E8 = {"mark_list_kernel": 0.8481e9 + 9.275e6, "cascade_kernel": 1.455e9 + 638.6e6}
 
 METRIC = "mphf_build_throughput"
 UNIT = "Mkeys/s"
@@ -433,7 +433,7 @@ def main():
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
         "traffic": next((v for k, v in NCU_TRAFFIC_1E8.items() if k_name.startswith(k)), None)
         if (world == 1 and n == 100_000_000) else None,
-        "traffic_source": "ncu --set full, profiles/r01b_summary.md",
+        "traffic_source": "ncu --set full, profiles/r01c_summary.md",
         "peak_source": peak_src, "kernel_ms": k_ms, "algorithmic_bytes_per_launch": k_bytes,
         "kernels": [{"kernel": c[0], "ms": c[1], "algorithmic_bytes": c[2],
                      "achieved": (c[2] / (c[1] * 1e-3) / 1e9) if c[1] > 0 else None} for c in cands],
