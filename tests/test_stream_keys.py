@@ -193,3 +193,13 @@ def test_golden_stream_fingerprints(oracle, K, entry):
     m = oracle.OracleMphf.new_stream(entry["gamma"], s, parallel=True)
     assert [l[0] for l in m.levels()] == entry["bits"] and oracle.fingerprint(m.levels()) == entry["sha256"]
     assert [int(v) for v in m.hash_batch_stream(s)[:4]] == entry["hash_first"]
+
+
+@settings(max_examples=200, deadline=None)
+@given(st.lists(st.binary(max_size=80), min_size=0, max_size=6), st.integers(min_value=0, max_value=70))
+def test_oracle_stream_hash_on_arbitrary_write_sequences(oracle, writes, it):
+    """any sequence of Hasher::write calls (empty writes included): C oracle == the Python restatement above"""
+    ends = np.cumsum([len(w) for w in writes]).astype(np.uint64) if writes else np.zeros(0, np.uint64)
+    data = np.frombuffer(b"".join(writes), dtype=np.uint8) if writes else np.zeros(0, np.uint8)
+    s = oracle.Stream(data, ends, [0, len(writes)])
+    assert oracle.hash_stream_with_seed(it, s) == py_stream_hash(it, writes)
