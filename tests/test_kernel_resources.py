@@ -1,0 +1,61 @@
+"""Resource-usage guard on the compiled sm_100a kernels (cuobjdump on the in-tree library, no GPU needed): the u64
+hot-path kernels must keep the register counts their occupancy was tuned for, without spills, and the stream-key
+variants must be SEPARATE kernels -- folding the stream hash into the u64 kernels as a runtime branch once doubled
+their registers (cascade 64 -> 128, pass 40 -> 80)."""
+import re
+import shutil
+import subprocess
+
+import pytest
+
+
+@pytest.fixture(scope="module")
+def usage(pkg):
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    out = subprocess.run([exe, "--dump-resource-usage", pkg.LIB_PATH], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-500:]
+    res, name = {}, None
+    for line in out.stdout.splitlines():
+        m = re.search(r"Function (\S+):", line)
+        if m:
+            name = m.group(1)
+            continue
+        m = re.search(r"REG:(\d+) STACK:(\d+) SHARED:(\d+)", line)
+        if m and name:
+            res[name] = tuple(int(x) for x in m.groups())
+            name = None
+    assert res, "no kernels found in the library"
+    return res
+
+
+def _one(usage, *parts):
+    hits = [(k, v) for k, v in usage.items() if all(p in k for p in parts)]
+    assert len(hits) == 1, (parts, [k for k, _ in hits])
+    return hits[0][1]
+
+
+@pytest.mark.parametrize("parts,max_reg", [
+    (("mark_list_kernelILb0E", "KeyCfg"), 40),     # level 0: 6 CTAs of 256 threads per SM
+    (("pass_kernelILb0E", "KeyCfg"), 40),
+    (("cascade_kernelILb0E",), 64),                # 4 CTAs per SM (32 KB TMA ring each)
+    (("query_sync_kernel",), 64),                  # 8 CTAs of 128 threads per SM
+    (("tail_kernel", "KeyCfg"), 64),
+])
+def test_hot_kernels_keep_their_registers_and_do_not_spill(usage, parts, max_reg):
+    reg, stack, _ = _one(usage, *parts)
+    assert reg <= max_reg, (parts, reg)
+    assert stack == 0, (parts, "spills / stack frame", stack)
+
+
+def test_stream_key_variants_are_separate_kernels(usage):
+    for parts in (("mark_list_kernel", "StreamCfg"), ("pass_kernel", "StreamCfg"), ("tail_kernel", "StreamCfg")):
+        _one(usage, *parts)
+    assert sum(1 for k in usage if "query_kernel" in k and "StreamCfg" in k) == 2
+    assert not any("cascade_kernel" in k and "StreamCfg" in k for k in usage)
+
+
+def test_ring_kernels_fit_four_ctas_per_sm(usage):
+    # the TMA key ring: 2 stages x 2048 keys x 8 B (+ barriers) of static shared memory, 4 CTAs <= 227 KB
+    for parts in (("cascade_kernelILb0E",), ("pass_kernelILb0E", "KeyCfg")):
+        _, _, shared = _one(usage, *parts)
+        assert 32 * 1024 <= shared <= 36 * 1024
