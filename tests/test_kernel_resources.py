@@ -59,3 +59,24 @@ def test_ring_kernels_fit_four_ctas_per_sm(usage):
     for parts in (("cascade_kernelILb0E",), ("pass_kernelILb0E", "KeyCfg")):
         _, _, shared = _one(usage, *parts)
         assert 32 * 1024 <= shared <= 36 * 1024
+
+
+def _sass(pkg, usage, *parts):
+    name = [k for k in usage if all(p in k for p in parts)]
+    assert len(name) == 1, (parts, name)
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    out = subprocess.run([exe, "-sass", "-fun", name[0], pkg.LIB_PATH], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-500:]
+    return out.stdout
+
+
+def test_level_kernels_use_the_bulk_copy_engine_and_fire_and_forget_reductions(pkg, usage):
+    """what the design claims, read off the machine code: key tiles arrive through TMA bulk copies completing on an
+    mbarrier (UBLKCP + SYNCS), the occupancy bit is a returning atomic OR, the collide bit a non-returning reduction"""
+    sass = _sass(pkg, usage, "cascade_kernelILb0E")
+    for mnemonic in ("UBLKCP", "SYNCS.ARRIVE.TRANS64", "SYNCS.PHASECHK", "ATOMG.E.OR", "REDG.E.OR"):
+        assert mnemonic in sass, mnemonic
+    mark = _sass(pkg, usage, "mark_list_kernelILb0E", "KeyCfg")
+    assert mark.count("ATOMG.E.OR") >= 8 and mark.count("REDG.E.OR") >= 8     # 8 keys per thread, issued back to back
+    look = _sass(pkg, usage, "query_sync_kernel")
+    assert "LDG.E.128" in look                                                # one 16-byte granule per probe
