@@ -241,11 +241,6 @@ BPHF_API int bphf_set_build_mode(int mode, uint64_t bucket_min_keys);
  * Mphf::from_chunked_iterator[_parallel] (src/lib.rs:103-111: "the iterator is re-created once per level"): here the
  * source is read twice in total, not once per level. */
 BPHF_API int bphf_set_ingest_mode(int mode, uint64_t ring_keys);
-/* hybrid level 0 of build mode 0 (measurement / tests; identical results): `frac` of the level's bit range is built
- * in shared memory, the rest with L2 atomics, in the same pass; levels below min_bits bits stay all-atomic.
- * Off by default (frac = 0: it measured no faster than the all-atomic level 0); out-of-range
- * values restore the defaults (off, 2^26). */
-BPHF_API int bphf_set_hybrid(double frac, uint64_t min_bits);
 /* lookup strategy (measurement only; identical results): 0 (default) = level-synchronous kernel over the packed
  * lookup structure, 1 = one thread per key over the same structure */
 BPHF_API int bphf_set_query_mode(int mode);

@@ -68,11 +68,6 @@ struct DeviceInfo {
 static DeviceInfo g_dev[MAX_DEVICES];
 static std::mutex g_dev_mutex;
 static int g_profile = 0;
-// share of level 0's bit range built in shared memory (0: off).  OFF by default: measured at 1e8 keys the hybrid
-// entry kernel + bucket mark take 1.04-1.19 ms (frac 0.3-0.6) against 1.04 ms all-atomic -- the partition's block
-// barriers keep too few atomics in flight for the two halves to overlap
-static double g_hybrid_frac = 0.0;
-static uint64_t g_hybrid_min_bits = 1ull << 26;  // smaller levels are not worth the second kernel
 static int g_query_mode = 0;  // 0: level-synchronous packed kernel, 1: thread-per-key packed kernel (measurement)
 
 static const DeviceInfo& device_info(int dev) {
@@ -115,7 +110,6 @@ static const DeviceInfo& device_info(int dev) {
         CK(cudaFuncSetAttribute(scatter0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CK(cudaFuncSetAttribute(scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CK(cudaFuncSetAttribute(bucket_mark_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        CK(cudaFuncSetAttribute(hybrid0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         // CUDA loads kernels lazily, and loading one may have to wait for running work: a shard spinning at a
         // barrier would then block the first launch of the very kernel it waits for.  Load everything now.
         {
@@ -130,7 +124,6 @@ static const DeviceInfo& device_info(int dev) {
                 (const void*)cascade_kernel<false>, (const void*)cascade_kernel<true>,
                 (const void*)scan_sums_kernel, (const void*)scan_top_kernel, (const void*)scan_apply_kernel,
                 (const void*)scatter0_kernel, (const void*)scatter_kernel, (const void*)bucket_mark_kernel,
-                (const void*)hybrid0_kernel,
                 (const void*)query_kernel<false>, (const void*)query_kernel<true>, (const void*)map_permute_kernel<false>,
                 (const void*)map_get_kernel<false>, (const void*)map_scatter_kernel, (const void*)map_gather_kernel,
                 (const void*)pack_query_kernel, (const void*)set_base_rank_kernel, (const void*)query_sync_kernel,
@@ -345,7 +338,6 @@ struct LevelPlan {
     bool maybe_bucket = false, surely_bucket = false;
     uint32_t range_max = 0, count_max = 1;  // bucket geometry upper bounds (for shared-memory sizing)
     uint64_t need_keys = 0;                 // capacity needed in buf[level & 1]
-    uint32_t hybrid_range = 0, hybrid_count = 0;  // level 0 only: buckets of the shared-memory part of a hybrid level
 };
 struct Plan {
     uint64_t words_cap = 0;
@@ -813,15 +805,6 @@ struct Builder {
         CK(cudaGetLastError());
         launches++;
     }
-    void launch_hybrid0(uint64_t begin, uint64_t end, uint32_t count) {
-        if (end <= begin) return;
-        const size_t smem = scatter_smem_bytes(count);
-        const uint64_t tiles = (end - begin + SRC_TILE - 1) / SRC_TILE;
-        const int grid = (int)std::min<uint64_t>(tiles, (uint64_t)info.sm_count * 2);
-        hybrid0_kernel<<<grid, BK_THREADS, smem, s>>>(d_state, d_keys, begin, end, d_buf[0], a32(), c32(), d_cursors, (uint32_t)smem);
-        CK(cudaGetLastError());
-        launches++;
-    }
     void launch_scatter(uint32_t level, uint32_t src_range_max, uint32_t src_count_max, uint32_t dst_count_max) {
         const size_t smem = std::min(MAX_DYN_SMEM, (size_t)src_range_max / 8 + scatter_smem_bytes(dst_count_max));
         const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (220 * 1024) / (smem + 1024)));
@@ -853,7 +836,6 @@ struct Builder {
         }
         const size_t e1 = begin_event(1, level);
         if (cur.maybe_bucket) launch_bucket_mark(level, cur.range_max, cur.count_max);
-        if (cur.hybrid_count) launch_bucket_mark(level, cur.hybrid_range, cur.hybrid_count);
         end_event(e1);
         if (sharded_now()) {
             // every shard has marked its keys -> fold the (a, collide) pairs of all shards -> everybody holds
@@ -983,31 +965,6 @@ static int build_once(const uint64_t* keys, uint64_t n, double gamma, int has_se
             for (int i = 0; i < 2; i++) plan.list_cap[i] = std::max<uint64_t>(plan.list_cap[i], GATHER_MAX_KEYS + 1024);
     }
 
-    // hybrid level 0 (unsharded, level fits the L2, default mode): part of the bit range goes through shared memory
-    struct { bool on = false; uint32_t shift = 0, count = 0, cap = 0; uint64_t split = 0; } hyb;
-    {
-        const double frac = g_hybrid_frac;
-        const uint64_t bits0 = level_size(gamma, n_global);
-        if (!comm && !b.stream_keys && !ingest && g_build_mode == 0 && !bucket_enable && rebuilds == 0 && frac > 0.0 && frac < 1.0 &&
-            bits0 >= g_hybrid_min_bits && (bits0 >> 32) == 0) {
-            uint32_t shift = BUCKET_SHIFT_MAX;
-            while (shift > BUCKET_SHIFT_MIN && (bits0 >> shift) < 2ull * b.slots()) shift--;
-            const uint64_t total = (bits0 + (1ull << shift) - 1) >> shift;
-            uint64_t cnt = (uint64_t)(frac * (double)total + 0.5);
-            cnt = std::max<uint64_t>(1, std::min<uint64_t>(cnt, total - 1));
-            const double mean = (double)n_global * (double)(1ull << shift) / (double)bits0;
-            uint64_t cap = (uint64_t)(mean + 6.0 * std::sqrt(mean) + 96.0);
-            cap = (cap + 31) & ~31ULL;
-            if (cnt <= BUCKET_MAX_COUNT && cap * cnt <= 0xffffffffULL) {
-                hyb.on = true;
-                hyb.shift = shift;
-                hyb.count = (uint32_t)cnt;
-                hyb.cap = (uint32_t)cap;
-                hyb.split = cnt << shift;
-                plan.list_cap[0] = std::max<uint64_t>(plan.list_cap[0], cnt * cap);
-            }
-        }
-    }
     if (ingest && plan.lv.size() < 2) return BUILD_RETRY_INCORE;  // level 1 may already belong to the tail kernel
     CK(cudaMallocAsync((void**)&b.d_state, sizeof(BuildState), s));
     trace.mark("a_state");
@@ -1044,14 +1001,6 @@ static int build_once(const uint64_t* keys, uint64_t n, double gamma, int has_se
     st.list_ready_level = NO_LEVEL;
     if (!try_make_level(&st, 0, n_global)) return fail(BPHF_ERR_INTERNAL, "level 0 does not fit the planned buffers");
     st.lv[0].k_loc = n;
-    if (hyb.on && st.lv[0].b_range == 0 && st.tail_level != 0) {
-        st.lv[0].h_shift = hyb.shift;
-        st.lv[0].h_count = hyb.count;
-        st.lv[0].h_cap = hyb.cap;
-        st.lv[0].h_split = hyb.split;
-    } else {
-        hyb.on = false;
-    }
     b.upload_state();
     trace.mark("prologue");
     const bool level0_bucketed = st.lv[0].b_range != 0;
@@ -1060,7 +1009,6 @@ static int build_once(const uint64_t* keys, uint64_t n, double gamma, int has_se
     // ---- level 0 entry step: keys (H2D in chunks when they live on the host, each chunk is consumed as it lands)
     auto level0_entry = [&](uint64_t lo, uint64_t hi) {
         if (level0_bucketed) b.launch_scatter0(lo, hi, count0);
-        else if (hyb.on) b.launch_hybrid0(lo, hi, hyb.count);
         else b.launch_mark_list(0, lo, hi, 0);
     };
     // ST_NEED_WORDS / ST_NEED_LIST for level `level`: grow what is missing and redo the level set-up on the host until
@@ -1167,8 +1115,6 @@ static int build_once(const uint64_t* keys, uint64_t n, double gamma, int has_se
     lp0.maybe_bucket = lp0.surely_bucket = level0_bucketed;
     lp0.range_max = st.lv[0].b_range;
     lp0.count_max = level0_bucketed ? count0 : 1;
-    lp0.hybrid_range = hyb.on ? (1u << hyb.shift) : 0;
-    lp0.hybrid_count = hyb.on ? hyb.count : 0;
     if (lps.empty()) lps.push_back(lp0);
     else if (!ingest) lps[0] = lp0;
     if (!ingest) b.launch_level(0, nullptr, lps[0]);
@@ -1472,12 +1418,6 @@ BPHF_API int bphf_set_ingest_mode(int mode, uint64_t ring_keys) {
     if (mode < 0 || mode > 2) return fail(BPHF_ERR_ARG, "ingest mode is 0 (automatic), 1 (always streamed) or 2 (never)");
     g_ingest_mode = mode;
     g_ingest_ring_keys = ring_keys ? ring_keys : (16ull << 20);
-    return BPHF_OK;
-}
-
-BPHF_API int bphf_set_hybrid(double frac, uint64_t min_bits) {
-    g_hybrid_frac = (frac >= 0.0 && frac < 1.0) ? frac : 0.0;
-    g_hybrid_min_bits = min_bits ? min_bits : (1ull << 26);
     return BPHF_OK;
 }
 

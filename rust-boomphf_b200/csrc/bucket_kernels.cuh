@@ -47,11 +47,7 @@ __device__ __forceinline__ ScatterDst make_dst(const BuildState* st, uint32_t le
     o.bits = (uint32_t)d->bits;
     o.keys = keys;
     o.cursor = cursor;
-    if (d->b_range == 0 && d->h_count != 0) {  // hybrid level: only the buckets below h_split exist
-        o.shift = d->h_shift;
-        o.count = d->h_count;
-        o.cap = d->h_cap;
-    } else if (d->b_range) {
+    if (d->b_range) {
         o.shift = (uint32_t)d->b_shift;
         o.count = d->b_count;
         o.cap = d->b_cap;
@@ -397,77 +393,6 @@ __global__ void __launch_bounds__(BK_THREADS, 2)
 }
 
 // -------------------------------------------------------------------------------------------------------
-// hybrid0_kernel: level-0 entry step of a hybrid level (common.cuh, LevelDesc::h_*).  Every input key is hashed once;
-// a key whose slot lies in [h_split, bits) is marked right away with L2 atomics (find_collisions, src/lib.rs:429-434),
-// a key whose slot lies below h_split is queued and grouped into its bucket region for bucket_mark_kernel.
-// The two halves load different units -- the L2 atomic units and the SMs' load/store pipes -- at the same time.
-// -------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(BK_THREADS, 2)
-    hybrid0_kernel(BuildState* __restrict__ st, const uint64_t* __restrict__ keys, uint64_t key_begin, uint64_t key_end,
-                   uint64_t* __restrict__ buf0, uint32_t* __restrict__ a32, uint32_t* __restrict__ c32,
-                   uint32_t* __restrict__ cursor0, uint32_t smem_bytes) {
-    extern __shared__ __align__(16) unsigned char dyn_smem[];
-    __shared__ uint32_t pend_cnt;
-    if (st->status != ST_RUNNING || st->n_levels != 0) return;
-    const LevelDesc* d = &st->lv[0];
-    if (d->b_range != 0 || d->h_count == 0) return;
-    const ScatterDst dst = make_dst(st, 0, buf0, cursor0);
-    if (scatter_smem_bytes(dst.count) > smem_bytes) {
-        if (threadIdx.x == 0) st->status = ST_ERR_INTERNAL;
-        return;
-    }
-    const ScatterSmem sm = carve_scatter(dyn_smem, dst.count);
-    for (uint32_t b = threadIdx.x; b < dst.count + 1; b += BK_THREADS) sm.hist[b] = 0;
-    if (threadIdx.x == 0) {
-        *sm.ovf = 0;
-        pend_cnt = 0;
-    }
-    const KeyCfg kc = st->kc;
-    const uint32_t bits = (uint32_t)d->bits, split = (uint32_t)d->h_split;
-    const uint64_t sp0 = d->sp0, off32 = d->word_off * 2;
-    const int lane = threadIdx.x & 31;
-    const uint64_t n = key_end - key_begin;
-    const uint64_t n_tiles = (n + SRC_TILE - 1) / SRC_TILE;
-    __syncthreads();
-    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const uint64_t base = key_begin + tile * SRC_TILE + threadIdx.x;
-        uint64_t key[SRC_KPT];
-        uint32_t idx[SRC_KPT];
-        bool live[SRC_KPT];
-#pragma unroll
-        for (int j = 0; j < SRC_KPT; j++) {
-            const uint64_t i = base + (uint64_t)j * BK_THREADS;
-            live[j] = i < key_end;
-            key[j] = live[j] ? ld_stream_u64(keys + i) : 0;
-        }
-        uint32_t old[SRC_KPT];
-#pragma unroll
-        for (int j = 0; j < SRC_KPT; j++) {
-            idx[j] = hashmod_small(kc, sp0, key[j], bits);
-            old[j] = 0;
-            if (live[j] && idx[j] >= split) old[j] = atomicOr(a32 + off32 + (idx[j] >> 5), 1u << (idx[j] & 31));
-        }
-#pragma unroll
-        for (int j = 0; j < SRC_KPT; j++)
-            if (old[j] & (1u << (idx[j] & 31))) red_or_u32(c32 + off32 + (idx[j] >> 5), 1u << (idx[j] & 31));
-        __syncthreads();  // every thread has taken its decision on the previous step's pend_cnt
-#pragma unroll
-        for (int j = 0; j < SRC_KPT; j++) {
-            const bool q = live[j] && idx[j] < split;
-            const uint32_t m = __ballot_sync(0xffffffffu, q);
-            uint32_t pos = 0;
-            if (lane == 0 && m) pos = atomicAdd(&pend_cnt, (uint32_t)__popc(m));
-            pos = __shfl_sync(0xffffffffu, pos, 0);
-            if (q) sm.stage_key[pos + __popc(m & ((1u << lane) - 1u))] = key[j];
-        }
-        __syncthreads();  // appends complete: pend_cnt is the same for everybody
-        if (pend_cnt > BK_TILE - SRC_TILE) flush_pending(st, dst, sm, &pend_cnt);
-    }
-    __syncthreads();
-    if (pend_cnt) flush_pending(st, dst, sm, &pend_cnt);
-}
-
-// -------------------------------------------------------------------------------------------------------
 // bucket_mark_kernel(level): find_collisions for one bucket in shared memory + finalize + popcounts
 // -------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mark_smem(uint32_t* a_sm, uint32_t* c_sm, uint32_t idx) {
@@ -487,10 +412,8 @@ __global__ void __launch_bounds__(BK_THREADS)
     __shared__ bool is_last;
     if (st->status != ST_RUNNING || st->n_levels != level) return;
     const LevelDesc* cu = &st->lv[level];
-    const bool hyb = cu->b_range == 0 && cu->h_count != 0;
-    if (cu->b_range == 0 && !hyb) return;
-    const uint32_t range = hyb ? (1u << cu->h_shift) : cu->b_range, count = hyb ? cu->h_count : cu->b_count,
-                   cap = hyb ? cu->h_cap : cu->b_cap, bits = (uint32_t)cu->bits;
+    if (cu->b_range == 0) return;
+    const uint32_t range = cu->b_range, count = cu->b_count, cap = cu->b_cap, bits = (uint32_t)cu->bits;
     const KeyCfg kc = st->kc;
     const uint64_t sp0 = cu->sp0;
     const uint64_t off32 = cu->word_off * 2;
@@ -587,10 +510,7 @@ __global__ void __launch_bounds__(BK_THREADS)
             const uint64_t sn = atomicAdd((unsigned long long*)&st->bucket_keys_seen, 0ULL);
             const uint64_t k_in = st->lv[level].k_in;
             st->bucket_keys_seen = 0;
-            if (hyb) {
-                // finalize_kernel finishes the level: it adds the unique count of the atomically built part
-                st->fin_ticket = 0;
-            } else if (raw) {
+            if (raw) {
                 // hand over to barrier + merge + finalize_kernel: this shard's key count of the level, counters reset
                 st->redo_count = sn;
                 st->uniq_count = 0;

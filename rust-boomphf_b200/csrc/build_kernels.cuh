@@ -127,13 +127,14 @@ __host__ __device__ inline void finish_level(BuildState* st, uint32_t level, uin
     st->uniq_count = 0;
     st->fin_ticket = 0;
     if (st->chunk_mode) {
-        // from_chunked_iterator_parallel: a chunked level l is refused when l > max_iters (src/lib.rs:570-573, checked
-        // before the level is built, only while keys remain); the tail is a new_parallel of its own whose counter
-        // starts at the switch (src/lib.rs:654) and fires like the check below
+        // from_chunked_iterator_parallel: `iter > max_iters` is tested at the top of the loop (src/lib.rs:568-573),
+        // BEFORE the `keys_remaining == 0` break (:580-582), so it fires for iter = level + 1 even when nothing is left;
+        // the loop is left right after the buffering level (:645-648, next == switch_level) without another test, and
+        // the tail is a new_parallel of its own whose counter starts at the switch (:654) and fires like the check below
         const uint32_t next = level + 1;
-        const bool tail_phase = st->switch_level != NO_LEVEL && next > st->switch_level;
+        const bool tail_phase = st->switch_level != NO_LEVEL && next >= st->switch_level;
         bool fail = next >= BPHF_MAX_LEVELS;
-        if (!tail_phase) fail = fail || (k_next != 0 && st->chunk_has_max && (uint64_t)next > st->chunk_max_iters);
+        if (!tail_phase) fail = fail || (st->chunk_has_max && (uint64_t)next > st->chunk_max_iters);
         else fail = fail || (next - st->switch_level > BPHF_MAX_ITERS);
         if (fail) {
             st->status = ST_ERR_MAX_ITERS;
@@ -435,8 +436,6 @@ __device__ __forceinline__ void finalize_body(BuildState* __restrict__ st, uint3
     __shared__ bool is_last;
     const uint64_t word_off = __ldcg(&st->lv[level].word_off);
     const uint64_t n_pairs = round_up8(__ldcg(&st->lv[level].n_words)) / 2;  // multiple of 4
-    // hybrid level: the words below h_split were finalized (and popcounted) by bucket_mark_kernel
-    const uint64_t first_pair = __ldcg(&st->lv[level].h_split) / 128;
     const int lane = threadIdx.x & 31;
     ulonglong2* __restrict__ a2 = reinterpret_cast<ulonglong2*>(words + word_off);
     const ulonglong2* __restrict__ c2 = reinterpret_cast<const ulonglong2*>(coll + word_off);
@@ -444,7 +443,7 @@ __device__ __forceinline__ void finalize_body(BuildState* __restrict__ st, uint3
 
     uint64_t uniq = 0;
     const uint64_t stride = (uint64_t)gridDim.x * FIN_THREADS;
-    for (uint64_t p0 = first_pair + (uint64_t)blockIdx.x * FIN_THREADS + (threadIdx.x & ~31u); p0 < n_pairs; p0 += stride) {
+    for (uint64_t p0 = (uint64_t)blockIdx.x * FIN_THREADS + (threadIdx.x & ~31u); p0 < n_pairs; p0 += stride) {
         const uint64_t p = p0 + lane;
         uint32_t pc = 0;
         if (p < n_pairs) {

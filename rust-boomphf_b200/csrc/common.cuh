@@ -36,12 +36,6 @@ struct LevelDesc {
     uint32_t b_count;
     uint32_t b_cap;     // key capacity of each bucket region
     uint32_t pad_;
-    // hybrid level (level 0 of an unsharded build that fits the L2): bits [0, h_split) are built in shared memory
-    // from h_count bucket regions of 2^h_shift bits, bits [h_split, bits) by L2 atomics in the same entry kernel.
-    // The L2 atomic units (126 G/s) bound an all-atomic level 0 while the SMs' load/store units idle half the time;
-    // splitting the level by bit range uses both.  b_range stays 0: every later step sees a plain level.
-    uint64_t h_split;
-    uint32_t h_count, h_cap, h_shift, pad2_;
 };
 
 enum BuildStatus : uint32_t {
@@ -182,8 +176,6 @@ __host__ __device__ inline void make_level(BuildState* st, uint32_t level, uint6
     d.sp0 = level_spx(st->kc, st->seed0 + level);
     d.sp0_query = level_spx(st->kc, level);
     d.b_shift = 0;
-    d.h_split = 0;
-    d.h_count = d.h_cap = d.h_shift = d.pad2_ = 0;
     d.b_range = d.b_count = d.b_cap = 0;
     d.pad_ = 0;
 }

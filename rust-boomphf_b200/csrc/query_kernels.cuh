@@ -300,9 +300,11 @@ __global__ void __launch_bounds__(QS_THREADS, 8)
             n_q = n_out;
             __syncwarp();
         }
-        // ---- stragglers: one lane per key walks the remaining levels; None when no level claims the key
-        if ((uint32_t)lane < n_q) {
-            const uint32_t i = queue_all[warp][r & 1][lane];
+        // ---- stragglers: one lane per key walks the remaining levels; None when no level claims the key.
+        // The round loop also ends when the levels run out (r == n_levels) with ANY number of keys still queued
+        // (absent keys against a shallow MPHF): every queued entry is drained, not just the first 32.
+        for (uint32_t t = lane; t < n_q; t += 32) {
+            const uint32_t i = queue_all[warp][r & 1][t];
             const uint64_t key = res[i];
             uint64_t rank = BPHF_NONE;
             for (uint32_t l = r; l < n_levels; l++) {

@@ -128,6 +128,23 @@ def test_absent_keys_match_oracle_including_none(pkg, oracle):
         m.hash(missing)
 
 
+@pytest.mark.parametrize("n", [1, 10, 1000, 20000])
+def test_absent_keys_against_small_mphfs_are_none_not_garbage(pkg, oracle, n):
+    # shallow MPHFs queried with keys outside the set: far more than 32 keys of a warp tile miss every level, all of
+    # them must come back as None (try_hash, src/lib.rs:340-355), never as the raw key
+    keys = oracle.keygen(n, seed=3 * n + 1, kind=0)
+    absent = oracle.keygen(10_000, seed=777, kind=0)
+    for gamma in (1.7, 5.0):
+        m = pkg.Mphf.new(gamma, keys)
+        ref = oracle.OracleMphf.new(gamma, keys)
+        out = m.hash_batch(absent)
+        assert np.array_equal(out, ref.hash_batch(absent))
+        none = out == np.uint64(pkg.NONE)
+        assert none.sum() > 0 and (out[~none] < n).all()
+        mixed = np.concatenate([absent[:300], keys, absent[300:900]])
+        assert np.array_equal(m.hash_batch(mixed), ref.hash_batch(mixed))
+
+
 def test_duplicate_keys_report_max_iters(pkg):
     for n in (10, 100_000):
         keys = np.arange(n, dtype=np.uint64) * 7 + 1
@@ -399,6 +416,51 @@ def test_from_chunked_iterator_parallel_gamma_switch_and_limits(pkg, oracle):
     assert e.value.code == -2
 
 
+def _chunked_parallel_both(pkg, oracle, gamma, chunks, max_iters, n):
+    """(levels or 'panic') from the GPU path and from the oracle."""
+    try:
+        got = pkg.Mphf.from_chunked_iterator_parallel(gamma, chunks, max_iters, n).levels()
+    except pkg.MphfPanic as e:
+        assert e.code == -3
+        got = "panic"
+    try:
+        exp = oracle.OracleMphf.from_chunked_iterator_parallel(gamma, chunks, max_iters, n).levels()
+    except oracle.OracleError:
+        exp = "panic"
+    return got, exp
+
+
+def test_from_chunked_iterator_parallel_max_iters_boundaries(pkg, oracle):
+    # `iter > max_iters` sits at the top of the reference's loop (src/lib.rs:568-573): before the keys_remaining == 0
+    # break, and never reached again once the buffering level has run (:645-648)
+    keys = oracle.keygen(1_000_000, seed=4, kind=1)
+    chunks = np.array_split(keys, 5)
+    free = oracle.OracleMphf.from_chunked_iterator_parallel(2.0, chunks, None, len(keys))
+    thr = int(np.float32(0.01) * np.float32(len(keys)))
+    # the buffering level = first level entered with fewer than min(50 M, thr) keys
+    sizes = [b for b, _, _ in free.levels()]
+    buf_level = next(l for l, b in enumerate(sizes) if b < 2.0 * min(50_000_000, thr))
+    assert 1 <= buf_level < len(sizes) - 1
+    for mi in (buf_level - 1, buf_level, buf_level + 1):
+        got, exp = _chunked_parallel_both(pkg, oracle, 2.0, chunks, mi, len(keys))
+        assert (got == "panic") == (exp == "panic"), (mi, buf_level)
+        if exp != "panic":
+            assert_same_levels(got, exp)
+    assert _chunked_parallel_both(pkg, oracle, 2.0, chunks, buf_level - 1, len(keys))[1] == "panic"
+    assert _chunked_parallel_both(pkg, oracle, 2.0, chunks, buf_level, len(keys))[1] != "panic"
+    # small n: no buffering at all (thr = 0); the check after the LAST level fires even though nothing is left
+    small = oracle.keygen(60, seed=8, kind=0)
+    full = oracle.OracleMphf.from_chunked_iterator_parallel(1.7, [small], None, len(small))
+    last = full.num_levels - 1
+    for mi in (last - 1, last, last + 1):
+        got, exp = _chunked_parallel_both(pkg, oracle, 1.7, [small], mi, len(small))
+        assert (got == "panic") == (exp == "panic"), (mi, last)
+        if exp != "panic":
+            assert_same_levels(got, exp)
+    assert _chunked_parallel_both(pkg, oracle, 1.7, [small], last, len(small))[1] == "panic"
+    assert _chunked_parallel_both(pkg, oracle, 1.7, [small], last + 1, len(small))[1] != "panic"
+
+
 def test_from_chunked_iterator_device_chunks(pkg, oracle):
     import torch
     keys = oracle.keygen(2_000_000, seed=12, kind=0)
@@ -465,48 +527,6 @@ def test_u32_device_keys_and_absent_keys(pkg, oracle):
     absent = _distinct(np.random.default_rng(8), np.uint32, 100_000)
     got = m.hash_batch(torch.from_numpy(absent.view(np.int32)).cuda()).cpu().numpy().view(np.uint64)
     assert np.array_equal(got, ref.hash_batch(absent))
-
-
-# ---- hybrid level 0: part of the bit range in shared memory, the rest with L2 atomics ------------------------------
-@pytest.fixture
-def small_hybrid(pkg):
-    pkg.lib().bphf_set_hybrid(0.45, 1 << 14)
-    yield
-    pkg.lib().bphf_set_hybrid(-1.0, 0)
-
-
-@pytest.mark.parametrize("n", [10_000, 65_537, 300_001, 3_000_000, 20_000_000])
-@pytest.mark.parametrize("frac", [0.1, 0.45, 0.9])
-def test_hybrid_level0_parity(pkg, oracle, small_hybrid, n, frac):
-    pkg.lib().bphf_set_hybrid(frac, 1 << 14)
-    keys = oracle.keygen(n, seed=n + 23, kind=0)
-    m = pkg.Mphf.new_parallel(1.7, keys, None)
-    assert_same_levels(m.levels(), oracle.OracleMphf.new_parallel(1.7, keys).levels())
-
-
-@pytest.mark.parametrize("gamma", [1.02, 2.0, 5.0, 17.5])
-def test_hybrid_level0_gammas_and_host_chunks(pkg, oracle, small_hybrid, gamma):
-    keys = oracle.keygen(1_500_000, seed=31, kind=1)
-    assert_same_levels(pkg.Mphf.new_parallel(gamma, keys, 7).levels(), oracle.OracleMphf.new_parallel(gamma, keys, 7).levels())
-
-
-def test_hybrid_level0_duplicates_fall_back(pkg, small_hybrid):
-    base = np.arange(50_000, dtype=np.uint64) * 3 + 5
-    with pytest.raises(pkg.MphfPanic) as e:
-        pkg.Mphf.new_parallel(1.7, np.tile(base, 40), None)   # bucket regions overflow -> plain rebuild -> MAX_ITERS
-    assert e.value.code == -3
-
-
-def test_hybrid_switch_gives_identical_structures(pkg, oracle):
-    keys = oracle.keygen(50_000_000, seed=6, kind=0)
-    try:
-        pkg.lib().bphf_set_hybrid(0.0, 0)           # the default: all-atomic level 0
-        a = pkg.Mphf.new_parallel(1.7, keys, None)
-        pkg.lib().bphf_set_hybrid(0.45, 0)          # hybrid for levels >= 2^26 bits
-        b = pkg.Mphf.new_parallel(1.7, keys, None)
-    finally:
-        pkg.lib().bphf_set_hybrid(-1.0, 0)
-    assert oracle.fingerprint(a.levels()) == oracle.fingerprint(b.levels())
 
 
 @pytest.mark.parametrize("entry", GOLDEN["key_kinds"], ids=[e["name"] for e in GOLDEN["key_kinds"]])

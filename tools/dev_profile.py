@@ -17,8 +17,6 @@ min_keys = int(float(sys.argv[5])) if len(sys.argv) > 5 else 0
 pkg = ge.load_package()
 L = pkg.lib()
 L.bphf_set_build_mode(mode, min_keys)
-if os.environ.get("HYB_FRAC") is not None:
-    L.bphf_set_hybrid(float(os.environ["HYB_FRAC"]), 0)
 keys = torch.empty(n, dtype=torch.int64, device="cuda")
 L.bphf_keygen_u64(C.c_void_p(keys.data_ptr()), 0, n, 1, 0, 0, None)
 torch.cuda.synchronize()
