@@ -5,7 +5,6 @@
 //!     if let Some(m) = cuda::try_new_cuda(gamma, objects, None /* or starting_seed */) { return m; }
 //! and keep their bodies as the path for builds without the feature.  The struct, its serde derive and
 //! `hash` / `try_hash` are untouched: a GPU-built Mphf is an ordinary Mphf.
-use std::any::TypeId;
 use std::ffi::CStr;
 use std::hash::{Hash, Hasher};
 use std::marker::PhantomData;
@@ -45,21 +44,33 @@ impl Recorder {
     }
 }
 
-/// (kind, width) of the key types that need no recording pass: their `Hash` impl is one `write` of the value's bytes
-fn word_kind<T: 'static>() -> Option<(i32, i32)> {
-    let t = TypeId::of::<T>();
-    macro_rules! is { ($($ty:ty),*) => { false $(|| t == TypeId::of::<$ty>())* } }
-    if is!(u64, i64, usize, isize) {
-        Some((sys::BPHF_KEY_U64, 8))
-    } else if is!(u32, i32) {
-        Some((sys::BPHF_KEY_UINT, 4))
-    } else if is!(u16, i16) {
-        Some((sys::BPHF_KEY_UINT, 2))
-    } else if is!(u8, i8) {
-        Some((sys::BPHF_KEY_UINT, 1))
-    } else {
-        None
+/// (kind, width) of the key types that need no recording pass: their `Hash` impl is one `write` of the value's bytes.
+///
+/// The reference's impl block is `impl<'a, T: 'a + Hash + Debug> Mphf<T>` (src/lib.rs:100, :229): no `'static`, so
+/// `TypeId` is not available without changing the public bounds (`Mphf<&str>` must keep compiling).  The primitive is
+/// recognised by `type_name` (exactly "u64", "i32", ... for primitives; any user type carries its module path) and
+/// then CONFIRMED on the first key: what `T::hash` writes must be one segment equal to the key's own bytes.  Anything
+/// else takes the recorded-stream path, which is correct for every `T: Hash`.
+fn word_kind<T: Hash>(first: Option<&T>) -> Option<(i32, i32)> {
+    let (kind, width) = match std::any::type_name::<T>() {
+        "u64" | "i64" | "usize" | "isize" => (sys::BPHF_KEY_U64, 8usize),
+        "u32" | "i32" => (sys::BPHF_KEY_UINT, 4),
+        "u16" | "i16" => (sys::BPHF_KEY_UINT, 2),
+        "u8" | "i8" => (sys::BPHF_KEY_UINT, 1),
+        _ => return None,
+    };
+    if std::mem::size_of::<T>() != width {
+        return None;
     }
+    if let Some(k) = first {
+        let r = Recorder::record(std::iter::once(k));
+        // SAFETY: T is one of the primitive integers above (size checked): no padding, any bit pattern is a value
+        let raw = unsafe { std::slice::from_raw_parts(k as *const T as *const u8, width) };
+        if r.seg_ends.len() != 1 || r.bytes.as_slice() != raw {
+            return None;
+        }
+    }
+    Some((kind as i32, width as i32))
 }
 
 fn check(rc: i32) {
@@ -72,11 +83,11 @@ fn check(rc: i32) {
 }
 
 /// Build on the GPU and copy the levels into the reference's own struct.
-pub(crate) fn try_new_cuda<T: 'static + Hash>(gamma: f64, objects: &[T], starting_seed: Option<u64>) -> Option<Mphf<T>> {
+pub(crate) fn try_new_cuda<T: Hash>(gamma: f64, objects: &[T], starting_seed: Option<u64>) -> Option<Mphf<T>> {
     assert!(gamma > 1.01);
     let mut h: *mut sys::bphf_mphf = std::ptr::null_mut();
     let (has_seed, seed) = (starting_seed.is_some() as i32, starting_seed.unwrap_or(0));
-    let rc = if let Some((kind, width)) = word_kind::<T>() {
+    let rc = if let Some((kind, width)) = word_kind::<T>(objects.first()) {
         unsafe {
             sys::bphf_build_keys(objects.as_ptr() as *const core::ffi::c_void, objects.len() as u64, kind, width, gamma,
                                  has_seed, seed, 0, sys::BPHF_MEM_HOST, &mut h)
@@ -105,7 +116,7 @@ pub(crate) fn try_new_cuda<T: 'static + Hash>(gamma: f64, objects: &[T], startin
     Some(Mphf { bitvecs: bitvecs.into_boxed_slice(), phantom: PhantomData })
 }
 
-impl<T: 'static + Hash> Mphf<T> {
+impl<T: Hash> Mphf<T> {
     /// `try_hash` over a slice on the GPU; `u64::MAX` where `try_hash` returns `None`
     pub fn try_hash_many(&self, items: &[T]) -> Vec<u64> {
         // upload the levels once per call here; a production shim caches the handle in a OnceCell next to `bitvecs`
@@ -113,11 +124,12 @@ impl<T: 'static + Hash> Mphf<T> {
         let words: Vec<Vec<u64>> = self.bitvecs.iter().map(|(bv, _)| (0..bv.num_words()).map(|i| bv.get_word(i)).collect()).collect();
         let wp: Vec<*const u64> = words.iter().map(|w| w.as_ptr()).collect();
         let rp: Vec<*const u64> = self.bitvecs.iter().map(|(_, r)| r.as_ptr()).collect();
-        let (kind, width) = word_kind::<T>().unwrap_or((sys::BPHF_KEY_STREAM, 0));
+        let wk = word_kind::<T>(items.first());
+        let (kind, width) = wk.unwrap_or((sys::BPHF_KEY_STREAM, 0));
         let mut h: *mut sys::bphf_mphf = std::ptr::null_mut();
         check(unsafe { sys::bphf_from_levels_keys(bits.len() as u32, bits.as_ptr(), wp.as_ptr(), rp.as_ptr(), kind, width, 0, &mut h) });
         let mut out = vec![0u64; items.len()];
-        let rc = if word_kind::<T>().is_some() {
+        let rc = if wk.is_some() {
             unsafe { sys::bphf_hash_batch_keys(h, items.as_ptr() as *const core::ffi::c_void, items.len() as u64, out.as_mut_ptr(),
                                                sys::BPHF_MEM_HOST, std::ptr::null_mut()) }
         } else {

@@ -9,7 +9,10 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(_HERE, "libboomphf_cuda.so")
+# measurement aid: BPHF_LIB_VARIANT=<tag> builds / loads libboomphf_cuda_<tag>.so with the extra nvcc flags of
+# BPHF_NVCC_EXTRA (e.g. -DBPHF_PASS_VARIANT=1), so that two kernel variants can be timed by the same bench command
+_VARIANT = os.environ.get("BPHF_LIB_VARIANT", "")
+LIB_PATH = os.path.join(_HERE, "libboomphf_cuda%s.so" % ("_" + _VARIANT if _VARIANT else ""))
 _REPO = os.path.dirname(_HERE)
 
 NVCC_FLAGS = [
@@ -83,7 +86,8 @@ def build_native(force=False, verbose=False):
                     os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(p) for p in _sources()):
                 return LIB_PATH  # another process built it while we waited
             tmp = LIB_PATH + ".tmp.%d" % os.getpid()
-            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [
+            extra = os.environ.get("BPHF_NVCC_EXTRA", "").split() if _VARIANT else []
+            cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + [
                 "-o", tmp, os.path.join(_CSRC, "boomphf_cuda.cu")]
             subprocess.check_call(cmd)
             os.replace(tmp, LIB_PATH)

@@ -105,7 +105,10 @@ static const DeviceInfo& device_info(int dev) {
                                           (const void*)pass_chunk_kernel<false>, (const void*)pass_chunk_kernel<true>,
                                           (const void*)cascade_kernel<false>, (const void*)cascade_kernel<true>,
                                           (const void*)shard_gather_kernel<false>, (const void*)shard_gather_kernel<true>};
-            for (const void* k : ring_kernels) CK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 60));
+            for (const void* k : ring_kernels) {
+                CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PASS_SMEM_BYTES));
+                CK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 60));
+            }
         }
         CK(cudaFuncSetAttribute(scatter0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CK(cudaFuncSetAttribute(scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -474,6 +477,7 @@ struct Builder {
     uint64_t* d_coll = nullptr;
     uint32_t* d_blockpop = nullptr;
     uint32_t* d_cursors = nullptr;  // [2][MAX_BUCKETS_ALLOC]
+    uint32_t* d_regcnt = nullptr;   // [2][n_regions]: keys per region of the striped key lists (pass_body)
     uint64_t* d_buf[2] = {nullptr, nullptr};   // key lists / bucket key regions, level l in d_buf[l & 1]
     uint64_t buf_cap[2] = {0, 0};               // allocated size of d_buf[] in keys (>= the planned list_cap)
     uint64_t phys_words = 0;  // words_cap + TAIL_RESERVE_WORDS
@@ -503,6 +507,7 @@ struct Builder {
         if (d_coll && !comm) cudaFreeAsync(d_coll, s);
         if (d_blockpop) cudaFreeAsync(d_blockpop, s);
         if (d_cursors) cudaFreeAsync(d_cursors, s);
+        if (d_regcnt) cudaFreeAsync(d_regcnt, s);
         for (int i = 0; i < 2; i++) {
             try {
                 release_list(i);
@@ -519,21 +524,26 @@ struct Builder {
 
     // persistent grids: exactly the CTAs that are resident at once (a grid of 8 per SM with 6 resident runs a second,
     // two-thirds empty wave: 41 tiles per CTA either way)
-    int resident_grid(const void* fn, int threads) const {
+    int resident_grid(const void* fn, int threads, size_t dyn_smem = 0) const {
         static std::mutex mu;
         static std::vector<std::pair<const void*, int>> cache;
         std::lock_guard<std::mutex> lock(mu);
         for (auto& e : cache)
             if (e.first == fn) return info.sm_count * e.second;
         int per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
-        cudaFuncAttributes fa;
-        if (cudaFuncGetAttributes(&fa, fn) == cudaSuccess && fa.sharedSizeBytes >= 32 * 1024)
-            per_sm = std::min(per_sm, 4);  // TMA-ring kernels: 4 x 32 KB of shared memory, the rest stays L1
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, dyn_smem) != cudaSuccess || per_sm < 1)
+            per_sm = dyn_smem ? 1 : 4;
+        if (dyn_smem) per_sm = std::min(per_sm, BPHF_PASS_CTAS);  // level kernels: the rest of the array stays L1
         cache.emplace_back(fn, per_sm);
         return info.sm_count * per_sm;
     }
     uint32_t slots() const { return (uint32_t)info.sm_count * 2; }
+    // regions of the striped key lists: one per warp of the persistent cascade grid
+    uint32_t n_regions() const { return (uint32_t)info.sm_count * BPHF_PASS_CTAS * WP_WARPS; }
+    static uint64_t region_cap(uint64_t dense_keys, uint32_t R) {  // key slots per region for a dense source of that size
+        const uint64_t tiles = (dense_keys + WP_TILE - 1) / WP_TILE;
+        return std::max<uint64_t>(1, (tiles + R - 1) / R) * WP_TILE;
+    }
 
     size_t begin_event(int kind, uint32_t level) {
         const bool want = profile >= 2 || (profile == 1 && (((kind <= 1 || kind == 4) && level <= 1) || kind == 5));
@@ -567,6 +577,8 @@ struct Builder {
         CK(cudaMemsetAsync(d_words, 0, phys_words * 8, s));
         CK(cudaMemsetAsync(d_coll, 0, phys_words * 8, s));
         CK(cudaMemsetAsync(d_cursors, 0, (size_t)2 * MAX_BUCKETS_ALLOC * CURSOR_STRIDE * 4, s));
+        CK(cudaMallocAsync((void**)&d_regcnt, (size_t)2 * n_regions() * 4, s));
+        CK(cudaMemsetAsync(d_regcnt, 0, (size_t)2 * n_regions() * 4, s));
     }
     // ST_NEED_WORDS: move to a larger arena, keeping everything built so far
     void grow_arena(uint64_t need_words) {
@@ -608,6 +620,7 @@ struct Builder {
         buf_cap[which] = 0;
         acquire_list(which, cap);
         hst.list_cap[which] = cap;
+        hst.reg_cap = std::min(hst.list_cap[0], hst.list_cap[1]) / hst.n_regions / WP_TILE * WP_TILE;
     }
     // list buffer `which` with room for `cap` keys: the parked one of this thread when it is large enough
     void acquire_list(int which, uint64_t cap) {
@@ -665,27 +678,28 @@ struct Builder {
         launches++;
     }
     void launch_pass(uint32_t level, uint64_t k_src_up) {
-        const uint64_t tiles = std::max<uint64_t>(1, (k_src_up + PASS_TILE - 1) / PASS_TILE);
+        const uint64_t tiles = std::max<uint64_t>(1, (k_src_up + WP_TILE - 1) / WP_TILE);
         const void* fn = stream_keys ? (const void*)pass_kernel<true, StreamCfg>
                          : maybe_big ? (const void*)pass_kernel<true> : (const void*)pass_kernel<false>;
-        const int grid = (int)std::min<uint64_t>(tiles, (uint64_t)resident_grid(fn, PASS_THREADS));
+        // one warp per region of the striped lists (fewer CTAs when there is less to read)
+        const int grid = (int)std::min<uint64_t>((tiles + WP_WARPS - 1) / WP_WARPS, (uint64_t)resident_grid(fn, PASS_THREADS, PASS_SMEM_BYTES));
         if (stream_keys)
-            pass_kernel<true, StreamCfg><<<grid, PASS_THREADS, 0, s>>>(d_state, level, d_keys, d_buf[0], d_buf[1], a32(), c32());
+            pass_kernel<true, StreamCfg><<<grid, PASS_THREADS, PASS_SMEM_BYTES, s>>>(d_state, level, d_keys, d_buf[0], d_buf[1], a32(), c32());
         else if (maybe_big)
-            pass_kernel<true><<<grid, PASS_THREADS, 0, s>>>(d_state, level, d_keys, d_buf[0], d_buf[1], a32(), c32());
+            pass_kernel<true><<<grid, PASS_THREADS, PASS_SMEM_BYTES, s>>>(d_state, level, d_keys, d_buf[0], d_buf[1], a32(), c32());
         else
-            pass_kernel<false><<<grid, PASS_THREADS, 0, s>>>(d_state, level, d_keys, d_buf[0], d_buf[1], a32(), c32());
+            pass_kernel<false><<<grid, PASS_THREADS, PASS_SMEM_BYTES, s>>>(d_state, level, d_keys, d_buf[0], d_buf[1], a32(), c32());
         CK(cudaGetLastError());
         launches++;
     }
     // streamed ingest: filter(0) + mark(1) over one chunk of the level-0 keys
     void launch_pass_chunk(const uint64_t* chunk, uint64_t cnt) {
         if (cnt == 0) return;
-        const uint64_t tiles = (cnt + PASS_TILE - 1) / PASS_TILE;
+        const uint64_t tiles = (cnt + WP_TILE - 1) / WP_TILE;
         const void* fn = maybe_big ? (const void*)pass_chunk_kernel<true> : (const void*)pass_chunk_kernel<false>;
-        const int grid = (int)std::min<uint64_t>(tiles, (uint64_t)resident_grid(fn, PASS_THREADS));
-        if (maybe_big) pass_chunk_kernel<true><<<grid, PASS_THREADS, 0, s>>>(d_state, chunk, cnt, d_buf[0], d_buf[1], a32(), c32());
-        else pass_chunk_kernel<false><<<grid, PASS_THREADS, 0, s>>>(d_state, chunk, cnt, d_buf[0], d_buf[1], a32(), c32());
+        const int grid = (int)std::min<uint64_t>((tiles + WP_WARPS - 1) / WP_WARPS, (uint64_t)resident_grid(fn, PASS_THREADS, PASS_SMEM_BYTES));
+        if (maybe_big) pass_chunk_kernel<true><<<grid, PASS_THREADS, PASS_SMEM_BYTES, s>>>(d_state, chunk, cnt, d_buf[0], d_buf[1], a32(), c32());
+        else pass_chunk_kernel<false><<<grid, PASS_THREADS, PASS_SMEM_BYTES, s>>>(d_state, chunk, cnt, d_buf[0], d_buf[1], a32(), c32());
         CK(cudaGetLastError());
         launches++;
     }
@@ -708,12 +722,12 @@ struct Builder {
     // sharded: collect the remaining keys on every shard, then mark + finalize level `level` from the collected list
     void launch_gather(uint32_t level, uint64_t k_src_up, uint64_t k_up) {
         const size_t e0 = begin_event(0, level);
-        const uint64_t tiles = std::max<uint64_t>(1, (k_src_up + PASS_TILE - 1) / PASS_TILE);
+        const uint64_t tiles = std::max<uint64_t>(1, (k_src_up + WP_TILE - 1) / WP_TILE);
         const void* gfn = maybe_big ? (const void*)shard_gather_kernel<true> : (const void*)shard_gather_kernel<false>;
-        const int grid = (int)std::min<uint64_t>(tiles, (uint64_t)resident_grid(gfn, PASS_THREADS));
+        const int grid = (int)std::min<uint64_t>((tiles + WP_WARPS - 1) / WP_WARPS, (uint64_t)resident_grid(gfn, PASS_THREADS, PASS_SMEM_BYTES));
         uint64_t* xk = comm->dev.xkeys[comm->rank];
-        if (maybe_big) shard_gather_kernel<true><<<grid, PASS_THREADS, 0, s>>>(d_state, level, d_keys, d_buf[0], d_buf[1], c32(), xk);
-        else shard_gather_kernel<false><<<grid, PASS_THREADS, 0, s>>>(d_state, level, d_keys, d_buf[0], d_buf[1], c32(), xk);
+        if (maybe_big) shard_gather_kernel<true><<<grid, PASS_THREADS, PASS_SMEM_BYTES, s>>>(d_state, level, d_keys, d_buf[0], d_buf[1], c32(), xk);
+        else shard_gather_kernel<false><<<grid, PASS_THREADS, PASS_SMEM_BYTES, s>>>(d_state, level, d_keys, d_buf[0], d_buf[1], c32(), xk);
         CK(cudaGetLastError());
         launches++;
         end_event(e0);
@@ -736,13 +750,13 @@ struct Builder {
         int want = per_sm[v].load();
         if (!want) {
             int n = 0;
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, PASS_THREADS, 0));
-            want = std::max(1, std::min(n, 4));  // 4 x 32 KB of TMA ring per SM; the rest of the array stays L1
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, PASS_THREADS, PASS_SMEM_BYTES));
+            want = std::max(1, std::min(n, BPHF_PASS_CTAS));  // 64 KB of warp rings per CTA; the rest of the array stays L1
         }
         const size_t ev = begin_event(5, 0);
         void* args[] = {(void*)&d_state, (void*)&d_keys, (void*)&d_buf[0], (void*)&d_buf[1], (void*)&d_words, (void*)&d_coll, (void*)&d_blockpop};
         for (;;) {
-            const cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(info.sm_count * want), dim3(PASS_THREADS), args, 0, s);
+            const cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(info.sm_count * want), dim3(PASS_THREADS), args, PASS_SMEM_BYTES, s);
             if (e == cudaSuccess) break;
             // the occupancy query and the launch can disagree (shared-memory carve-out): every CTA must be resident
             if (e == cudaErrorCooperativeLaunchTooLarge && want > 1) {
@@ -966,6 +980,23 @@ static int build_once(const uint64_t* keys, uint64_t n, double gamma, int has_se
     }
 
     if (ingest && plan.lv.size() < 2) return BUILD_RETRY_INCORE;  // level 1 may already belong to the tail kernel
+    // ---- striped key lists (pass_body): every region must be able to hold what its share of the first dense source
+    // holds -- the input, or the list the last bucketed level leaves behind; later levels only shrink
+    const uint32_t n_regions = b.n_regions();
+    uint64_t reg_cap = 0;
+    if (!plan.lv.empty()) {
+        if (ingest) {
+            // the chunks of the input pass through pass_chunk_kernel one by one and accumulate in the regions
+            for (uint64_t g = 0; g < chunk->n_segs; g++)
+                for (uint64_t off = 0; off < chunk->seg_len[g]; off += chunk->ring_keys)
+                    reg_cap += Builder::region_cap(std::min(chunk->ring_keys, chunk->seg_len[g] - off), n_regions);
+        } else {
+            const bool l0_bucketed = plan.lv[0].maybe_bucket;
+            const uint64_t dense = comm ? n : (l0_bucketed && plan.lv.size() > 1 ? plan.lv[1].k_up : n_global);
+            reg_cap = Builder::region_cap(dense, n_regions);
+        }
+        for (int i = 0; i < 2; i++) plan.list_cap[i] = std::max<uint64_t>(plan.list_cap[i], (uint64_t)n_regions * reg_cap);
+    }
     CK(cudaMallocAsync((void**)&b.d_state, sizeof(BuildState), s));
     trace.mark("a_state");
     b.alloc_arena(plan.words_cap);
@@ -999,6 +1030,9 @@ static int build_once(const uint64_t* keys, uint64_t n, double gamma, int has_se
     }
     st.gather_level = gather_level;
     st.list_ready_level = NO_LEVEL;
+    st.n_regions = n_regions;
+    st.reg_cap = reg_cap;
+    st.reg_cnt = b.d_regcnt;
     if (!try_make_level(&st, 0, n_global)) return fail(BPHF_ERR_INTERNAL, "level 0 does not fit the planned buffers");
     st.lv[0].k_loc = n;
     b.upload_state();
@@ -1931,6 +1965,17 @@ BPHF_API void bphf_free(bphf_mphf* m) {
     if (prev >= 0) cudaSetDevice(prev);
     delete m;
 }
+
+#ifdef BPHF_TRACE
+// measurement builds only (not declared in the header): copies the cascade phase timestamps to the host
+BPHF_API int bphf_debug_cascade_trace(uint64_t* out, uint64_t bytes) {
+    API_BEGIN
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpyFromSymbol(out, g_cascade_trace, std::min<uint64_t>(bytes, sizeof(g_cascade_trace))));
+    return BPHF_OK;
+    API_END
+}
+#endif
 
 BPHF_API int bphf_get_build_stats(const bphf_mphf* m, bphf_build_stats* out) {
     if (!m || !out) return fail(BPHF_ERR_ARG, "null argument");

@@ -243,170 +243,261 @@ __global__ void __launch_bounds__(PASS_THREADS)
 // ---------------------------------------------------------------------------------------------
 // pass_kernel: level >= 1.  filter(level-1) + compaction + mark(level) fused.
 // ---------------------------------------------------------------------------------------------
-// GATHER: only filter + compact, into `gather_dst` (a shard's exchange slot); level `level` is marked later from
-// the collected list
+// Striped key lists.  The list of level l (the keys that collided at level l-1) is NOT one dense array: it is cut into
+// st->n_regions "regions" of st->reg_cap key slots each (buf[l & 1] + r * reg_cap), with reg_cnt[l & 1][r] keys in
+// region r.  Region r of level l holds exactly the survivors of region r of level l-1 (level 1: of the input tiles
+// r, r + R, r + 2R, ...), so a region never receives more keys than its predecessor held: reg_cap = the tiles of the
+// first source per region x 256 can never overflow, and whoever filters region r appends to it with a private cursor.
+// Why: with one dense list every 256 survivors cost a reservation on ONE global cursor -- 174 k same-address atomics
+// for level 1 of a 1e8-key build -- and those alone held the pass at 0.94 ms against 0.69 ms without them
+// (tools/microbench_pass.cu, profiles/r02a_summary.md); ordering does not matter (only the redo SET feeds the next
+// level).  Lists that other kernels produce stay dense (the input, scatter_kernel's output after the
+// bucketed levels, the collected list of a sharded build): list_is_striped() tells which kind level l has.
+//
+// Schedule: every WARP runs on its own -- a region at a time, 256-key tiles through a two-deep TMA ring of its own
+// (cp.async.bulk + mbarrier), all collide probes of a tile issued before anything is waited for, ballot compaction
+// into a per-warp ring in shared memory, and whenever 256 survivors are staged: coalesced append to the warp's region
+// plus the fetch_or's of level l for them, whose results are consumed one flush later (by then they have arrived).
+// No block barrier, no shared cursor: the warps of an SM drift apart, so the probes of some are in flight together
+// with the atomics of others.
+// GATHER: only filter + compact, into the DENSE array `gather_dst` (a shard's exchange slot, read by its peers as one
+// array: reservations on st->redo_count, at most 2^20 keys); level `level` is marked later from the collected list.
+#ifndef BPHF_PASS_CTAS
+#define BPHF_PASS_CTAS 2  // CTAs per SM of the level kernels: 64 KB of shared memory each, the rest of the array stays L1
+#endif
+constexpr int WP_TILE = 32 * PASS_KPT;        // 256 keys per warp tile (2 KB)
+constexpr int WP_RING = 2 * WP_TILE;          // survivors staged per warp (power of two)
+constexpr int WP_WARPS = PASS_THREADS / 32;
+constexpr size_t PASS_SMEM_BYTES = (size_t)WP_WARPS * (WP_RING + 2 * WP_TILE) * 8 + WP_WARPS * 2 * 8;
+
+template <bool BIG> struct SlotIdx { typedef uint32_t type; };
+template <> struct SlotIdx<true> { typedef uint64_t type; };
+
+// level `level`'s key list is striped iff a filter pass wrote it (see above)
+__device__ __forceinline__ bool list_is_striped(const BuildState* st, uint32_t level) {
+    return level >= 1 && __ldcg(&st->lv[level - 1].b_range) == 0 && __ldcg(&st->list_ready_level) != level;
+}
+
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+
 template <bool MAYBE_BIG, bool GATHER = false, class KC = KeyCfg>
 __device__ __forceinline__ void pass_body(BuildState* __restrict__ st, uint32_t level, const uint64_t* __restrict__ user_keys,
                                           uint64_t* __restrict__ buf0, uint64_t* __restrict__ buf1,
                                           uint32_t* __restrict__ a32, uint32_t* __restrict__ c32,
                                           uint64_t* __restrict__ gather_dst = nullptr,
                                           const uint64_t* __restrict__ src_chunk = nullptr, uint64_t chunk_keys = 0) {
-    // ring[b]: TMA destination of a key tile, and -- once every thread holds its keys in registers -- the
-    // compaction stage of that same tile
-    __shared__ __align__(128) uint64_t ring[2][PASS_TILE];
-    __shared__ __align__(8) uint64_t mbar[2];
-    __shared__ uint32_t warp_tot[PASS_THREADS / 32];
-    __shared__ uint64_t sh_base;
+    typedef typename SlotIdx<MAYBE_BIG>::type slot_t;
+    extern __shared__ __align__(128) unsigned char pass_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint64_t* __restrict__ ring = reinterpret_cast<uint64_t*>(pass_smem) + warp * WP_RING;
+    uint64_t* __restrict__ stage = reinterpret_cast<uint64_t*>(pass_smem) + WP_WARPS * WP_RING + warp * 2 * WP_TILE;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(pass_smem) + WP_WARPS * (WP_RING + 2 * WP_TILE) + warp * 2;
 
-    // level descriptors are written by another CTA earlier in the same launch when this runs inside the
-    // persistent cascade kernel: read them through L2
     const KC kc(st->kc);
     const LevelDesc* pv = &st->lv[level - 1];
     const LevelDesc* cu = &st->lv[level];
-    // src_chunk: one chunk of the previous level's keys (streamed ingest); otherwise the whole list
+    // (descriptors and lists may have been written by another CTA earlier in the same launch: read through L2)
     const uint64_t p_bits = __ldcg(&pv->bits), p_sp0 = __ldcg(&pv->sp0), p_off32 = __ldcg(&pv->word_off) * 2;
-    const uint64_t k_src = src_chunk ? chunk_keys : __ldcg(&pv->k_loc);
     const uint64_t c_bits = __ldcg(&cu->bits), c_sp0 = __ldcg(&cu->sp0), c_off32 = __ldcg(&cu->word_off) * 2;
     const bool p_big = MAYBE_BIG && (p_bits >> 32) != 0;
     const bool c_big = MAYBE_BIG && (c_bits >> 32) != 0;
-    const uint64_t* __restrict__ src = src_chunk ? src_chunk : (level == 1) ? user_keys : (((level - 1) & 1) ? buf1 : buf0);
+    const uint32_t R = __ldcg(&st->n_regions);
+    const uint64_t reg_cap = __ldcg(&st->reg_cap);
+    uint32_t* __restrict__ reg_cnt = st->reg_cnt;   // [2][R]
+    // ---- source: one chunk of the input (streamed ingest), a dense list (the input, a scatter / collect output) or the
+    // striped list the previous filter pass wrote
+    const bool src_striped = !src_chunk && list_is_striped(st, level - 1);
+    const uint64_t* __restrict__ src =
+        src_chunk ? src_chunk : (level == 1) ? user_keys : (((level - 1) & 1) ? buf1 : buf0);
+    const uint64_t k_dense = src_chunk ? chunk_keys : __ldcg(&pv->k_loc);   // dense sources only
+    const uint64_t dense_tiles = (k_dense + WP_TILE - 1) / WP_TILE;
+    const uint32_t* __restrict__ src_cnt = reg_cnt + (size_t)((level - 1) & 1) * R;
     uint64_t* __restrict__ dst = GATHER ? gather_dst : ((level & 1) ? buf1 : buf0);
-    const uint64_t dst_cap = GATHER ? GATHER_MAX_KEYS : __ldcg(&st->list_cap[level & 1]);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-
-    const uint64_t n_tiles = (k_src + PASS_TILE - 1) / PASS_TILE;
-    // full tiles of a 16-byte aligned source come through the TMA ring; a partial last tile (or an unaligned
-    // caller buffer) through plain loads
-    const bool tma_ok = (reinterpret_cast<uintptr_t>(src) & 15) == 0;
-    auto issue = [&](uint64_t t, int b) {
-        if (tma_ok && t < n_tiles && (t + 1) * PASS_TILE <= k_src) {
-            mbar_expect_tx(&mbar[b], PASS_TILE * 8);
-            bulk_load(ring[b], src + t * PASS_TILE, PASS_TILE * 8, &mbar[b]);
+    uint32_t* __restrict__ dst_cnt = reg_cnt + (size_t)(level & 1) * R;
+    const bool append = src_chunk != nullptr;  // streamed ingest: the chunks of one level accumulate in the regions
+    if (!GATHER && !src_striped && !append) {
+        // a dense source decides what a region may receive: uniform check, before anything is written
+        const uint64_t per = (dense_tiles + R - 1) / R;
+        if (per * WP_TILE > reg_cap) {
+            if (blockIdx.x == 0 && threadIdx.x == 0) {
+                st->status = ST_NEED_LIST;
+                st->need = (per * WP_TILE + WP_TILE) * R;
+            }
+            return;
         }
+    }
+    uint32_t* __restrict__ a_lv = a32 + c_off32;        // level l's occupancy words
+    uint32_t* __restrict__ c_lv = c32 + c_off32;        // level l's collision words
+    const uint32_t* __restrict__ c_pv = c32 + p_off32;  // level l-1's collision words (final)
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const bool src_aligned = (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+
+    uint32_t head = 0, n_st = 0;   // warp-uniform: first staged survivor, number of staged survivors
+    slot_t aidx[PASS_KPT];         // slots of the fetch_or's in flight ...
+    uint32_t old[PASS_KPT];        // ... and the words they return
+    uint32_t amask = 0;            // which of them exist
+#pragma unroll
+    for (int j = 0; j < PASS_KPT; j++) {
+        aidx[j] = 0;
+        old[j] = 0;
+    }
+    // find_collisions (src/lib.rs:429-434), second half: the slot was taken already -> it collides
+    auto settle = [&]() {
+#pragma unroll
+        for (int j = 0; j < PASS_KPT; j++) {
+            const uint32_t m = 1u << ((uint32_t)aidx[j] & 31);
+            if (((amask >> j) & 1u) && (old[j] & m)) red_or_u32(c_lv + (aidx[j] >> 5), m);
+        }
+        amask = 0;
     };
-    if (threadIdx.x == 0) {
+    // rayon filter_map().collect() (src/lib.rs:374-377): `cnt` staged keys go to level l's list (coalesced), and the
+    // first half of find_collisions of level l runs for them while they are on chip
+    uint64_t out_pos = 0;          // append position (region base + keys written; GATHER: set per flush)
+    auto flush = [&](uint32_t cnt) {
+        settle();
+        bool ok = true;
+        if (GATHER) {
+            unsigned long long t = 0;
+            if (lane == 0) t = atomicAdd((unsigned long long*)&st->redo_count, (unsigned long long)cnt);
+            out_pos = __shfl_sync(0xffffffffu, t, 0);
+            if (out_pos + cnt > GATHER_MAX_KEYS) {
+                if (lane == 0) st->status = ST_ERR_LIST_OVERFLOW;
+                ok = false;
+            }
+        }
+        if (ok) {
+#pragma unroll
+            for (int j = 0; j < PASS_KPT; j++) {
+                const uint32_t i = lane + 32 * j;
+                if (i < cnt) {
+                    const uint64_t kk = ring[(head + i) & (WP_RING - 1)];
+                    dst[out_pos + i] = kk;
+                    if (GATHER) continue;
+                    const uint64_t idx = c_big ? level_index<true>(kc, c_sp0, kk, c_bits) : level_index<false>(kc, c_sp0, kk, c_bits);
+                    aidx[j] = (slot_t)idx;
+                    amask |= 1u << j;
+                }
+            }
+            if (!GATHER) {
+#pragma unroll
+                for (int j = 0; j < PASS_KPT; j++)
+                    if ((amask >> j) & 1u) old[j] = atomicOr(a_lv + (aidx[j] >> 5), 1u << ((uint32_t)aidx[j] & 31));
+            }
+        }
+        out_pos += cnt;
+        head = (head + cnt) & (WP_RING - 1);
+        n_st -= cnt;
+        __syncwarp();  // the ring entries just read may be overwritten by the next tile's survivors
+    };
+
+    // ---- TMA key ring of this warp: tile j of the current region lands in stage[j & 1]
+    if (lane == 0) {
         mbar_init(&mbar[0], 1);
         mbar_init(&mbar[1], 1);
         fence_mbar_init();
         fence_proxy_async();
-        issue(blockIdx.x, 0);
-        issue((uint64_t)blockIdx.x + gridDim.x, 1);
+        fence_proxy_async_global();  // lists written with ordinary stores (earlier in this launch) are read by bulk copies
     }
-    __syncthreads();
-    uint32_t phase = 0;  // bit b: parity of mbar[b]'s next completion
-    uint32_t it = 0;
-    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
-        const int rb = it & 1;
-        uint64_t* __restrict__ stage = ring[rb];
-        const uint64_t base = tile * PASS_TILE + threadIdx.x;
-        uint64_t key[PASS_KPT];
-        uint32_t cw[PASS_KPT], sh[PASS_KPT];
-        if (tma_ok && (tile + 1) * PASS_TILE <= k_src) {
-            mbar_wait(&mbar[rb], (phase >> rb) & 1u);
-            phase ^= 1u << rb;
-#pragma unroll
-            for (int j = 0; j < PASS_KPT; j++) key[j] = stage[threadIdx.x + j * PASS_THREADS];
+    __syncwarp();
+    uint32_t phase = 0;        // bit b: parity of mbar[b]'s next completion
+    uint64_t total = 0;        // keys this warp appended (all its regions)
+
+    const uint64_t n_gw = (uint64_t)gridDim.x * WP_WARPS;
+    for (uint64_t r = (uint64_t)blockIdx.x * WP_WARPS + warp; r < R; r += n_gw) {
+        // tiles of region r: (pointer, valid keys) of tile j
+        uint64_t n_rt;          // number of tiles
+        uint64_t cnt_src = 0;   // striped: keys in the source region
+        if (src_striped) {
+            cnt_src = __ldcg(src_cnt + r);
+            n_rt = (cnt_src + WP_TILE - 1) / WP_TILE;
         } else {
-#pragma unroll
-            for (int j = 0; j < PASS_KPT; j++) {
-                const uint64_t i = base + (uint64_t)j * PASS_THREADS;
-                key[j] = (i < k_src) ? ld_stream_u64(src + i) : 0;
+            n_rt = r < dense_tiles ? (dense_tiles - r + R - 1) / R : 0;
+        }
+        auto tile_ptr = [&](uint64_t j) -> const uint64_t* {
+            return src_striped ? src + r * reg_cap + j * WP_TILE : src + (r + j * R) * WP_TILE;
+        };
+        auto tile_valid = [&](uint64_t j) -> uint32_t {
+            const uint64_t left = src_striped ? cnt_src - j * WP_TILE : k_dense - (r + j * R) * WP_TILE;
+            return left < (uint64_t)WP_TILE ? (uint32_t)left : (uint32_t)WP_TILE;
+        };
+        // a tile comes through the copy engine when it is whole (a striped region may be over-read by one key: the
+        // slot exists) and 16-byte aligned; otherwise with plain loads
+        auto tile_tma = [&](uint64_t j) -> bool {
+            return src_striped ? true : (src_aligned && tile_valid(j) == (uint32_t)WP_TILE);
+        };
+        auto issue = [&](uint64_t j) {
+            if (j < n_rt && tile_tma(j) && lane == 0) {
+                const uint32_t bytes = ((tile_valid(j) + 1u) & ~1u) * 8u;
+                mbar_expect_tx(&mbar[j & 1], bytes);
+                bulk_load(stage + (j & 1) * WP_TILE, tile_ptr(j), bytes, &mbar[j & 1]);
             }
-        }
-        // Context::filter (src/lib.rs:443-452): does this key's level-(l-1) slot collide?
+        };
+        const uint64_t written0 = (append && !GATHER) ? (uint64_t)__ldcg(dst_cnt + r) : 0;
+        if (!GATHER) out_pos = r * reg_cap + written0;
+        const uint64_t region_first = out_pos;
+        issue(0);
+        issue(1);
+        for (uint64_t j = 0; j < n_rt; j++) {
+            const int b = (int)(j & 1);
+            const uint32_t valid = tile_valid(j);
+            uint64_t key[PASS_KPT];
+            if (tile_tma(j)) {
+                mbar_wait(&mbar[b], (phase >> b) & 1u);
+                phase ^= 1u << b;
 #pragma unroll
-        for (int j = 0; j < PASS_KPT; j++) {
-            const uint64_t idx = p_big ? level_index<true>(kc, p_sp0, key[j], p_bits) : level_index<false>(kc, p_sp0, key[j], p_bits);
-            cw[j] = __ldcg(c32 + p_off32 + (idx >> 5));
-            sh[j] = (uint32_t)idx & 31;
-        }
-        uint32_t flags = 0;
+                for (int q = 0; q < PASS_KPT; q++) key[q] = stage[b * WP_TILE + lane + 32 * q];
+                __syncwarp();
+                if (lane == 0) fence_proxy_async();
+            } else {
+                const uint64_t* __restrict__ tp = tile_ptr(j);
 #pragma unroll
-        for (int j = 0; j < PASS_KPT; j++) {
-            const uint64_t i = base + (uint64_t)j * PASS_THREADS;
-            if (i < k_src && ((cw[j] >> sh[j]) & 1u)) flags |= 1u << j;
-        }
-        // block-wide exclusive scan of per-thread counts (warp shuffle scan + 8 warp totals)
-        const uint32_t cnt = __popc(flags);
-        uint32_t incl = cnt;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += t;
-        }
-        if (lane == 31) warp_tot[warp] = incl;
-        __syncthreads();
-        uint32_t warp_off = 0, total = 0;
-#pragma unroll
-        for (int w = 0; w < PASS_THREADS / 32; w++) {
-            const uint32_t t = warp_tot[w];
-            if (w < warp) warp_off += t;
-            total += t;
-        }
-        uint32_t pos = warp_off + incl - cnt;
-#pragma unroll
-        for (int j = 0; j < PASS_KPT; j++)
-            if (flags & (1u << j)) stage[pos++] = key[j];
-        if (threadIdx.x == 0)
-            sh_base = (uint64_t)atomicAdd((unsigned long long*)&st->redo_count, (unsigned long long)total);
-        __syncthreads();
-        const uint64_t out = sh_base;
-        // an unsharded build knows k(level) before this kernel runs and sized the list for it; a shard of a
-        // sharded build only has an estimate of its own share
-        if (out + total > dst_cap) {
-            if (threadIdx.x == 0) {
-                st->status = ST_ERR_LIST_OVERFLOW;
-                fence_proxy_async();
-                issue(tile + 2 * (uint64_t)gridDim.x, rb);  // keep the ring protocol intact on the error path
+                for (int q = 0; q < PASS_KPT; q++) key[q] = (lane + 32u * q < valid) ? ld_stream_u64(tp + lane + 32 * q) : 0;
             }
-            __syncthreads();
-            continue;
-        }
-        // rayon filter_map().collect() (src/lib.rs:374-377): append to level l's list (coalesced), and
-        // find_collisions of level l for the same key while it is still on chip
-        {
-            uint64_t w[PASS_KPT];
-            uint32_t m[PASS_KPT], old[PASS_KPT];
+            issue(j + 2);  // stage b is free again
+            // Context::filter (src/lib.rs:443-452): does this key's level-(l-1) slot collide?  All probes of the tile
+            // are issued before anything else is waited for
+            uint32_t cw[PASS_KPT];
+            uint64_t shs = 0;  // 8 x 5 bits: position of each key's bit in its probe word
 #pragma unroll
-            for (int j = 0; j < PASS_KPT; j++) {
-                const uint32_t i = threadIdx.x + j * PASS_THREADS;
-                m[j] = 0;
-                w[j] = c_off32;
-                if (i < total) {
-                    const uint64_t kk = stage[i];
-                    dst[out + i] = kk;
-                    if (GATHER) continue;
-                    const uint64_t idx = c_big ? level_index<true>(kc, c_sp0, kk, c_bits) : level_index<false>(kc, c_sp0, kk, c_bits);
-                    w[j] = c_off32 + (idx >> 5);
-                    m[j] = 1u << (idx & 31);
-                }
+            for (int q = 0; q < PASS_KPT; q++) {
+                const uint64_t idx = p_big ? level_index<true>(kc, p_sp0, key[q], p_bits) : level_index<false>(kc, p_sp0, key[q], p_bits);
+                cw[q] = (lane + 32u * q < valid) ? __ldcg(c_pv + (idx >> 5)) : 0u;
+                shs |= (uint64_t)((uint32_t)idx & 31) << (5 * q);
             }
+            if (n_st >= WP_TILE) flush(WP_TILE);   // the previous tiles' survivors, while the probes are in flight
 #pragma unroll
-            for (int j = 0; j < PASS_KPT; j++) {
-                old[j] = 0;
-                if (m[j]) old[j] = atomicOr(a32 + w[j], m[j]);
+            for (int q = 0; q < PASS_KPT; q++) {
+                const bool redo = (cw[q] >> ((uint32_t)(shs >> (5 * q)) & 31)) & 1u;
+                const uint32_t mk = __ballot_sync(0xffffffffu, redo);
+                if (redo) ring[(head + n_st + __popc(mk & lt_mask)) & (WP_RING - 1)] = key[q];
+                n_st += __popc(mk);
             }
-#pragma unroll
-            for (int j = 0; j < PASS_KPT; j++)
-                if (old[j] & m[j]) red_or_u32(c32 + w[j], m[j]);
+            __syncwarp();
         }
-        __syncthreads();
-        // ring[rb] is free again: fetch the tile this CTA handles after the next one
-        if (threadIdx.x == 0) {
-            fence_proxy_async();
-            issue(tile + 2 * (uint64_t)gridDim.x, rb);
+        // end of the region: everything staged belongs to it
+        if (n_st >= WP_TILE) flush(WP_TILE);
+        if (n_st) flush(n_st);
+        if (!GATHER) {
+            const uint64_t wrote = out_pos - region_first;
+            if (lane == 0) dst_cnt[r] = (uint32_t)(written0 + wrote);
+            total += wrote;
         }
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
+    settle();
+    if (!GATHER && lane == 0 && total) atomicAdd((unsigned long long*)&st->redo_count, (unsigned long long)total);
+    fence_proxy_async_global();  // this warp's list stores, before a later bulk copy (async proxy) reads them
+    __syncwarp();
+    if (lane == 0) {
         mbar_inval(&mbar[0]);
         mbar_inval(&mbar[1]);
     }
-    __syncthreads();
 }
 
+template <class KC> struct PassOcc { static constexpr int ctas = BPHF_PASS_CTAS; };
+template <> struct PassOcc<StreamCfg> { static constexpr int ctas = 1; };  // the stream hash walks the key's bytes: more registers
+
 template <bool MAYBE_BIG, class KC = KeyCfg>
-__global__ void __launch_bounds__(PASS_THREADS)
+__global__ void __launch_bounds__(PASS_THREADS, PassOcc<KC>::ctas)
     pass_kernel(BuildState* __restrict__ st, uint32_t level, const uint64_t* __restrict__ user_keys,
                 uint64_t* __restrict__ buf0, uint64_t* __restrict__ buf1, uint32_t* __restrict__ a32,
                 uint32_t* __restrict__ c32) {
@@ -418,7 +509,7 @@ __global__ void __launch_bounds__(PASS_THREADS)
 // streamed ingest (host key sets that stay out of HBM): filter(0) + compaction + mark(1) over ONE chunk of the level-0
 // keys; the survivors of all chunks accumulate in level 1's list, which is where the key set becomes device resident
 template <bool MAYBE_BIG>
-__global__ void __launch_bounds__(PASS_THREADS)
+__global__ void __launch_bounds__(PASS_THREADS, BPHF_PASS_CTAS)
     pass_chunk_kernel(BuildState* __restrict__ st, const uint64_t* __restrict__ chunk, uint64_t chunk_keys,
                       uint64_t* __restrict__ buf0, uint64_t* __restrict__ buf1, uint32_t* __restrict__ a32,
                       uint32_t* __restrict__ c32) {
@@ -530,15 +621,31 @@ __device__ __forceinline__ void grid_barrier(BuildState* st) {
             __threadfence();
             atomicAdd(&st->bar_gen, 1u);
         } else {
-            while (ld_volatile_u32(&st->bar_gen) == gen) __nanosleep(40);
+            while (ld_volatile_u32(&st->bar_gen) == gen) __nanosleep(100);
         }
         __threadfence();
     }
     __syncthreads();
 }
 
+// -DBPHF_TRACE: per-CTA timestamps of the cascade phases (measurement builds only; tools/cascade_trace.py)
+#ifdef BPHF_TRACE
+constexpr int TRACE_LEVELS = 16, TRACE_POINTS = 5, TRACE_CTAS = 1024;
+__device__ uint64_t g_cascade_trace[TRACE_LEVELS][TRACE_POINTS][TRACE_CTAS];
+__device__ __forceinline__ void trace_point(uint32_t level, int point) {
+    if (threadIdx.x == 0 && level < TRACE_LEVELS && blockIdx.x < TRACE_CTAS) {
+        uint64_t t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_cascade_trace[level][point][blockIdx.x] = t;
+    }
+}
+#define TRACE_POINT(level, point) trace_point(level, point)
+#else
+#define TRACE_POINT(level, point)
+#endif
+
 template <bool MAYBE_BIG>
-__global__ void __launch_bounds__(PASS_THREADS)
+__global__ void __launch_bounds__(PASS_THREADS, BPHF_PASS_CTAS)
     cascade_kernel(BuildState* __restrict__ st, const uint64_t* __restrict__ user_keys, uint64_t* __restrict__ buf0,
                    uint64_t* __restrict__ buf1, uint64_t* __restrict__ words, uint64_t* __restrict__ coll,
                    uint32_t* __restrict__ blockpop) {
@@ -556,11 +663,20 @@ __global__ void __launch_bounds__(PASS_THREADS)
         if (status != ST_RUNNING || level == 0 || level >= tail || level > BPHF_MAX_LEVELS) break;
         // only plain levels with a plain predecessor (uniform: written before the previous grid barrier)
         if (__ldcg(&st->lv[level - 1].b_range) != 0 || __ldcg(&st->lv[level].b_range) != 0) break;
+        TRACE_POINT(level, 0);
         pass_body<MAYBE_BIG>(st, level, user_keys, buf0, buf1, reinterpret_cast<uint32_t*>(words),
                              reinterpret_cast<uint32_t*>(coll));
+        TRACE_POINT(level, 1);
         grid_barrier(st);
+        TRACE_POINT(level, 2);
+        // the pass may have stopped before writing anything (a list buffer has to grow first): uniform, set before the barrier
+        if (threadIdx.x == 0) ctl[3] = ld_volatile_u32(&st->status);
+        __syncthreads();
+        if (ctl[3] != ST_RUNNING) break;
         finalize_body(st, level, words, coll, blockpop);
+        TRACE_POINT(level, 3);
         grid_barrier(st);
+        TRACE_POINT(level, 4);
     }
 }
 
@@ -616,13 +732,24 @@ __global__ void __launch_bounds__(TAIL_THREADS)
         const uint64_t p_bits = pv->bits, p_sp0 = pv->sp0, p_off32 = pv->word_off * 2, k_src = pv->k_in;
         const bool p_big = (p_bits >> 32) != 0;
         const uint64_t* src = (level == 1) ? user_keys : (((level - 1) & 1) ? buf1 : buf0);
-        for (uint64_t i = tid; i < k_src; i += TAIL_THREADS) {
-            const uint64_t key = src[i];
+        auto take = [&](uint64_t key) {
             const uint64_t idx = p_big ? hashmod_big(kc, p_sp0, key, p_bits) : (uint64_t)hashmod_small(kc, p_sp0, key, (uint32_t)p_bits);
             if ((c32[p_off32 + (idx >> 5)] >> (idx & 31)) & 1u) {
                 const uint32_t pos = atomicAdd(&s.count, 1u);
                 if (pos < TAIL_MAX_KEYS) s.keys[0][pos] = key;
             }
+        };
+        if (list_is_striped(st, level - 1)) {
+            // the previous filter pass left level-1's keys in regions (pass_body): a few keys per region by now
+            const uint32_t R = st->n_regions;
+            const uint64_t reg_cap = st->reg_cap;
+            const uint32_t* cnt = st->reg_cnt + (size_t)((level - 1) & 1) * R;
+            for (uint32_t r = tid; r < R; r += TAIL_THREADS) {
+                const uint32_t n_r = cnt[r];
+                for (uint32_t i = 0; i < n_r; i++) take(src[(uint64_t)r * reg_cap + i]);
+            }
+        } else {
+            for (uint64_t i = tid; i < k_src; i += TAIL_THREADS) take(src[i]);
         }
     }
     __syncthreads();

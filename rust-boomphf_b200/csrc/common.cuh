@@ -52,14 +52,21 @@ enum BuildStatus : uint32_t {
 
 // device-resident build state; the level loop runs without host round trips (kernels for all
 // expected levels are enqueued up front and read their sizes from here)
-struct BuildState {
+// Layout: the words that thousands of warps update or poll at the same time sit in 128-byte lines of their own.  They
+// used to share the first line of the struct: the CTAs waiting at the cascade's grid barrier poll bar_gen, and every
+// update of the append cursor by the CTAs still working queued behind those polls in the same L2 slice
+// (profiles/r02a_summary.md).
+struct alignas(128) BuildState {
     uint32_t status;
     uint32_t n_levels;    // levels completed so far
     uint32_t tail_level;  // first level owned by the single-CTA tail kernel (0xffffffff: none yet)
-    uint32_t fin_ticket;  // "last block done" ticket of the finalize kernel
-    uint64_t redo_count;  // append cursor of the redo list being written by the current pass
-    uint64_t uniq_count;  // popcount(a & ~collide) of the level being finalized
-    uint64_t words_used;  // arena words handed out so far (multiple of 8)
+    uint32_t pad0_;
+    alignas(128) uint64_t redo_count;  // append cursor of the redo list being written by the current pass
+    alignas(128) uint64_t uniq_count;  // popcount(a & ~collide) of the level being finalized
+    uint32_t fin_ticket;               // "last block done" ticket of the finalize kernel
+    alignas(128) uint32_t bar_count;   // grid barrier of the persistent cascade kernel: arrivals ...
+    alignas(128) uint32_t bar_gen;     // ... and the generation the waiting CTAs poll
+    alignas(128) uint64_t words_used;  // arena words handed out so far (multiple of 8)
     uint64_t words_cap;   // arena capacity in words (excluding the tail reserve)
     uint64_t list_cap[2]; // capacity (keys) of redo buffers: level l's key list lives in buf[l & 1]
     uint64_t seed0;       // starting_seed.unwrap_or(0)
@@ -70,7 +77,6 @@ struct BuildState {
     uint32_t bucket_slots;     // CTAs that run concurrently (SM count x 2): bucket counts are multiples of it
     uint32_t bucket_enable;
     uint64_t bucket_keys_seen; // sum of bucket fills seen by the mark kernel (consistency check)
-    uint32_t bar_count, bar_gen;  // grid barrier of the persistent cascade kernel
     uint32_t shard_rank;       // sharded build: this shard's index ...
     uint32_t shard_world;      // ... of shard_world shards (1 = unsharded)
     uint32_t gather_level;     // sharded: level at which all remaining keys are collected on every shard (host plan)
@@ -82,7 +88,11 @@ struct BuildState {
     uint64_t chunk_max_iters;  // max_iters of the chunked levels (chunk_has_max != 0)
     uint32_t chunk_mode, chunk_has_max;
     uint32_t switch_level;     // first level built with gamma 1.7 (NO_LEVEL: not reached yet)
-    uint32_t pad2_;
+    // striped key lists (build_kernels.cuh, pass_body): n_regions regions of reg_cap key slots in each list buffer,
+    // reg_cnt[(l & 1) * n_regions + r] keys of level l's list in region r
+    uint32_t n_regions;
+    uint64_t reg_cap;
+    uint32_t* reg_cnt;
     KeyCfg kc;                 // how the keys' Hash impl feeds the hasher (u64 unless built through bphf_build_keys)
     double shard_frac;         // this shard's share of the keys (n_local / n_global; 1 unsharded): sizes bucket regions
     LevelDesc lv[BPHF_MAX_LEVELS + 1];

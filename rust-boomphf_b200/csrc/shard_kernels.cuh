@@ -184,13 +184,23 @@ __global__ void __launch_bounds__(TAIL_THREADS)
         const uint64_t p_bits = pv->bits, p_sp0 = pv->sp0, p_off32 = pv->word_off * 2, k_src = pv->k_loc;
         const bool p_big = (p_bits >> 32) != 0;
         const uint64_t* src = (level == 1) ? user_keys : (((level - 1) & 1) ? buf1 : buf0);
-        for (uint64_t i = tid; i < k_src; i += TAIL_THREADS) {
-            const uint64_t key = src[i];
+        auto take = [&](uint64_t key) {
             const uint64_t idx = p_big ? hashmod_big(st->kc, p_sp0, key, p_bits) : (uint64_t)hashmod_small(st->kc, p_sp0, key, (uint32_t)p_bits);
             if ((c32[p_off32 + (idx >> 5)] >> (idx & 31)) & 1u) {
                 const uint32_t pos = atomicAdd(&count, 1u);
                 if (pos < TAIL_MAX_KEYS) xk[8 + pos] = key;
             }
+        };
+        if (list_is_striped(st, level - 1)) {
+            const uint32_t R = st->n_regions;
+            const uint64_t reg_cap = st->reg_cap;
+            const uint32_t* cnt = st->reg_cnt + (size_t)((level - 1) & 1) * R;
+            for (uint32_t r = tid; r < R; r += TAIL_THREADS) {
+                const uint32_t n_r = cnt[r];
+                for (uint32_t i = 0; i < n_r; i++) take(src[(uint64_t)r * reg_cap + i]);
+            }
+        } else {
+            for (uint64_t i = tid; i < k_src; i += TAIL_THREADS) take(src[i]);
         }
     }
     __syncthreads();
@@ -207,7 +217,7 @@ __global__ void __launch_bounds__(TAIL_THREADS)
 // whole remaining key set and finishes the cascade with the unsharded kernels, redundantly -> identical replicas.
 // ---------------------------------------------------------------------------------------------
 template <bool MAYBE_BIG>
-__global__ void __launch_bounds__(PASS_THREADS)
+__global__ void __launch_bounds__(PASS_THREADS, BPHF_PASS_CTAS)
     shard_gather_kernel(BuildState* __restrict__ st, uint32_t level, const uint64_t* __restrict__ user_keys,
                         uint64_t* __restrict__ buf0, uint64_t* __restrict__ buf1, uint32_t* __restrict__ c32,
                         uint64_t* __restrict__ xk) {

@@ -36,15 +36,16 @@ def _one(usage, *parts):
 
 @pytest.mark.parametrize("parts,max_reg", [
     (("mark_list_kernelILb0E", "KeyCfg"), 40),     # level 0: 6 CTAs of 256 threads per SM
-    (("pass_kernelILb0E", "KeyCfg"), 40),
-    (("cascade_kernelILb0E",), 64),                # 4 CTAs per SM (32 KB TMA ring each)
+    (("pass_kernelILb0E", "KeyCfg"), 128),         # level kernels: 2 CTAs of 256 threads per SM (64 KB of warp rings each)
+    (("cascade_kernelILb0E",), 128),
     (("query_sync_kernel",), 64),                  # 8 CTAs of 128 threads per SM
     (("tail_kernel", "KeyCfg"), 64),
 ])
 def test_hot_kernels_keep_their_registers_and_do_not_spill(usage, parts, max_reg):
     reg, stack, _ = _one(usage, *parts)
     assert reg <= max_reg, (parts, reg)
-    assert stack == 0, (parts, "spills / stack frame", stack)
+    # the level kernels may park a few loop-invariant words (<= 32 bytes); anything more means the pipeline state spilled
+    assert stack <= (32 if max_reg == 128 else 0), (parts, "spills / stack frame", stack)
 
 
 def test_stream_key_variants_are_separate_kernels(usage):
@@ -54,11 +55,12 @@ def test_stream_key_variants_are_separate_kernels(usage):
     assert not any("cascade_kernel" in k and "StreamCfg" in k for k in usage)
 
 
-def test_ring_kernels_fit_four_ctas_per_sm(usage):
-    # the TMA key ring: 2 stages x 2048 keys x 8 B (+ barriers) of static shared memory, 4 CTAs <= 227 KB
+def test_level_kernels_keep_their_rings_in_dynamic_shared_memory(usage):
+    # per warp: 512 staged survivors + a two-deep TMA key ring of 256-key tiles = 8 KB, 64 KB per CTA, requested at launch
+    # (PASS_SMEM_BYTES); the static part is only control words
     for parts in (("cascade_kernelILb0E",), ("pass_kernelILb0E", "KeyCfg")):
         _, _, shared = _one(usage, *parts)
-        assert 32 * 1024 <= shared <= 36 * 1024
+        assert shared <= 2048
 
 
 def _sass(pkg, usage, *parts):
