@@ -1,7 +1,7 @@
 """Writes the JSON that tools/ref_dump (the cargo project) would print, but computed by the ORACLE -- only to exercise
 tests/test_oracle.py::test_reference_dump_if_present in an image without cargo:
 
-    python tools/ref_dump_emulate.py /tmp/emulated.json && BPHF_REF_DUMP=/tmp/emulated.json python -m pytest tests/test_oracle.py -k reference_dump
+    python tests/golden/ref_dump_emulate.py /tmp/emulated.json && BPHF_REF_DUMP=/tmp/emulated.json python -m pytest tests/test_oracle.py -k reference_dump
 
 Never commit its output as tests/golden/ref_dump.json: that file must come from the real crates."""
 import json
@@ -10,7 +10,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import boomphf_oracle as o
