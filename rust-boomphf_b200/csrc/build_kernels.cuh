@@ -444,8 +444,9 @@ __device__ __forceinline__ void pass_body(BuildState* __restrict__ st, uint32_t 
             if (tile_tma(j)) {
                 mbar_wait(&mbar[b], (phase >> b) & 1u);
                 phase ^= 1u << b;
+                // (slots past the region's count hold whatever was there: a stream key is an INDEX and must be a valid one)
 #pragma unroll
-                for (int q = 0; q < PASS_KPT; q++) key[q] = stage[b * WP_TILE + lane + 32 * q];
+                for (int q = 0; q < PASS_KPT; q++) key[q] = (lane + 32u * q < valid) ? stage[b * WP_TILE + lane + 32 * q] : 0;
                 __syncwarp();
                 if (lane == 0) fence_proxy_async();
             } else {

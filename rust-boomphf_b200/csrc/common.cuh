@@ -36,6 +36,9 @@ struct LevelDesc {
     uint32_t b_count;
     uint32_t b_cap;     // key capacity of each bucket region
     uint32_t pad_;
+    // sharded build, exchange ("owner computes") level: shard g owns bits [g * x_slice_bits, (g + 1) * x_slice_bits) of
+    // the level and marks every shard's keys that fall there (xchg_kernels.cuh); 0 = not an exchange level
+    uint64_t x_slice_bits;
 };
 
 enum BuildStatus : uint32_t {
@@ -93,6 +96,11 @@ struct alignas(128) BuildState {
     uint32_t n_regions;
     uint64_t reg_cap;
     uint32_t* reg_cnt;
+    // sharded build: the first xchg_levels levels are exchange levels (host plan, identical on every shard);
+    // xreg_cnt[(l & 1) * R * SHARD_MAX + r * world + o] = keys of level l that region r of this shard sent to owner o
+    uint32_t xchg_levels;
+    uint32_t x_sub_cap;
+    uint32_t* xreg_cnt;
     KeyCfg kc;                 // how the keys' Hash impl feeds the hasher (u64 unless built through bphf_build_keys)
     double shard_frac;         // this shard's share of the keys (n_local / n_global; 1 unsharded): sizes bucket regions
     LevelDesc lv[BPHF_MAX_LEVELS + 1];
@@ -123,7 +131,13 @@ struct CommDev {
     uint64_t* words[SHARD_MAX];   // level bit vectors (raw a while marking, final a after the merge)
     uint64_t* coll[SHARD_MAX];    // collision bit vectors
     uint64_t* xkeys[SHARD_MAX];   // keys this shard hands to the tail
-    uint64_t* flags[SHARD_MAX];   // flags[p][r * FLAG_STRIDE + {0: epoch, 1: payload, 2: status}] written by shard r
+    uint64_t* flags[SHARD_MAX];   // flags[p][r * FLAG_STRIDE + {0: epoch, 1: payload, 2: status, 3: payload2}] written by shard r
+    // exchange levels (xchg_kernels.cuh): [sender s][region r][x_sub_cap] blocks
+    uint32_t* xidx[SHARD_MAX];    // xidx[p]: slot indices (relative to p's slice) that the shards sent to owner p
+    uint32_t* xcnt[SHARD_MAX];    // xcnt[p][s * R + r]: how many of them block (s, r) holds
+    uint32_t* xbits[SHARD_MAX];   // xbits[p]: survivor bits that the owners returned to sender p, [owner o][region r][x_sub_cap / 32]
+    uint32_t x_sub_cap;           // entries per (sender, region, owner) block; multiple of 256
+    uint32_t x_regions;           // R
 };
 
 // ---- bucket geometry --------------------------------------------------------------------------------
@@ -188,6 +202,11 @@ __host__ __device__ inline void make_level(BuildState* st, uint32_t level, uint6
     d.b_shift = 0;
     d.b_range = d.b_count = d.b_cap = 0;
     d.pad_ = 0;
+    d.x_slice_bits = 0;
+    if (st->shard_world > 1 && level < st->xchg_levels) {
+        const uint64_t slice_words = round_up8((d.n_words + st->shard_world - 1) / st->shard_world);
+        d.x_slice_bits = slice_words * 64;  // <= 2^32 by the host's choice of xchg_levels: slots travel as 32-bit offsets
+    }
 }
 
 }  // namespace bphf

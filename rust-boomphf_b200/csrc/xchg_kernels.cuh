@@ -1,0 +1,380 @@
+// xchg_kernels.cuh -- sharded construction of the levels that do not fit the L2: "owner computes".
+//
+// The OR-collide merge (shard_kernels.cuh) has every shard mark its keys into a FULL-WIDTH (a, collide) pair and then
+// folds the pairs over NVLink.  That is right while the pair fits the L2; beyond it (8 x 1e8 keys: 2 x 170 MB per GPU
+// for level 0) the marks miss to HBM, the keys have to be grouped into thousands of shared-memory buckets first, and
+// the per-GPU bytes grow with the number of GPUs -- weak-scaling efficiency 0.37 at 8 GPUs.  For those
+// levels the roles are turned around, and the per-GPU working set becomes what a single-GPU build of n/G keys has:
+//
+//   shard g OWNS bits [g * slice, (g + 1) * slice) of the level; its slice of (a, collide) stays L2 resident.
+//   xscatter : every shard hashes its keys for the level, routes each key to the owner of its slot, keeps the key in
+//              a local list GROUPED BY OWNER and pushes the slot's offset within the owner's slice (4 bytes) into the
+//              owner's receive buffer over NVLink -- same position in both, so no key ever crosses the link.
+//   (barrier)
+//   xmark    : the owner runs find_collisions (src/lib.rs:429-434) over everything it received: one fetch_or per
+//              offset on its slice, collide update for late arrivals -- the single-GPU level-0 kernel, fed offsets.
+//   xfinalize: a &= ~collide on the slice (Context::filter's a.remove, src/lib.rs:447), unique count, and the final
+//              slice of a is stored into EVERY shard's arena (the all-gather half of the old merge; collide never
+//              leaves the owner).
+//   xbits    : for every received offset the owner looks up the collide bit (Context::filter, src/lib.rs:443-452) and
+//              returns ONE BIT per key to the sender, in arrival order.
+//   (barrier, carrying every owner's unique count: k(l+1) = k(l) - sum, derived identically on every shard)
+//   The next level's entry step (xscatter again, or pass_body / the collect of the merge path) streams the grouped keys
+//   next to the returned bits: the filter costs no random access at all on the sender.
+//
+// NVLink traffic per level: 4 bytes per key out + 1 bit per key back + the a slices (W * 8 * (G-1)/G in per GPU),
+// against 16 W * (G-1)/G in AND out for the fold.  Results are identical (same (cnt >= 1, cnt >= 2) per slot).
+//
+// Layout: sender s, region r (the warp-private regions of pass_body), owner o form one block of x_sub_cap entries:
+//   keys  : sender's buf[l & 1] + ((r * world + o) * x_sub_cap)           (8 B, local)
+//   offsets: owner o's xidx    + ((s * R + r) * x_sub_cap)                (4 B, pushed by the sender)
+//   counts : owner o's xcnt[s * R + r]  and the sender's xreg_cnt[l & 1][r * world + o]
+//   bits  : sender's xbits     + ((o * R + r) * x_sub_cap) / 32           (written by owner o)
+// Blocks are private to one warp on the sending side: no cursor is shared, nothing is reserved atomically.
+#pragma once
+#include "shard_kernels.cuh"
+
+namespace bphf {
+
+constexpr int XS_STAGE = 64;  // keys staged per owner and warp (power of two); flushed 32 at a time
+
+__device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// xscatter_kernel: route this shard's keys of an exchange level to the owners of their slots
+// ---------------------------------------------------------------------------------------------
+template <bool MAYBE_BIG>
+__global__ void __launch_bounds__(PASS_THREADS, BPHF_PASS_CTAS)
+    xscatter_kernel(BuildState* __restrict__ st, uint32_t level, const uint64_t* __restrict__ user_keys,
+                    uint64_t* __restrict__ buf0, uint64_t* __restrict__ buf1, CommDev cd) {
+    if (st->status != ST_RUNNING || st->n_levels != level || level >= st->tail_level) return;
+    const LevelDesc* cu = &st->lv[level];
+    const uint64_t slice_bits = cu->x_slice_bits;
+    if (slice_bits == 0) return;
+    extern __shared__ __align__(128) unsigned char pass_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // same carve-up as pass_body: 4 KB staging (here SHARD_MAX x XS_STAGE keys), two 2 KB key tiles, two mbarriers
+    uint64_t* __restrict__ stg = reinterpret_cast<uint64_t*>(pass_smem) + warp * WP_RING;
+    uint64_t* __restrict__ stage = reinterpret_cast<uint64_t*>(pass_smem) + WP_WARPS * WP_RING + warp * 2 * WP_TILE;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(pass_smem) + WP_WARPS * (WP_RING + 2 * WP_TILE) + warp * 2;
+    static_assert(SHARD_MAX * XS_STAGE <= WP_RING, "per-owner staging must fit the warp's ring");
+
+    const KeyCfg kc(st->kc);
+    const uint64_t c_bits = cu->bits, c_sp0 = cu->sp0;
+    const bool c_big = MAYBE_BIG && (c_bits >> 32) != 0;
+    const uint32_t R = st->n_regions, world = cd.world, me = cd.rank, sub_cap = st->x_sub_cap;
+    const bool xsrc = level >= 1;  // exchange levels are a prefix: the predecessor is one, too
+    const uint64_t* __restrict__ src = xsrc ? (((level - 1) & 1) ? buf1 : buf0) : user_keys;
+    const uint64_t k_dense = st->lv[0].k_loc;
+    const uint64_t dense_tiles = (k_dense + WP_TILE - 1) / WP_TILE;
+    const uint32_t* __restrict__ src_cnt = st->xreg_cnt + (size_t)((level - 1) & 1) * R * SHARD_MAX;
+    const uint32_t* __restrict__ src_bits = cd.xbits[me];
+    uint64_t* __restrict__ dst = (level & 1) ? buf1 : buf0;
+    uint32_t* __restrict__ dst_cnt = st->xreg_cnt + (size_t)(level & 1) * R * SHARD_MAX;
+    const bool src_aligned = (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+
+    if (lane == 0) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        fence_mbar_init();
+        fence_proxy_async();
+        fence_proxy_async_global();
+    }
+    __syncwarp();
+    uint32_t phase = 0;
+    uint64_t total = 0;
+    bool overflow = false;
+    uint32_t n_o[SHARD_MAX], h_o[SHARD_MAX], pos_o[SHARD_MAX];  // per owner: staged keys, ring head, entries written
+
+    auto slot_of = [&](uint64_t key) -> uint64_t {
+        return c_big ? level_index<true>(kc, c_sp0, key, c_bits) : level_index<false>(kc, c_sp0, key, c_bits);
+    };
+    const uint64_t n_gw = (uint64_t)gridDim.x * WP_WARPS;
+    for (uint64_t r = (uint64_t)blockIdx.x * WP_WARPS + warp; r < R; r += n_gw) {
+#pragma unroll
+        for (int o = 0; o < SHARD_MAX; o++) n_o[o] = h_o[o] = pos_o[o] = 0;
+        // `cnt` staged keys of owner o -> the block (r, o): key stays here, its offset in o's slice goes to o
+        auto flush = [&](int o, uint32_t& n, uint32_t& h, uint32_t& pos, uint32_t cnt) {
+            if (pos + cnt > sub_cap) {
+                overflow = true;  // more keys for one owner than the block holds (grossly unbalanced hash / shards)
+            } else if ((uint32_t)lane < cnt) {
+                const uint64_t kk = stg[o * XS_STAGE + ((h + lane) & (XS_STAGE - 1))];
+                const uint64_t loc = slot_of(kk) - (uint64_t)o * slice_bits;
+                dst[((uint64_t)r * world + o) * sub_cap + pos + lane] = kk;
+                cd.xidx[o][((uint64_t)me * R + r) * sub_cap + pos + lane] = (uint32_t)loc;
+            }
+            pos += cnt;
+            h = (h + cnt) & (XS_STAGE - 1);
+            n -= cnt;
+            __syncwarp();
+        };
+        const uint32_t n_seg = xsrc ? world : 1u;
+        for (uint32_t seg = 0; seg < n_seg; seg++) {
+            // tiles of this segment: the shard's share of the input (level 0), or block (r, seg) of the previous level
+            uint64_t n_rt, cnt_src = 0;
+            if (xsrc) {
+                cnt_src = ld_cg_u32(src_cnt + r * world + seg);
+                n_rt = (cnt_src + WP_TILE - 1) / WP_TILE;
+            } else {
+                n_rt = r < dense_tiles ? (dense_tiles - r + R - 1) / R : 0;
+            }
+            const uint64_t blk = ((uint64_t)r * world + seg) * sub_cap;                  // xsrc: key block
+            const uint32_t* __restrict__ bits = src_bits + (((uint64_t)seg * R + r) * sub_cap) / 32;  // xsrc: its survivor bits
+            auto tile_ptr = [&](uint64_t j) -> const uint64_t* {
+                return xsrc ? src + blk + j * WP_TILE : src + (r + j * R) * WP_TILE;
+            };
+            auto tile_valid = [&](uint64_t j) -> uint32_t {
+                const uint64_t left = xsrc ? cnt_src - j * WP_TILE : k_dense - (r + j * R) * WP_TILE;
+                return left < (uint64_t)WP_TILE ? (uint32_t)left : (uint32_t)WP_TILE;
+            };
+            auto tile_tma = [&](uint64_t j) -> bool { return xsrc ? true : (src_aligned && tile_valid(j) == (uint32_t)WP_TILE); };
+            auto issue = [&](uint64_t j) {
+                if (j < n_rt && tile_tma(j) && lane == 0) {
+                    const uint32_t bytes = ((tile_valid(j) + 1u) & ~1u) * 8u;
+                    mbar_expect_tx(&mbar[j & 1], bytes);
+                    bulk_load(stage + (j & 1) * WP_TILE, tile_ptr(j), bytes, &mbar[j & 1]);
+                }
+            };
+            issue(0);
+            issue(1);
+            for (uint64_t j = 0; j < n_rt; j++) {
+                const int b = (int)(j & 1);
+                const uint32_t valid = tile_valid(j);
+                uint64_t* __restrict__ tile = stage + b * WP_TILE;
+                if (tile_tma(j)) {
+                    mbar_wait(&mbar[b], (phase >> b) & 1u);
+                    phase ^= 1u << b;
+                } else {
+                    const uint64_t* __restrict__ tp = tile_ptr(j);
+#pragma unroll
+                    for (int q = 0; q < PASS_KPT; q++)
+                        if (lane + 32u * q < valid) tile[lane + 32 * q] = ld_stream_u64(tp + lane + 32 * q);
+                    __syncwarp();
+                }
+#pragma unroll 1
+                for (int q = 0; q < PASS_KPT; q++) {
+                    bool live = lane + 32u * q < valid;
+                    // Context::filter of the previous level: the owner's answer, one bit per key in arrival order
+                    if (xsrc) live = live && ((ld_cg_u32(bits + j * PASS_KPT + q) >> lane) & 1u);
+                    const uint64_t key = tile[lane + 32 * q];
+                    uint32_t own = 0;
+                    if (live) own = (uint32_t)(slot_of(key) / slice_bits);
+#pragma unroll
+                    for (int o = 0; o < SHARD_MAX; o++) {
+                        if ((uint32_t)o < world) {
+                            const bool mine = live && own == (uint32_t)o;
+                            const uint32_t mk = __ballot_sync(0xffffffffu, mine);
+                            if (mine) stg[o * XS_STAGE + ((h_o[o] + n_o[o] + __popc(mk & lt_mask)) & (XS_STAGE - 1))] = key;
+                            n_o[o] += __popc(mk);
+                        }
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int o = 0; o < SHARD_MAX; o++)
+                        if ((uint32_t)o < world && n_o[o] >= 32) flush(o, n_o[o], h_o[o], pos_o[o], 32);
+                }
+                __syncwarp();
+                if (lane == 0) fence_proxy_async();
+                issue(j + 2);  // this tile's buffer is free again
+            }
+        }
+        // end of the region: the rest of every owner's staging, then the block counts (here and at the owner)
+#pragma unroll
+        for (int o = 0; o < SHARD_MAX; o++) {
+            if ((uint32_t)o < world) {
+                if (n_o[o]) flush(o, n_o[o], h_o[o], pos_o[o], n_o[o]);
+                if (lane == 0) {
+                    dst_cnt[r * world + o] = overflow ? 0u : pos_o[o];
+                    cd.xcnt[o][(size_t)me * R + r] = overflow ? 0u : pos_o[o];
+                }
+                total += pos_o[o];
+            }
+        }
+    }
+    if (lane == 0) {
+        if (overflow) st->status = ST_ERR_LIST_OVERFLOW;
+        if (total) atomicAdd((unsigned long long*)&st->redo_count, (unsigned long long)total);
+    }
+    fence_proxy_async_global();
+    __threadfence_system();  // offsets and counts must be performed at the owners before the barrier kernel signals
+    __syncwarp();
+    if (lane == 0) {
+        mbar_inval(&mbar[0]);
+        mbar_inval(&mbar[1]);
+    }
+}
+
+// (sender, region) blocks of the offsets this owner received, dealt to the warps round robin
+template <class F>
+__device__ __forceinline__ void for_each_received_tile(const CommDev& cd, uint32_t R, uint32_t sub_cap, F&& body) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t n_blocks = (uint64_t)cd.world * R;
+    const uint64_t n_gw = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint32_t* __restrict__ idx = cd.xidx[cd.rank];
+    const uint32_t* __restrict__ cnt = cd.xcnt[cd.rank];
+    for (uint64_t blk = (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); blk < n_blocks; blk += n_gw) {
+        const uint32_t n = ld_cg_u32(cnt + blk);
+        const uint32_t* __restrict__ base = idx + blk * sub_cap;
+        for (uint32_t i0 = 0; i0 < n; i0 += WP_TILE) {
+            uint32_t loc[PASS_KPT];
+            uint32_t live = 0;
+#pragma unroll
+            for (int q = 0; q < PASS_KPT; q++) {
+                const uint32_t i = i0 + lane + 32 * q;
+                loc[q] = 0;
+                if (i < n) {
+                    loc[q] = ld_cg_u32(base + i);
+                    live |= 1u << q;
+                }
+            }
+            body(blk, i0, loc, live);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// xmark_kernel: find_collisions over the offsets received from all shards, on this owner's slice
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(PASS_THREADS)
+    xmark_kernel(BuildState* __restrict__ st, uint32_t level, CommDev cd, uint32_t* __restrict__ a32, uint32_t* __restrict__ c32) {
+    if (st->status != ST_RUNNING || st->n_levels != level || level >= st->tail_level) return;
+    const LevelDesc* cu = &st->lv[level];
+    const uint64_t slice_bits = cu->x_slice_bits;
+    if (slice_bits == 0) return;
+    const uint64_t off32 = cu->word_off * 2 + (uint64_t)cd.rank * (slice_bits / 32);
+    uint32_t* __restrict__ a_sl = a32 + off32;
+    uint32_t* __restrict__ c_sl = c32 + off32;
+    for_each_received_tile(cd, st->n_regions, st->x_sub_cap, [&](uint64_t, uint32_t, const uint32_t (&loc)[PASS_KPT], uint32_t live) {
+        uint32_t old[PASS_KPT];
+#pragma unroll
+        for (int q = 0; q < PASS_KPT; q++) {
+            old[q] = 0;
+            if ((live >> q) & 1u) old[q] = atomicOr(a_sl + (loc[q] >> 5), 1u << (loc[q] & 31));
+        }
+#pragma unroll
+        for (int q = 0; q < PASS_KPT; q++) {
+            const uint32_t m = 1u << (loc[q] & 31);
+            if (((live >> q) & 1u) && (old[q] & m)) red_or_u32(c_sl + (loc[q] >> 5), m);
+        }
+    });
+}
+
+// ---------------------------------------------------------------------------------------------
+// xfinalize_kernel: a &= ~collide on the owner's slice, unique count, final a slice -> every shard's arena
+// ---------------------------------------------------------------------------------------------
+template <int WORLD>
+__device__ __forceinline__ uint64_t xfinalize_slice(const CommDev& cd, uint64_t pair_off, uint64_t p0, uint64_t p1) {
+    uint64_t uniq = 0;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const ulonglong2* __restrict__ a2 = reinterpret_cast<const ulonglong2*>(cd.words[cd.rank]);
+    const ulonglong2* __restrict__ c2 = reinterpret_cast<const ulonglong2*>(cd.coll[cd.rank]);
+    for (uint64_t p = p0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < p1; p += stride) {
+        ulonglong2 a = a2[pair_off + p];
+        const ulonglong2 c = c2[pair_off + p];
+        a.x &= ~c.x;
+        a.y &= ~c.y;
+        uniq += __popcll(a.x) + __popcll(a.y);
+#pragma unroll
+        for (int r = 0; r < WORLD; r++) reinterpret_cast<ulonglong2*>(cd.words[r])[pair_off + p] = a;
+    }
+    return uniq;
+}
+
+__global__ void __launch_bounds__(FIN_THREADS)
+    xfinalize_kernel(BuildState* __restrict__ st, uint32_t level, CommDev cd) {
+    __shared__ uint64_t warp_u[FIN_THREADS / 32];
+    if (st->status != ST_RUNNING || st->n_levels != level || level >= st->tail_level) return;
+    const LevelDesc* cu = &st->lv[level];
+    const uint64_t slice_bits = cu->x_slice_bits;
+    if (slice_bits == 0) return;
+    const uint64_t pair_off = cu->word_off / 2;
+    const uint64_t n_pairs = round_up8(cu->n_words) / 2;
+    const uint64_t per = slice_bits / 128;
+    const uint64_t p0 = min(n_pairs, per * cd.rank), p1 = min(n_pairs, p0 + per);
+    uint64_t u = 0;
+    switch (cd.world) {
+        case 2: u = xfinalize_slice<2>(cd, pair_off, p0, p1); break;
+        case 3: u = xfinalize_slice<3>(cd, pair_off, p0, p1); break;
+        case 4: u = xfinalize_slice<4>(cd, pair_off, p0, p1); break;
+        case 5: u = xfinalize_slice<5>(cd, pair_off, p0, p1); break;
+        case 6: u = xfinalize_slice<6>(cd, pair_off, p0, p1); break;
+        case 7: u = xfinalize_slice<7>(cd, pair_off, p0, p1); break;
+        case 8: u = xfinalize_slice<8>(cd, pair_off, p0, p1); break;
+        default: break;
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) u += __shfl_xor_sync(0xffffffffu, u, d);
+    if ((threadIdx.x & 31) == 0) warp_u[threadIdx.x >> 5] = u;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint64_t t = 0;
+#pragma unroll
+        for (int w = 0; w < FIN_THREADS / 32; w++) t += warp_u[w];
+        if (t) atomicAdd((unsigned long long*)&st->uniq_count, (unsigned long long)t);
+    }
+    __threadfence_system();  // the slice must be performed at every shard before the barrier kernel signals
+}
+
+// ---------------------------------------------------------------------------------------------
+// xbits_kernel: Context::filter for everything received -- one bit per key back to its sender, in arrival order
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(PASS_THREADS)
+    xbits_kernel(BuildState* __restrict__ st, uint32_t level, CommDev cd, const uint32_t* __restrict__ c32) {
+    if (st->status != ST_RUNNING || st->n_levels != level || level >= st->tail_level) return;
+    const LevelDesc* cu = &st->lv[level];
+    const uint64_t slice_bits = cu->x_slice_bits;
+    if (slice_bits == 0) return;
+    const uint32_t* __restrict__ c_sl = c32 + cu->word_off * 2 + (uint64_t)cd.rank * (slice_bits / 32);
+    const uint32_t R = st->n_regions, sub_cap = st->x_sub_cap;
+    const int lane = threadIdx.x & 31;
+    for_each_received_tile(cd, R, sub_cap, [&](uint64_t blk, uint32_t i0, const uint32_t (&loc)[PASS_KPT], uint32_t live) {
+        uint32_t cw[PASS_KPT];
+#pragma unroll
+        for (int q = 0; q < PASS_KPT; q++) cw[q] = ((live >> q) & 1u) ? __ldcg(c_sl + (loc[q] >> 5)) : 0u;
+        uint32_t mine = 0;
+#pragma unroll
+        for (int q = 0; q < PASS_KPT; q++) {
+            const uint32_t w = __ballot_sync(0xffffffffu, (cw[q] >> (loc[q] & 31)) & 1u);
+            if (lane == q) mine = w;
+        }
+        // block blk = (sender s, region r) of this owner -> the sender's bits for (owner me, region r)
+        const uint32_t s = (uint32_t)(blk / R), r = (uint32_t)(blk % R);
+        if (lane < PASS_KPT) cd.xbits[s][(((uint64_t)cd.rank * R + r) * sub_cap + i0) / 32 + lane] = mine;
+    });
+    __threadfence_system();
+}
+
+// ---------------------------------------------------------------------------------------------
+// xpop_kernel: per-512-bit popcounts (compute_ranks, src/lib.rs:277-297) of an exchange level, once every owner's
+// final slice has arrived (each shard keeps a complete replica and scans its own ranks)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(FIN_THREADS)
+    xpop_kernel(const BuildState* __restrict__ st, uint32_t level, const uint64_t* __restrict__ words, uint32_t* __restrict__ blockpop) {
+    // runs after the level is complete: n_levels has moved on, the descriptor stays
+    if (level >= st->n_levels || st->lv[level].x_slice_bits == 0) return;
+    if (st->status != ST_RUNNING && st->status != ST_DONE && st->status != ST_NEED_WORDS && st->status != ST_NEED_LIST) return;
+    const uint64_t word_off = st->lv[level].word_off;
+    const uint64_t n_pairs = round_up8(st->lv[level].n_words) / 2;
+    const ulonglong2* __restrict__ a2 = reinterpret_cast<const ulonglong2*>(words + word_off);
+    uint32_t* __restrict__ bp = blockpop + word_off / 8;
+    const int lane = threadIdx.x & 31;
+    const uint64_t stride = (uint64_t)gridDim.x * FIN_THREADS;
+    for (uint64_t p0 = (uint64_t)blockIdx.x * FIN_THREADS + (threadIdx.x & ~31u); p0 < n_pairs; p0 += stride) {
+        const uint64_t p = p0 + lane;
+        uint32_t pc = 0;
+        if (p < n_pairs) {
+            const ulonglong2 a = a2[p];
+            pc = __popcll(a.x) + __popcll(a.y);
+        }
+        pc += __shfl_xor_sync(0xffffffffu, pc, 1);
+        pc += __shfl_xor_sync(0xffffffffu, pc, 2);
+        if (p < n_pairs && (lane & 3) == 0) bp[p >> 2] = pc;
+    }
+}
+
+}  // namespace bphf
