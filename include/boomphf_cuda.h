@@ -212,7 +212,8 @@ typedef struct bphf_build_stats {
     float fin_ms[BPHF_MAX_LEVELS + 1];     /* per-level finalize kernel time (profile 2)            */
     float tail_ms, ranks_ms, total_ms;     /* profile 2 (total_ms always)                           */
     float h2d_ms;                          /* reserved                                              */
-    uint32_t bucketed_levels;              /* levels built by the shared-memory (bucketed) kernels  */
+    uint32_t bucketed_levels;              /* levels built by the shared-memory (bucketed) kernels; sharded builds:
+                                            * + 1000 * levels built by the exchange (owner computes) kernels */
     uint32_t rebuilds;                     /* 1 when a bucket overflow forced an unbucketed rebuild */
     float merge_ms[BPHF_MAX_LEVELS + 1];   /* sharded build: barrier + OR-collide merge + barrier (profile 2) */
     float cascade_ms;                      /* persistent kernel that runs every level >= 1 (build mode 0)     */
@@ -231,6 +232,12 @@ BPHF_API int bphf_set_profile(int level);
  *   mode 2           = large levels are built in shared memory after grouping the keys by bit range ("bucketed"),
  *                      levels with fewer than bucket_min_keys keys (0 = default 2^20) by the mode-1 kernels. */
 BPHF_API int bphf_set_build_mode(int mode, uint64_t bucket_min_keys);
+/* sharded builds (mode 0): levels with more than `bits` bits are built "owner computes" -- every shard routes its keys'
+ * slot offsets (4 bytes per key over NVLink) to the shard that owns the slot range, the owners mark their L2-resident
+ * slices and return one survivor bit per key -- instead of marking full-width levels on every shard and folding them
+ * with the OR-collide merge.  Default 4.5e8 (a full-width (a, collide) pair beyond the L2); 0 = never.  Identical
+ * results either way; call it with the same value on every shard. */
+BPHF_API int bphf_set_xchg_bits(double bits);
 /* ingest of HOST key sets (bphf_build_u64 and bphf_build_chunked_u64 with BPHF_MEM_HOST; identical results):
  *   mode 0 (default) = automatic: a key set whose 8 n bytes plus the work buffers of an in-core build do not fit the
  *                      device's free memory is STREAMED -- the host keys pass through a 3-slot device ring twice (mark of

@@ -19,6 +19,7 @@
 #include "bucket_kernels.cuh"
 #include "query_kernels.cuh"
 #include "shard_kernels.cuh"
+#include "xchg_kernels.cuh"
 
 using namespace bphf;
 
@@ -104,7 +105,10 @@ static const DeviceInfo& device_info(int dev) {
                                           (const void*)pass_kernel<true, StreamCfg>,
                                           (const void*)pass_chunk_kernel<false>, (const void*)pass_chunk_kernel<true>,
                                           (const void*)cascade_kernel<false>, (const void*)cascade_kernel<true>,
-                                          (const void*)shard_gather_kernel<false>, (const void*)shard_gather_kernel<true>};
+                                          (const void*)shard_gather_kernel<false>, (const void*)shard_gather_kernel<true>,
+                                          (const void*)shard_gather_x_kernel<false>, (const void*)shard_gather_x_kernel<true>,
+                                          (const void*)pass_x_kernel<false>, (const void*)pass_x_kernel<true>,
+                                          (const void*)xscatter_kernel<false>, (const void*)xscatter_kernel<true>};
             for (const void* k : ring_kernels) {
                 CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PASS_SMEM_BYTES));
                 CK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 60));
@@ -133,7 +137,11 @@ static const DeviceInfo& device_info(int dev) {
                 (const void*)key_words_kernel, (const void*)keygen_kernel, (const void*)check_perm_kernel, (const void*)checksum_kernel,
                 (const void*)shard_barrier_kernel, (const void*)or_collide_merge_kernel, (const void*)tail_gather_kernel,
                 (const void*)shard_gather_kernel<false>, (const void*)shard_gather_kernel<true>,
-                (const void*)shard_collect_kernel, (const void*)shard_switch_kernel};
+                (const void*)shard_collect_kernel, (const void*)shard_switch_kernel,
+                (const void*)shard_gather_x_kernel<false>, (const void*)shard_gather_x_kernel<true>,
+                (const void*)pass_x_kernel<false>, (const void*)pass_x_kernel<true>,
+                (const void*)xscatter_kernel<false>, (const void*)xscatter_kernel<true>, (const void*)xmark_kernel,
+                (const void*)xfinalize_kernel, (const void*)xbits_kernel, (const void*)xpop_kernel};
             for (const void* k : all_kernels) CK(cudaFuncGetAttributes(&fa, k));
         }
         if (prev != dev) CK(cudaSetDevice(prev));
@@ -255,9 +263,16 @@ struct bphf_comm {
     cudaStream_t stream = nullptr;  // the shard's build stream (owned: one hardware queue per live shard)
     void* pinned = nullptr;         // pinned staging for the build state read-back
     CommDev dev;
+    // exchange levels (xchg_kernels.cuh): world x x_regions blocks of x_sub_cap entries each way
+    uint32_t x_regions = 0, x_sub_cap = 0;
+    size_t x_entries() const { return (size_t)world * x_regions * x_sub_cap; }
     size_t off_coll() const { return (size_t)phys_words * 8; }
     size_t off_xkeys() const { return (size_t)phys_words * 16; }
     size_t off_flags() const { return off_xkeys() + XKEYS_WORDS * 8; }
+    size_t off_xidx() const { return off_flags() + (size_t)SHARD_MAX * FLAG_STRIDE * 8; }
+    size_t off_xcnt() const { return off_xidx() + x_entries() * 4; }
+    size_t off_xbits() const { return (off_xcnt() + (size_t)world * x_regions * 4 + 127) & ~(size_t)127; }
+    size_t total_bytes() const { return off_xbits() + x_entries() / 8 + 128; }
     void map_peer(int p, void* b) {
         peer_base[p] = b;
         unsigned char* u = static_cast<unsigned char*>(b);
@@ -265,6 +280,9 @@ struct bphf_comm {
         dev.coll[p] = reinterpret_cast<uint64_t*>(u + off_coll());
         dev.xkeys[p] = reinterpret_cast<uint64_t*>(u + off_xkeys());
         dev.flags[p] = reinterpret_cast<uint64_t*>(u + off_flags());
+        dev.xidx[p] = reinterpret_cast<uint32_t*>(u + off_xidx());
+        dev.xcnt[p] = reinterpret_cast<uint32_t*>(u + off_xcnt());
+        dev.xbits[p] = reinterpret_cast<uint32_t*>(u + off_xbits());
     }
 };
 
@@ -352,6 +370,9 @@ struct Plan {
 // 0: L2-atomic kernels, levels >= 1 in one persistent cascade kernel (default, fastest measured)
 // 1: L2-atomic kernels, two launches per level   2: bucketed shared-memory kernels for the large levels
 static int g_build_mode = 0;
+// sharded builds (mode 0): a level is built by the exchange ("owner computes") kernels when its bit count exceeds this
+// (the full-width (a, collide) pair of the merge path would not stay L2 resident); 0 disables the exchange path
+static double g_xchg_bits = 4.5e8;
 static uint64_t g_bucket_min_keys = 1ull << 20;   // levels below this are built by the plain kernels
 
 // a level is built by the bucketed kernels when its (a, collide) pair clearly exceeds the L2: random L2 atomics fall
@@ -478,6 +499,7 @@ struct Builder {
     uint32_t* d_blockpop = nullptr;
     uint32_t* d_cursors = nullptr;  // [2][MAX_BUCKETS_ALLOC]
     uint32_t* d_regcnt = nullptr;   // [2][n_regions]: keys per region of the striped key lists (pass_body)
+    uint32_t* d_xregcnt = nullptr;  // sharded: [2][n_regions][SHARD_MAX] keys per (region, owner) block of an exchange level
     uint64_t* d_buf[2] = {nullptr, nullptr};   // key lists / bucket key regions, level l in d_buf[l & 1]
     uint64_t buf_cap[2] = {0, 0};               // allocated size of d_buf[] in keys (>= the planned list_cap)
     uint64_t phys_words = 0;  // words_cap + TAIL_RESERVE_WORDS
@@ -488,6 +510,7 @@ struct Builder {
     uint32_t launches = 0, syncs = 0;
     bphf_comm* comm = nullptr;  // sharded build: the arenas live in the comm's peer-visible allocation
     bool gathered = false;      // sharded build: the remaining keys were collected on every shard; unsharded from here
+    uint32_t xchg_levels = 0;   // sharded build: leading levels built by the exchange kernels (same on every shard)
     std::vector<EventPair> events;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
 
@@ -508,6 +531,7 @@ struct Builder {
         if (d_blockpop) cudaFreeAsync(d_blockpop, s);
         if (d_cursors) cudaFreeAsync(d_cursors, s);
         if (d_regcnt) cudaFreeAsync(d_regcnt, s);
+        if (d_xregcnt) cudaFreeAsync(d_xregcnt, s);
         for (int i = 0; i < 2; i++) {
             try {
                 release_list(i);
@@ -579,6 +603,10 @@ struct Builder {
         CK(cudaMemsetAsync(d_cursors, 0, (size_t)2 * MAX_BUCKETS_ALLOC * CURSOR_STRIDE * 4, s));
         CK(cudaMallocAsync((void**)&d_regcnt, (size_t)2 * n_regions() * 4, s));
         CK(cudaMemsetAsync(d_regcnt, 0, (size_t)2 * n_regions() * 4, s));
+        if (comm) {
+            CK(cudaMallocAsync((void**)&d_xregcnt, (size_t)2 * n_regions() * SHARD_MAX * 4, s));
+            CK(cudaMemsetAsync(d_xregcnt, 0, (size_t)2 * n_regions() * SHARD_MAX * 4, s));
+        }
     }
     // ST_NEED_WORDS: move to a larger arena, keeping everything built so far
     void grow_arena(uint64_t need_words) {
@@ -730,6 +758,15 @@ struct Builder {
         else shard_gather_kernel<false><<<grid, PASS_THREADS, PASS_SMEM_BYTES, s>>>(d_state, level, d_keys, d_buf[0], d_buf[1], c32(), xk);
         CK(cudaGetLastError());
         launches++;
+        if (level == xchg_levels && xchg_levels > 0) {  // the collect follows an exchange level: filter by the owners' bits
+            const void* xfn = maybe_big ? (const void*)shard_gather_x_kernel<true> : (const void*)shard_gather_x_kernel<false>;
+            const int xgrid = resident_grid(xfn, PASS_THREADS, PASS_SMEM_BYTES);
+            const uint32_t* xb = comm->dev.xbits[comm->rank];
+            if (maybe_big) shard_gather_x_kernel<true><<<xgrid, PASS_THREADS, PASS_SMEM_BYTES, s>>>(d_state, level, d_buf[0], d_buf[1], xk, xb);
+            else shard_gather_x_kernel<false><<<xgrid, PASS_THREADS, PASS_SMEM_BYTES, s>>>(d_state, level, d_buf[0], d_buf[1], xk, xb);
+            CK(cudaGetLastError());
+            launches++;
+        }
         end_event(e0);
         const size_t em = begin_event(4, level);
         launch_barrier(BAR_LIST_SUM, level);
@@ -808,6 +845,51 @@ struct Builder {
         CK(cudaGetLastError());
         launches++;
     }
+    // ---- exchange levels (owner computes, xchg_kernels.cuh) ------------------------------------------
+    void launch_xchg_level(uint32_t level, uint64_t k_up) {
+        const size_t e0 = begin_event(0, level);
+        {
+            const void* fn = maybe_big ? (const void*)xscatter_kernel<true> : (const void*)xscatter_kernel<false>;
+            const int grid = resident_grid(fn, PASS_THREADS, PASS_SMEM_BYTES);
+            if (maybe_big) xscatter_kernel<true><<<grid, PASS_THREADS, PASS_SMEM_BYTES, s>>>(d_state, level, d_keys, d_buf[0], d_buf[1], comm->dev);
+            else xscatter_kernel<false><<<grid, PASS_THREADS, PASS_SMEM_BYTES, s>>>(d_state, level, d_keys, d_buf[0], d_buf[1], comm->dev);
+            CK(cudaGetLastError());
+            launches++;
+        }
+        end_event(e0);
+        const size_t em = begin_event(4, level);
+        launch_barrier(BAR_PLAIN, level);
+        end_event(em);
+        const size_t e1 = begin_event(1, level);
+        const int wgrid = info.sm_count * 6;
+        xmark_kernel<<<wgrid, PASS_THREADS, 0, s>>>(d_state, level, comm->dev, a32(), c32());
+        const uint64_t bits = level_size(hst.gamma, k_up);
+        const uint64_t pairs = round_up8((bits + 63) / 64) / 2;
+        const uint64_t per = (pairs + comm->world - 1) / comm->world;
+        const int fgrid = (int)std::min<uint64_t>(std::max<uint64_t>(1, (per + FIN_THREADS - 1) / FIN_THREADS), (uint64_t)info.sm_count * 4);
+        xfinalize_kernel<<<fgrid, FIN_THREADS, 0, s>>>(d_state, level, comm->dev);
+        xbits_kernel<<<wgrid, PASS_THREADS, 0, s>>>(d_state, level, comm->dev, c32());
+        CK(cudaGetLastError());
+        launches += 3;
+        end_event(e1);
+        const size_t em2 = begin_event(4, level);
+        launch_barrier(BAR_XDONE, level);
+        end_event(em2);
+        const int pgrid = (int)std::min<uint64_t>(std::max<uint64_t>(1, (pairs + FIN_THREADS - 1) / FIN_THREADS), (uint64_t)info.sm_count * 8);
+        xpop_kernel<<<pgrid, FIN_THREADS, 0, s>>>(d_state, level, d_words, d_blockpop);
+        CK(cudaGetLastError());
+        launches++;
+    }
+    // first level after the exchange levels: filter by the owners' survivor bits, then as any merge-mode level
+    void launch_pass_x(uint32_t level) {
+        const void* fn = maybe_big ? (const void*)pass_x_kernel<true> : (const void*)pass_x_kernel<false>;
+        const int grid = resident_grid(fn, PASS_THREADS, PASS_SMEM_BYTES);
+        const uint32_t* xb = comm->dev.xbits[comm->rank];
+        if (maybe_big) pass_x_kernel<true><<<grid, PASS_THREADS, PASS_SMEM_BYTES, s>>>(d_state, level, d_buf[0], d_buf[1], a32(), c32(), xb);
+        else pass_x_kernel<false><<<grid, PASS_THREADS, PASS_SMEM_BYTES, s>>>(d_state, level, d_buf[0], d_buf[1], a32(), c32(), xb);
+        CK(cudaGetLastError());
+        launches++;
+    }
     // ---- bucketed (shared-memory) kernels -----------------------------------------------------------
     void launch_scatter0(uint64_t begin, uint64_t end, uint32_t count_max) {
         if (end <= begin) return;
@@ -846,6 +928,7 @@ struct Builder {
             if (prev_maybe_b) launch_scatter(level, prev->range_max, prev->count_max, cur.maybe_bucket ? cur.count_max : 1);
             if (!cur.surely_bucket && prev_maybe_b) launch_mark_list(level, 0, 0, cur.k_up);
             if (!prev_surely_b) launch_pass(level, prev->k_up);
+            if (comm && !gathered && level == xchg_levels && xchg_levels > 0) launch_pass_x(level);
             end_event(e0);
         }
         const size_t e1 = begin_event(1, level);
@@ -979,6 +1062,26 @@ static int build_once(const uint64_t* keys, uint64_t n, double gamma, int has_se
             for (int i = 0; i < 2; i++) plan.list_cap[i] = std::max<uint64_t>(plan.list_cap[i], GATHER_MAX_KEYS + 1024);
     }
 
+    if (comm && g_build_mode == 0 && g_xchg_bits > 0.0 && !bucket_enable && !b.stream_keys) {
+        // exchange levels: a prefix of levels that surely exceed the threshold (both plan estimates), whose slices can
+        // be addressed with 32-bit offsets, and that leave two ordinary levels in front of the tail
+        if (comm->x_regions != b.n_regions()) return fail(BPHF_ERR_INTERNAL, "comm and builder disagree on the region count");
+        uint32_t xl = 0;
+        for (size_t l = 0; l + 2 < plan.lv.size(); l++) {
+            const uint64_t bits_lo = level_size(gamma, plan.lv[l].k_lo), bits_up = level_size(gamma, plan.lv[l].k_up);
+            const uint64_t slice_words = round_up8(((bits_up + 63) / 64 + comm->world - 1) / comm->world);
+            if ((double)bits_lo > g_xchg_bits && slice_words * 64 <= (1ull << 32)) xl = (uint32_t)l + 1;
+            else break;
+        }
+        b.xchg_levels = xl;
+        if (xl > 0) {
+            // (region, owner) key blocks of the exchange levels live in the list buffers
+            const uint64_t need = (uint64_t)b.n_regions() * comm->world * comm->x_sub_cap;
+            for (int i = 0; i < 2; i++) plan.list_cap[i] = std::max<uint64_t>(plan.list_cap[i], need);
+            // the collect level may directly follow the exchange levels, but not be one of them
+            if (gather_level != NO_LEVEL && gather_level < xl) gather_level = NO_LEVEL;
+        }
+    }
     if (ingest && plan.lv.size() < 2) return BUILD_RETRY_INCORE;  // level 1 may already belong to the tail kernel
     // ---- striped key lists (pass_body): every region must be able to hold what its share of the first dense source
     // holds -- the input, or the list the last bucketed level leaves behind; later levels only shrink
@@ -1033,6 +1136,9 @@ static int build_once(const uint64_t* keys, uint64_t n, double gamma, int has_se
     st.n_regions = n_regions;
     st.reg_cap = reg_cap;
     st.reg_cnt = b.d_regcnt;
+    st.xchg_levels = b.xchg_levels;
+    st.x_sub_cap = comm ? comm->x_sub_cap : 0;
+    st.xreg_cnt = b.d_xregcnt;
     if (!try_make_level(&st, 0, n_global)) return fail(BPHF_ERR_INTERNAL, "level 0 does not fit the planned buffers");
     st.lv[0].k_loc = n;
     b.upload_state();
@@ -1113,6 +1219,11 @@ static int build_once(const uint64_t* keys, uint64_t n, double gamma, int has_se
         } else {
             first_level = (uint32_t)lps.size();  // done or failed at level 0: the loop below reports it
         }
+    } else if (keys_mem == BPHF_MEM_HOST && n && b.xchg_levels > 0) {
+        // exchange level 0 routes the shard's whole key set in one pass
+        CK(cudaMallocAsync((void**)&b.d_keys_owned, n * 8, s));
+        b.d_keys = b.d_keys_owned;
+        CK(cudaMemcpyAsync(b.d_keys_owned, keys, n * 8, cudaMemcpyHostToDevice, s));
     } else if (keys_mem == BPHF_MEM_HOST && n) {
         CK(cudaMallocAsync((void**)&b.d_keys_owned, n * 8, s));
         b.d_keys = b.d_keys_owned;
@@ -1138,9 +1249,11 @@ static int build_once(const uint64_t* keys, uint64_t n, double gamma, int has_se
         cudaEventDestroy(ready);
     } else {
         b.d_keys = keys;
-        const size_t pe = b.begin_event(0, 0);
-        level0_entry(0, n);
-        b.end_event(pe);
+        if (b.xchg_levels == 0) {
+            const size_t pe = b.begin_event(0, 0);
+            level0_entry(0, n);
+            b.end_event(pe);
+        }
     }
 
     // ---- all planned levels, then the tail, without a host round trip
@@ -1151,12 +1264,17 @@ static int build_once(const uint64_t* keys, uint64_t n, double gamma, int has_se
     lp0.count_max = level0_bucketed ? count0 : 1;
     if (lps.empty()) lps.push_back(lp0);
     else if (!ingest) lps[0] = lp0;
-    if (!ingest) b.launch_level(0, nullptr, lps[0]);
+    if (b.xchg_levels > 0) b.launch_xchg_level(0, n_global);
+    else if (!ingest) b.launch_level(0, nullptr, lps[0]);
     {
         // the persistent cascade kernel takes over at the first level whose predecessor is surely plain; the
         // bucketed prefix (and the level right after it) is launched step by step
         uint32_t l = first_level;
         for (; l < lps.size(); l++) {
+            if (l < b.xchg_levels) {
+                b.launch_xchg_level(l, lps[l].k_up);
+                continue;
+            }
             if (comm && l == st.gather_level) {
                 b.launch_gather(l, lps[l - 1].k_up, lps[l].k_up);
                 l++;
@@ -1304,7 +1422,7 @@ static int build_once(const uint64_t* keys, uint64_t n, double gamma, int has_se
     }
     bs.h2d_ms = 0.f;
     uint32_t nb = 0;
-    for (uint32_t l = 0; l < st.n_levels; l++) nb += st.lv[l].b_range != 0;
+    for (uint32_t l = 0; l < st.n_levels; l++) nb += (st.lv[l].b_range != 0) + 1000u * (st.lv[l].x_slice_bits != 0);
     bs.bucketed_levels = nb;
     bs.rebuilds = rebuilds;
     bs.streamed_ingest = ingest ? 1 : 0;
@@ -1448,6 +1566,11 @@ BPHF_API int bphf_set_build_mode(int mode, uint64_t bucket_min_keys) {
     return BPHF_OK;
 }
 
+BPHF_API int bphf_set_xchg_bits(double bits) {
+    g_xchg_bits = bits > 0.0 ? bits : 0.0;
+    return BPHF_OK;
+}
+
 BPHF_API int bphf_set_ingest_mode(int mode, uint64_t ring_keys) {
     if (mode < 0 || mode > 2) return fail(BPHF_ERR_ARG, "ingest mode is 0 (automatic), 1 (always streamed) or 2 (never)");
     g_ingest_mode = mode;
@@ -1568,10 +1691,20 @@ BPHF_API int bphf_comm_create(int device, int rank, int world, uint64_t max_keys
     c->rank = rank;
     c->world = world;
     c->phys_words = round_up8(plan.words_cap + plan.words_cap / 64 + TAIL_RESERVE_WORDS);
-    c->bytes = c->off_flags() + (size_t)SHARD_MAX * FLAG_STRIDE * 8;
+    // exchange blocks: a (sender, region, owner) block holds the keys of one warp region that fall into one owner's slice
+    // -- about n_local / (R * world) of them; sized for shards up to twice the even share, + 6 sigma, in whole tiles
+    c->x_regions = (uint32_t)info.sm_count * BPHF_PASS_CTAS * WP_WARPS;
+    {
+        const double mean = 2.0 * (double)max_keys_global / (double)world / (double)world / (double)c->x_regions;
+        const uint64_t cap = (uint64_t)(mean + 6.0 * std::sqrt(mean) + 64.0);
+        c->x_sub_cap = (uint32_t)std::min<uint64_t>(((cap + WP_TILE - 1) / WP_TILE) * WP_TILE, 1u << 30);
+    }
+    c->bytes = c->total_bytes();
     memset(&c->dev, 0, sizeof c->dev);
     c->dev.rank = (uint32_t)rank;
     c->dev.world = (uint32_t)world;
+    c->dev.x_sub_cap = c->x_sub_cap;
+    c->dev.x_regions = c->x_regions;
     // plain cudaMalloc: exportable with cudaIpcGetMemHandle (pool memory is not)
     CK(cudaMalloc((void**)&c->base, c->bytes));
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -1622,7 +1755,8 @@ BPHF_API int bphf_comm_connect_local(bphf_comm* c, bphf_comm* const* all) {
     for (int p = 0; p < c->world; p++) {
         if (p == c->rank) continue;
         const bphf_comm* o = all[p];
-        if (!o || o->rank != p || o->world != c->world || o->phys_words != c->phys_words)
+        if (!o || o->rank != p || o->world != c->world || o->phys_words != c->phys_words || o->x_sub_cap != c->x_sub_cap ||
+            o->x_regions != c->x_regions)
             return fail(BPHF_ERR_ARG, "comms do not match (rank order, world, arena size)");
         if (o->device == c->device) c->co_located = true;
         if (o->device != c->device) {
@@ -1671,7 +1805,9 @@ BPHF_API int bphf_build_sharded_u64(bphf_comm* c, const uint64_t* keys, uint64_t
     // same policy as an unsharded build, on the GLOBAL level sizes (every shard marks full-width levels)
     bool bucket = g_build_mode == 2;
     uint64_t min_keys = g_bucket_min_keys;
-    if (g_build_mode == 0) {
+    if (g_build_mode == 0 && g_xchg_bits <= 0.0) {
+        // exchange path switched off: every shard marks full-width levels, grouped into shared-memory buckets while they
+        // exceed the L2 (the round-1 schedule)
         const double fit_bits = bucket_fit_bits();
         bucket = (double)level_size(gamma, n_global) > fit_bits;
         min_keys = (uint64_t)(fit_bits / gamma);

@@ -183,8 +183,9 @@ __global__ void __launch_bounds__(PASS_THREADS)
                      const uint32_t* __restrict__ list_cursor) {
     if (st->status != ST_RUNNING || st->n_levels != level || level >= st->tail_level) return;
     if (st->lv[level].b_range != 0) return;                         // bucketed level: bucket_mark_kernel
+    if (st->lv[level].x_slice_bits != 0) return;                    // exchange level of a sharded build: xchg_kernels.cuh
     const bool list_ready = st->list_ready_level == level;          // collected list of a sharded build
-    if (level >= 1 && st->lv[level - 1].b_range == 0 && !list_ready) return;  // plain predecessor: pass_kernel marks
+    if (level >= 1 && st->lv[level - 1].b_range == 0 && !list_ready) return;  // plain / exchange predecessor: pass_kernel marks
     const uint64_t* __restrict__ keys = user_keys;
     if (level >= 1) {
         keys = (level & 1) ? buf1 : buf0;
@@ -280,12 +281,16 @@ __device__ __forceinline__ bool list_is_striped(const BuildState* st, uint32_t l
 
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
-template <bool MAYBE_BIG, bool GATHER = false, class KC = KeyCfg>
+// XSRC: the previous level was an exchange level of a sharded build (xchg_kernels.cuh): its keys sit in this shard's
+// list grouped by (region, owner) and the owners' answers -- one survivor bit per key, in the same order -- in `xbits`;
+// the filter is then a sequential read instead of a random probe.
+template <bool MAYBE_BIG, bool GATHER = false, class KC = KeyCfg, bool XSRC = false>
 __device__ __forceinline__ void pass_body(BuildState* __restrict__ st, uint32_t level, const uint64_t* __restrict__ user_keys,
                                           uint64_t* __restrict__ buf0, uint64_t* __restrict__ buf1,
                                           uint32_t* __restrict__ a32, uint32_t* __restrict__ c32,
                                           uint64_t* __restrict__ gather_dst = nullptr,
-                                          const uint64_t* __restrict__ src_chunk = nullptr, uint64_t chunk_keys = 0) {
+                                          const uint64_t* __restrict__ src_chunk = nullptr, uint64_t chunk_keys = 0,
+                                          const uint32_t* __restrict__ xbits = nullptr) {
     typedef typename SlotIdx<MAYBE_BIG>::type slot_t;
     extern __shared__ __align__(128) unsigned char pass_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -306,9 +311,12 @@ __device__ __forceinline__ void pass_body(BuildState* __restrict__ st, uint32_t 
     uint32_t* __restrict__ reg_cnt = st->reg_cnt;   // [2][R]
     // ---- source: one chunk of the input (streamed ingest), a dense list (the input, a scatter / collect output) or the
     // striped list the previous filter pass wrote
-    const bool src_striped = !src_chunk && list_is_striped(st, level - 1);
+    const bool src_striped = XSRC || (!src_chunk && list_is_striped(st, level - 1));
+    const uint32_t x_world = XSRC ? __ldcg(&st->shard_world) : 1u;
+    const uint64_t x_sub_cap = XSRC ? (uint64_t)__ldcg(&st->x_sub_cap) : 0;
+    const uint32_t* __restrict__ x_cnt = st->xreg_cnt + (size_t)((level - 1) & 1) * R * SHARD_MAX;
     const uint64_t* __restrict__ src =
-        src_chunk ? src_chunk : (level == 1) ? user_keys : (((level - 1) & 1) ? buf1 : buf0);
+        src_chunk ? src_chunk : (level == 1 && !XSRC) ? user_keys : (((level - 1) & 1) ? buf1 : buf0);
     const uint64_t k_dense = src_chunk ? chunk_keys : __ldcg(&pv->k_loc);   // dense sources only
     const uint64_t dense_tiles = (k_dense + WP_TILE - 1) / WP_TILE;
     const uint32_t* __restrict__ src_cnt = reg_cnt + (size_t)((level - 1) & 1) * R;
@@ -404,17 +412,26 @@ __device__ __forceinline__ void pass_body(BuildState* __restrict__ st, uint32_t 
 
     const uint64_t n_gw = (uint64_t)gridDim.x * WP_WARPS;
     for (uint64_t r = (uint64_t)blockIdx.x * WP_WARPS + warp; r < R; r += n_gw) {
+        const uint64_t written0 = (append && !GATHER) ? (uint64_t)__ldcg(dst_cnt + r) : 0;
+        if (!GATHER) out_pos = r * reg_cap + written0;
+        const uint64_t region_first = out_pos;
+        for (uint32_t seg = 0; seg < x_world; seg++) {   // XSRC: one block per owner; otherwise one segment
         // tiles of region r: (pointer, valid keys) of tile j
         uint64_t n_rt;          // number of tiles
         uint64_t cnt_src = 0;   // striped: keys in the source region
-        if (src_striped) {
+        const uint64_t x_blk = ((uint64_t)r * x_world + seg) * x_sub_cap;                          // XSRC: key block (r, owner)
+        const uint32_t* __restrict__ xb = XSRC ? xbits + (((uint64_t)seg * R + r) * x_sub_cap) / 32 : nullptr;  // its survivor bits
+        if (XSRC) {
+            cnt_src = __ldcg(x_cnt + r * x_world + seg);
+            n_rt = (cnt_src + WP_TILE - 1) / WP_TILE;
+        } else if (src_striped) {
             cnt_src = __ldcg(src_cnt + r);
             n_rt = (cnt_src + WP_TILE - 1) / WP_TILE;
         } else {
             n_rt = r < dense_tiles ? (dense_tiles - r + R - 1) / R : 0;
         }
         auto tile_ptr = [&](uint64_t j) -> const uint64_t* {
-            return src_striped ? src + r * reg_cap + j * WP_TILE : src + (r + j * R) * WP_TILE;
+            return XSRC ? src + x_blk + j * WP_TILE : src_striped ? src + r * reg_cap + j * WP_TILE : src + (r + j * R) * WP_TILE;
         };
         auto tile_valid = [&](uint64_t j) -> uint32_t {
             const uint64_t left = src_striped ? cnt_src - j * WP_TILE : k_dense - (r + j * R) * WP_TILE;
@@ -432,9 +449,6 @@ __device__ __forceinline__ void pass_body(BuildState* __restrict__ st, uint32_t 
                 bulk_load(stage + (j & 1) * WP_TILE, tile_ptr(j), bytes, &mbar[j & 1]);
             }
         };
-        const uint64_t written0 = (append && !GATHER) ? (uint64_t)__ldcg(dst_cnt + r) : 0;
-        if (!GATHER) out_pos = r * reg_cap + written0;
-        const uint64_t region_first = out_pos;
         issue(0);
         issue(1);
         for (uint64_t j = 0; j < n_rt; j++) {
@@ -461,9 +475,17 @@ __device__ __forceinline__ void pass_body(BuildState* __restrict__ st, uint32_t 
             uint64_t shs = 0;  // 8 x 5 bits: position of each key's bit in its probe word
 #pragma unroll
             for (int q = 0; q < PASS_KPT; q++) {
-                const uint64_t idx = p_big ? level_index<true>(kc, p_sp0, key[q], p_bits) : level_index<false>(kc, p_sp0, key[q], p_bits);
-                cw[q] = (lane + 32u * q < valid) ? __ldcg(c_pv + (idx >> 5)) : 0u;
-                shs |= (uint64_t)((uint32_t)idx & 31) << (5 * q);
+                if (XSRC) {
+                    // the owner's answers for keys 32q .. 32q+31 of this tile: bit `lane` is this key's
+                    uint32_t w;
+                    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(w) : "l"(xb + j * PASS_KPT + q));
+                    cw[q] = (lane + 32u * q < valid) ? w : 0u;
+                    shs |= (uint64_t)lane << (5 * q);
+                } else {
+                    const uint64_t idx = p_big ? level_index<true>(kc, p_sp0, key[q], p_bits) : level_index<false>(kc, p_sp0, key[q], p_bits);
+                    cw[q] = (lane + 32u * q < valid) ? __ldcg(c_pv + (idx >> 5)) : 0u;
+                    shs |= (uint64_t)((uint32_t)idx & 31) << (5 * q);
+                }
             }
             if (n_st >= WP_TILE) flush(WP_TILE);   // the previous tiles' survivors, while the probes are in flight
 #pragma unroll
@@ -475,6 +497,7 @@ __device__ __forceinline__ void pass_body(BuildState* __restrict__ st, uint32_t 
             }
             __syncwarp();
         }
+        }  // segments
         // end of the region: everything staged belongs to it
         if (n_st >= WP_TILE) flush(WP_TILE);
         if (n_st) flush(n_st);
@@ -504,7 +527,18 @@ __global__ void __launch_bounds__(PASS_THREADS, PassOcc<KC>::ctas)
                 uint32_t* __restrict__ c32) {
     if (st->status != ST_RUNNING || st->n_levels != level || level >= st->tail_level) return;
     if (st->lv[level - 1].b_range != 0) return;  // bucketed predecessor: scatter_kernel filtered it already
+    if (st->lv[level - 1].x_slice_bits != 0 || st->lv[level].x_slice_bits != 0) return;  // exchange levels: xchg_kernels.cuh
     pass_body<MAYBE_BIG, false, KC>(st, level, user_keys, buf0, buf1, a32, c32);
+}
+
+// first level after the exchange levels of a sharded build: the filter reads the owners' survivor bits
+template <bool MAYBE_BIG>
+__global__ void __launch_bounds__(PASS_THREADS, BPHF_PASS_CTAS)
+    pass_x_kernel(BuildState* __restrict__ st, uint32_t level, uint64_t* __restrict__ buf0, uint64_t* __restrict__ buf1,
+                  uint32_t* __restrict__ a32, uint32_t* __restrict__ c32, const uint32_t* __restrict__ xbits) {
+    if (st->status != ST_RUNNING || st->n_levels != level || level >= st->tail_level) return;
+    if (st->lv[level - 1].x_slice_bits == 0 || st->lv[level].x_slice_bits != 0 || level == st->gather_level) return;
+    pass_body<MAYBE_BIG, false, KeyCfg, true>(st, level, nullptr, buf0, buf1, a32, c32, nullptr, nullptr, 0, xbits);
 }
 
 // streamed ingest (host key sets that stay out of HBM): filter(0) + compaction + mark(1) over ONE chunk of the level-0
@@ -595,6 +629,7 @@ __global__ void __launch_bounds__(FIN_THREADS)
     if (st->status != ST_RUNNING || st->n_levels != level || level >= st->tail_level) return;
     // bucketed levels are finalized by bucket_mark_kernel, except in a sharded build (the merge comes in between)
     if (st->lv[level].b_range != 0 && st->shard_world <= 1) return;
+    if (st->lv[level].x_slice_bits != 0) return;  // exchange level: xfinalize_kernel + the XDONE barrier
     finalize_body(st, level, words, coll, blockpop);
 }
 

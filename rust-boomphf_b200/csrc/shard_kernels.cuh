@@ -48,6 +48,9 @@ __device__ __forceinline__ uint64_t ld_relaxed_sys(const uint64_t* p) {
 enum BarrierKind : uint32_t {
     BAR_PLAIN = 0,
     BAR_LIST_SUM = 1,  // payload = keys this shard listed for `level`; the shard sum must equal lv[level].k_in
+    // end of an exchange level (xchg_kernels.cuh): payload = unique slots of this owner's slice, payload2 = keys this shard
+    // sent; every shard derives k(level + 1) = k(level) - sum(payload) and sets up the next level
+    BAR_XDONE = 2,
 };
 
 // One warp.  Lane p signals shard p (epoch + payload + this shard's status into p's flag line for this shard) and
@@ -57,14 +60,22 @@ __global__ void __launch_bounds__(32)
     shard_barrier_kernel(BuildState* __restrict__ st, CommDev cd, uint64_t epoch, uint32_t kind, uint32_t level) {
     const uint32_t p = threadIdx.x;
     const uint32_t my_status = st->status;
-    const bool live = my_status == ST_RUNNING && st->n_levels == level && level < st->tail_level;
-    uint64_t payload = 0;
+    bool live = my_status == ST_RUNNING && st->n_levels == level && level < st->tail_level;
+    const bool x_level = live && st->lv[level].x_slice_bits != 0;
+    if (kind == BAR_XDONE) live = x_level;          // the plan enqueues both variants of a level; only one applies
+    else if (kind == BAR_LIST_SUM && x_level) live = false;
+    uint64_t payload = 0, payload2 = 0;
     if (kind == BAR_LIST_SUM && live) payload = (level == 0) ? st->lv[0].k_loc : st->redo_count;
-    uint64_t peer_payload = 0, peer_status = ST_RUNNING;
+    if (kind == BAR_XDONE && live) {
+        payload = st->uniq_count;
+        payload2 = st->redo_count;
+    }
+    uint64_t peer_payload = 0, peer_payload2 = 0, peer_status = ST_RUNNING;
     bool timeout = false;
     if (p < cd.world) {
         uint64_t* dst = cd.flags[p] + (size_t)cd.rank * FLAG_STRIDE;
         st_relaxed_sys(dst + 1, payload);
+        st_relaxed_sys(dst + 3, payload2);
         st_relaxed_sys(dst + 2, (uint64_t)((my_status == ST_RUNNING || my_status == ST_DONE) ? ST_RUNNING : my_status));
         __threadfence_system();
         st_release_sys(dst, epoch);
@@ -79,15 +90,19 @@ __global__ void __launch_bounds__(32)
         }
         if (!timeout) {
             peer_payload = ld_relaxed_sys(src + 1);
+            peer_payload2 = ld_relaxed_sys(src + 3);
             peer_status = ld_relaxed_sys(src + 2);
         }
     }
     if (kind == BAR_LIST_SUM && live && p < cd.world) st->peer_count[p] = peer_payload;
     const bool bad = timeout || peer_status != ST_RUNNING;
     const uint32_t any_bad = __ballot_sync(0xffffffffu, bad);
-    uint64_t sum = peer_payload;
+    uint64_t sum = peer_payload, sum2 = peer_payload2;
 #pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+    for (int d = 16; d >= 1; d >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, d);
+        sum2 += __shfl_xor_sync(0xffffffffu, sum2, d);
+    }
     if (p == 0 && st->status == ST_RUNNING) {
         if (any_bad) {
             st->status = ST_ERR_COMM;
@@ -95,6 +110,15 @@ __global__ void __launch_bounds__(32)
         } else if (kind == BAR_LIST_SUM && live && sum != st->lv[level].k_in) {
             st->status = ST_ERR_INTERNAL;
             st->err_info = ((uint64_t)level << 48) | (sum & 0xffffffffffULL) | (1ULL << 44);
+        } else if (kind == BAR_XDONE && live) {
+            const uint64_t k_in = st->lv[level].k_in;
+            if (sum2 != k_in || sum > k_in) {
+                st->status = ST_ERR_INTERNAL;
+                st->err_info = ((uint64_t)level << 48) | (sum2 & 0xffffffffffULL) | (1ULL << 43);
+            } else {
+                st->lv[level].k_loc = st->redo_count;   // what this shard holds of the level
+                finish_level(st, level, k_in - sum);     // identical on every shard: same sums
+            }
         }
     }
 }
@@ -136,6 +160,7 @@ __device__ __forceinline__ void merge_slice(const CommDev& cd, uint64_t pair_off
 __global__ void __launch_bounds__(MERGE_THREADS)
     or_collide_merge_kernel(const BuildState* __restrict__ st, uint32_t level, CommDev cd) {
     if (st->status != ST_RUNNING || st->n_levels != level || level >= st->tail_level) return;
+    if (st->lv[level].x_slice_bits != 0) return;  // exchange level: nothing to fold, the owners marked their slices
     const uint64_t pair_off = st->lv[level].word_off / 2;
     const uint64_t n_pairs = round_up8(st->lv[level].n_words) / 2;
     const uint64_t per = (n_pairs + cd.world - 1) / cd.world;
@@ -167,6 +192,11 @@ __global__ void __launch_bounds__(TAIL_THREADS)
     if (st->status != ST_RUNNING || st->tail_level == NO_TAIL || st->n_levels != st->tail_level) return;
     if (st->shard_world <= 1) return;  // all keys were collected on every shard already: the tail reads local lists
     const uint32_t tid = threadIdx.x, level = st->tail_level;
+    if (level >= 1 && st->lv[level - 1].x_slice_bits != 0) {
+        // the host plan keeps at least two non-exchange levels in front of the tail
+        if (tid == 0) { st->status = ST_ERR_INTERNAL; st->err_info = ((uint64_t)level << 48) | (1ULL << 42); }
+        return;
+    }
     if (tid == 0) count = 0;
     __syncthreads();
     if (level == 0) {
@@ -222,7 +252,16 @@ __global__ void __launch_bounds__(PASS_THREADS, BPHF_PASS_CTAS)
                         uint64_t* __restrict__ buf0, uint64_t* __restrict__ buf1, uint32_t* __restrict__ c32,
                         uint64_t* __restrict__ xk) {
     if (st->status != ST_RUNNING || st->n_levels != level || level != st->gather_level || level >= st->tail_level) return;
+    if (st->lv[level - 1].x_slice_bits != 0) return;  // exchange predecessor: shard_gather_x_kernel
     pass_body<MAYBE_BIG, true>(st, level, user_keys, buf0, buf1, nullptr, c32, xk + 8);
+}
+template <bool MAYBE_BIG>
+__global__ void __launch_bounds__(PASS_THREADS, BPHF_PASS_CTAS)
+    shard_gather_x_kernel(BuildState* __restrict__ st, uint32_t level, uint64_t* __restrict__ buf0, uint64_t* __restrict__ buf1,
+                          uint64_t* __restrict__ xk, const uint32_t* __restrict__ xbits) {
+    if (st->status != ST_RUNNING || st->n_levels != level || level != st->gather_level || level >= st->tail_level) return;
+    if (st->lv[level - 1].x_slice_bits == 0) return;
+    pass_body<MAYBE_BIG, true, KeyCfg, true>(st, level, nullptr, buf0, buf1, nullptr, nullptr, xk + 8, nullptr, 0, xbits);
 }
 
 __global__ void __launch_bounds__(256)

@@ -192,3 +192,120 @@ def test_wrong_global_count_is_an_error_on_every_shard_not_a_hang(pkg, oracle):
     finally:
         for c in comms:
             c.close()
+
+
+# ---- sharded build with the exchange ("owner computes") kernels for the large levels ------------------------------------
+@pytest.fixture
+def small_xchg(pkg):
+    """lower the exchange threshold so that unit-test sizes take the path 8 x 1e8 keys take (and every transition out of it)"""
+    pkg.lib().bphf_set_xchg_bits(2.0e5)
+    yield
+    pkg.lib().bphf_set_xchg_bits(4.5e8)
+
+
+def _xchg_levels(m):
+    return m.build_stats()["bucketed_levels"] // 1000
+
+
+@pytest.mark.parametrize("world", [2, 3, 4, 8])
+@pytest.mark.parametrize("n", [70_000, 300_001, 1_000_003, 3_000_000])
+def test_sharded_exchange_parity(pkg, oracle, small_xchg, world, n):
+    ms = _run(pkg, oracle, oracle.keygen(n, seed=7 * n + world, kind=0), world)
+    # 1.7 n bits at level 0, 0.76 n at level 1, ...: levels above 2e5 bits are exchange levels
+    want = sum(1 for k in ms[0].build_stats()["keys_in"][:4] if 1.7 * k > 2.0e5)
+    assert _xchg_levels(ms[0]) == want and (want > 0) == (n > 120_000)
+
+
+@pytest.mark.parametrize("how", ["first_empty", "skewed"])
+def test_sharded_exchange_unbalanced_shards(pkg, oracle, small_xchg, how):
+    ms = _run(pkg, oracle, oracle.keygen(900_001, seed=9, kind=0), 4, how=how)
+    assert _xchg_levels(ms[0]) >= 2
+
+
+@pytest.mark.parametrize("gamma", [1.02, 2.0, 5.0, 17.5])
+def test_sharded_exchange_gammas(pkg, oracle, small_xchg, gamma):
+    ms = _run(pkg, oracle, oracle.keygen(400_000, seed=21, kind=1), 3, gamma=gamma)
+    # (gamma 17.5 leaves 2.8 % of the keys per level: two levels and the tail -- too few for an exchange level, which
+    # needs two ordinary levels behind it)
+    assert _xchg_levels(ms[0]) >= (1 if gamma <= 5.0 else 0)
+
+
+@pytest.mark.parametrize("seed", [5, 31, 2 ** 64 - 3])
+def test_sharded_exchange_starting_seed(pkg, oracle, small_xchg, seed):
+    _run(pkg, oracle, oracle.keygen(500_000, seed=4, kind=0), 2, seed=seed)
+
+
+def test_sharded_exchange_comm_is_reusable(pkg, oracle, small_xchg):
+    sh = _sharded(pkg)
+    world = 4
+    comms = sh.ShardComm.local_group([0] * world, 2_000_000, 2.0)
+    try:
+        for n, gamma in [(2_000_000, 1.7), (654_321, 2.0), (2_000_000, 1.7), (5000, 1.7)]:
+            keys = oracle.keygen(n, seed=n, kind=0)
+            ms = sh.build_in_threads(comms, gamma, _split(keys, world, "even"))
+            fp = oracle.fingerprint(oracle.OracleMphf.new_parallel(gamma, keys).levels())
+            for m in ms:
+                assert oracle.fingerprint(m.levels()) == fp
+    finally:
+        for c in comms:
+            c.close()
+
+
+def test_sharded_exchange_duplicates_across_shards_report_max_iters(pkg, small_xchg):
+    sh = _sharded(pkg)
+    keys = np.arange(400_000, dtype=np.uint64)
+    comms = sh.ShardComm.local_group([0, 0], 800_000, 1.7)
+    try:
+        with pytest.raises(pkg.MphfPanic) as e:
+            sh.build_in_threads(comms, 1.7, [keys, keys.copy()])  # every key appears in both shards
+        assert "unique hashes" in str(e.value) or e.value.code in (-4, -5)   # or the shards' buffers give out first
+    finally:
+        for c in comms:
+            c.close()
+
+
+def test_sharded_exchange_all_keys_on_one_shard_fails_cleanly_or_matches(pkg, oracle, small_xchg):
+    # the exchange blocks are sized for shards of up to twice the even share: one shard holding everything either still
+    # fits (small sets) or is reported as an error on every shard -- no hang, no wrong structure
+    sh = _sharded(pkg)
+    keys = oracle.keygen(3_000_000, seed=8, kind=0)
+    comms = sh.ShardComm.local_group([0] * 4, len(keys), 1.7)
+    try:
+        shards = [keys[:0], keys[:0], keys[:0], keys]
+        try:
+            ms = sh.build_in_threads(comms, 1.7, shards)
+        except pkg.MphfPanic as e:
+            assert e.code in (-4, -5)
+        else:
+            assert_same_levels(ms[0].levels(), oracle.OracleMphf.new_parallel(1.7, keys).levels())
+    finally:
+        for c in comms:
+            c.close()
+
+
+def test_sharded_exchange_wrong_global_count_is_an_error_not_a_hang(pkg, oracle, small_xchg):
+    import threading
+    import time
+    sh = _sharded(pkg)
+    keys = oracle.keygen(400_000, seed=77, kind=0)
+    comms = sh.ShardComm.local_group([0, 0], 800_000, 1.7)
+    errs = [None, None]
+
+    def run(r):
+        try:
+            comms[r].build(1.7, keys[r * 200_000:(r + 1) * 200_000], 480_000)   # shards hold 400 000 keys in total
+        except pkg.MphfPanic as e:
+            errs[r] = e
+
+    t0 = time.time()
+    ts = [threading.Thread(target=run, args=(r,)) for r in range(2)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    try:
+        assert all(e is not None for e in errs) and time.time() - t0 < 5.0
+        assert all(e.code in (-6, -4) for e in errs)
+    finally:
+        for c in comms:
+            c.close()
