@@ -258,6 +258,9 @@ BPHF_API int bphf_set_query_mode(int mode);
  * 2 = 2*i (benches/build.rs:11).  out is a device pointer, i runs over [start, start+n). */
 BPHF_API int bphf_keygen_u64(uint64_t *out_dev, uint64_t start, uint64_t n, uint64_t seed, int kind, int device,
                              void *stream);
+/* the "L2-atomic ceiling" of this device, measured: best-of-3 time of n_ops random 4-byte operations on an array of
+ * array_bytes bytes -- kind 0: non-returning OR (REDG), 1: returning fetch_or (ATOMG), 2: L1-bypassing load */
+BPHF_API int bphf_l2_probe(int kind, uint64_t array_bytes, uint64_t n_ops, int device, float *ms_out);
 /* MPHF property at full size: *n_bad = number of values that are >= n or repeat an earlier one */
 BPHF_API int bphf_check_permutation(const uint64_t *vals_dev, uint64_t n, int device, uint64_t *n_bad);
 /* order-independent checksum (sum and xor of splitmix64(v)) of a device u64 array */

@@ -38,7 +38,7 @@ SYMBOLS = [
     "bphf_comm_create", "bphf_comm_ipc_handle", "bphf_comm_connect_ipc", "bphf_comm_connect_local",
     "bphf_comm_destroy", "bphf_build_sharded_u64", "bphf_build_chunked_u64",
     "bphf_build_keys", "bphf_hash_batch_keys", "bphf_from_levels_keys", "bphf_key_kind",
-    "bphf_build_stream", "bphf_hash_batch_stream", "bphf_set_ingest_mode", "bphf_set_xchg_bits",
+    "bphf_build_stream", "bphf_hash_batch_stream", "bphf_set_ingest_mode", "bphf_set_xchg_bits", "bphf_l2_probe",
 ]
 
 
@@ -175,6 +175,8 @@ def lib():
     L.bphf_set_ingest_mode.argtypes = [i32, u64]
     L.bphf_set_xchg_bits.restype = i32
     L.bphf_set_xchg_bits.argtypes = [dbl]
+    L.bphf_l2_probe.restype = i32
+    L.bphf_l2_probe.argtypes = [i32, u64, u64, i32, C.POINTER(C.c_float)]
     L.bphf_build_stream.restype = i32
     L.bphf_build_stream.argtypes = [vp, u64, vp, u64, vp, u64, dbl, i32, u64, i32, i32, C.POINTER(vp)]
     L.bphf_hash_batch_stream.restype = i32

@@ -110,7 +110,7 @@ static const DeviceInfo& device_info(int dev) {
                                           (const void*)pass_x_kernel<false>, (const void*)pass_x_kernel<true>,
                                           (const void*)xscatter_kernel<false>, (const void*)xscatter_kernel<true>};
             for (const void* k : ring_kernels) {
-                CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PASS_SMEM_BYTES));
+                CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XS_SMEM_BYTES));
                 CK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 60));
             }
         }
@@ -134,7 +134,7 @@ static const DeviceInfo& device_info(int dev) {
                 (const void*)query_kernel<false>, (const void*)query_kernel<true>, (const void*)map_permute_kernel<false>,
                 (const void*)map_get_kernel<false>, (const void*)map_scatter_kernel, (const void*)map_gather_kernel,
                 (const void*)pack_query_kernel, (const void*)set_base_rank_kernel, (const void*)query_sync_kernel,
-                (const void*)key_words_kernel, (const void*)keygen_kernel, (const void*)check_perm_kernel, (const void*)checksum_kernel,
+                (const void*)key_words_kernel, (const void*)l2_probe_kernel, (const void*)keygen_kernel, (const void*)check_perm_kernel, (const void*)checksum_kernel,
                 (const void*)shard_barrier_kernel, (const void*)or_collide_merge_kernel, (const void*)tail_gather_kernel,
                 (const void*)shard_gather_kernel<false>, (const void*)shard_gather_kernel<true>,
                 (const void*)shard_collect_kernel, (const void*)shard_switch_kernel,
@@ -372,7 +372,10 @@ struct Plan {
 static int g_build_mode = 0;
 // sharded builds (mode 0): a level is built by the exchange ("owner computes") kernels when its bit count exceeds this
 // (the full-width (a, collide) pair of the merge path would not stay L2 resident); 0 disables the exchange path
-static double g_xchg_bits = 4.5e8;
+static double g_xchg_bits = [] {
+    const char* e = getenv("BPHF_XCHG_BITS");  // measurement override (bphf_set_xchg_bits is the API)
+    return e ? atof(e) : 4.5e8;
+}();
 static uint64_t g_bucket_min_keys = 1ull << 20;   // levels below this are built by the plain kernels
 
 // a level is built by the bucketed kernels when its (a, collide) pair clearly exceeds the L2: random L2 atomics fall
@@ -850,9 +853,9 @@ struct Builder {
         const size_t e0 = begin_event(0, level);
         {
             const void* fn = maybe_big ? (const void*)xscatter_kernel<true> : (const void*)xscatter_kernel<false>;
-            const int grid = resident_grid(fn, PASS_THREADS, PASS_SMEM_BYTES);
-            if (maybe_big) xscatter_kernel<true><<<grid, PASS_THREADS, PASS_SMEM_BYTES, s>>>(d_state, level, d_keys, d_buf[0], d_buf[1], comm->dev);
-            else xscatter_kernel<false><<<grid, PASS_THREADS, PASS_SMEM_BYTES, s>>>(d_state, level, d_keys, d_buf[0], d_buf[1], comm->dev);
+            const int grid = resident_grid(fn, PASS_THREADS, XS_SMEM_BYTES);
+            if (maybe_big) xscatter_kernel<true><<<grid, PASS_THREADS, XS_SMEM_BYTES, s>>>(d_state, level, d_keys, d_buf[0], d_buf[1], comm->dev);
+            else xscatter_kernel<false><<<grid, PASS_THREADS, XS_SMEM_BYTES, s>>>(d_state, level, d_keys, d_buf[0], d_buf[1], comm->dev);
             CK(cudaGetLastError());
             launches++;
         }
@@ -1070,7 +1073,7 @@ static int build_once(const uint64_t* keys, uint64_t n, double gamma, int has_se
         for (size_t l = 0; l + 2 < plan.lv.size(); l++) {
             const uint64_t bits_lo = level_size(gamma, plan.lv[l].k_lo), bits_up = level_size(gamma, plan.lv[l].k_up);
             const uint64_t slice_words = round_up8(((bits_up + 63) / 64 + comm->world - 1) / comm->world);
-            if ((double)bits_lo > g_xchg_bits && slice_words * 64 <= (1ull << 32)) xl = (uint32_t)l + 1;
+            if ((double)bits_lo > g_xchg_bits && slice_words * 64 < (1ull << 32)) xl = (uint32_t)l + 1;
             else break;
         }
         b.xchg_levels = xl;
@@ -2368,6 +2371,39 @@ BPHF_API int bphf_map_get_batch_u64(const bphf_mphf* m, const uint64_t* map_keys
 }
 
 // ---- utilities --------------------------------------------------------------------------------
+BPHF_API int bphf_l2_probe(int kind, uint64_t array_bytes, uint64_t n_ops, int device, float* ms_out) {
+    API_BEGIN
+    if (!ms_out || kind < 0 || kind > 2 || array_bytes < 4 || n_ops == 0) return fail(BPHF_ERR_ARG, "bad argument");
+    const DeviceInfo& info = device_info(device);
+    DeviceGuard guard(device);
+    cudaStream_t s = own_stream(device, false);
+    uint32_t *arr = nullptr, *sink = nullptr;
+    CK(cudaMallocAsync((void**)&arr, array_bytes, s));
+    CK(cudaMallocAsync((void**)&sink, 4, s));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; rep++) {
+        CK(cudaMemsetAsync(arr, 0, array_bytes, s));
+        CK(cudaEventRecord(e0, s));
+        l2_probe_kernel<<<info.sm_count * 8, 256, 0, s>>>(arr, array_bytes / 4, n_ops, kind, sink);
+        CK(cudaEventRecord(e1, s));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        best = std::min(best, ms);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    CK(cudaFreeAsync(arr, s));
+    CK(cudaFreeAsync(sink, s));
+    CK(cudaStreamSynchronize(s));
+    *ms_out = best;
+    return BPHF_OK;
+    API_END
+}
+
 BPHF_API int bphf_keygen_u64(uint64_t* out_dev, uint64_t start, uint64_t n, uint64_t seed, int kind, int device, void* stream) {
     API_BEGIN
     if (n == 0) return BPHF_OK;

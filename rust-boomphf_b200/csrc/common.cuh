@@ -205,7 +205,7 @@ __host__ __device__ inline void make_level(BuildState* st, uint32_t level, uint6
     d.x_slice_bits = 0;
     if (st->shard_world > 1 && level < st->xchg_levels) {
         const uint64_t slice_words = round_up8((d.n_words + st->shard_world - 1) / st->shard_world);
-        d.x_slice_bits = slice_words * 64;  // <= 2^32 by the host's choice of xchg_levels: slots travel as 32-bit offsets
+        d.x_slice_bits = slice_words * 64;  // < 2^32 by the host's choice of xchg_levels: slots travel as 32-bit offsets
     }
 }
 

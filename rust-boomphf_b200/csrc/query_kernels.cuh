@@ -441,6 +441,39 @@ __host__ __device__ __forceinline__ uint64_t splitmix64_fin(uint64_t z) {
     return z ^ (z >> 31);
 }
 
+// "L2-atomic ceiling" probe (north_star): n_ops random 4-byte operations on an array of n_words words, 8 in flight per
+// thread -- kind 0: fire-and-forget OR (REDG), 1: returning fetch_or (ATOMG), 2: ld.cg probe.  bench.py times it in
+// process to quote the build kernels against what this very GPU sustains (tools/microbench_atomics.cu is the long form).
+__global__ void __launch_bounds__(256) l2_probe_kernel(uint32_t* __restrict__ arr, uint64_t n_words, uint64_t n_ops, int kind,
+                                                       uint32_t* __restrict__ sink) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x * 8;
+    uint32_t acc = 0;
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x * 8 + threadIdx.x; base < n_ops; base += stride) {
+        uint64_t w[8];
+        uint32_t m[8], old[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const uint64_t h = splitmix64_fin((base + (uint64_t)j * blockDim.x) * 0x9E3779B97F4A7C15ULL + 12345);
+            w[j] = (uint64_t)(((h >> 32) * n_words) >> 32);
+            m[j] = 1u << (h & 31);
+            old[j] = 0;
+        }
+        if (kind == 0) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) asm volatile("red.global.or.b32 [%0], %1;" ::"l"(arr + w[j]), "r"(m[j]) : "memory");
+        } else if (kind == 1) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) old[j] = atomicOr(arr + w[j], m[j]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; j++) old[j] = __ldcg(arr + w[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc += old[j];
+    }
+    if (acc == 0x12345678u) *sink = acc;
+}
+
 __global__ void keygen_kernel(uint64_t* __restrict__ out, uint64_t start, uint64_t n, uint64_t seed, int kind) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {

@@ -47,6 +47,12 @@ __device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t* p) {
 // ---------------------------------------------------------------------------------------------
 // xscatter_kernel: route this shard's keys of an exchange level to the owners of their slots
 // ---------------------------------------------------------------------------------------------
+// Per warp, in shared memory: for every owner a ring of XS_STAGE (key, offset) pairs + its fill, head and the number
+// of entries already written to the owner's block.  A step takes 32 keys (one per lane): __match_any groups the lanes
+// by owner, each group appends to its owner's ring, and an owner with >= 32 staged pairs is flushed: 32 keys to the
+// local block (256 B), 32 offsets to the owner's receive block over NVLink (128 B).
+constexpr size_t XS_SMEM_BYTES = PASS_SMEM_BYTES + (size_t)WP_WARPS * (SHARD_MAX * XS_STAGE * 4 + 3 * SHARD_MAX * 4);
+
 template <bool MAYBE_BIG>
 __global__ void __launch_bounds__(PASS_THREADS, BPHF_PASS_CTAS)
     xscatter_kernel(BuildState* __restrict__ st, uint32_t level, const uint64_t* __restrict__ user_keys,
@@ -57,16 +63,26 @@ __global__ void __launch_bounds__(PASS_THREADS, BPHF_PASS_CTAS)
     if (slice_bits == 0) return;
     extern __shared__ __align__(128) unsigned char pass_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // same carve-up as pass_body: 4 KB staging (here SHARD_MAX x XS_STAGE keys), two 2 KB key tiles, two mbarriers
-    uint64_t* __restrict__ stg = reinterpret_cast<uint64_t*>(pass_smem) + warp * WP_RING;
+    // carve-up as in pass_body (4 KB key staging, two 2 KB key tiles, two mbarriers) + offsets and ring state
+    uint64_t* __restrict__ stg_key = reinterpret_cast<uint64_t*>(pass_smem) + warp * WP_RING;
     uint64_t* __restrict__ stage = reinterpret_cast<uint64_t*>(pass_smem) + WP_WARPS * WP_RING + warp * 2 * WP_TILE;
     uint64_t* mbar = reinterpret_cast<uint64_t*>(pass_smem) + WP_WARPS * (WP_RING + 2 * WP_TILE) + warp * 2;
-    static_assert(SHARD_MAX * XS_STAGE <= WP_RING, "per-owner staging must fit the warp's ring");
+    uint32_t* __restrict__ stg_loc = reinterpret_cast<uint32_t*>(pass_smem + PASS_SMEM_BYTES) + warp * (SHARD_MAX * XS_STAGE);
+    uint32_t* __restrict__ ring_st =
+        reinterpret_cast<uint32_t*>(pass_smem + PASS_SMEM_BYTES) + WP_WARPS * (SHARD_MAX * XS_STAGE) + warp * (3 * SHARD_MAX);
+    uint32_t* __restrict__ r_cnt = ring_st;                   // staged pairs per owner
+    uint32_t* __restrict__ r_head = ring_st + SHARD_MAX;      // ring head per owner
+    uint32_t* __restrict__ r_pos = ring_st + 2 * SHARD_MAX;   // entries written to the (region, owner) block
+    static_assert(SHARD_MAX * XS_STAGE <= WP_RING, "per-owner key staging must fit the warp's ring");
 
     const KeyCfg kc(st->kc);
     const uint64_t c_bits = cu->bits, c_sp0 = cu->sp0;
     const bool c_big = MAYBE_BIG && (c_bits >> 32) != 0;
     const uint32_t R = st->n_regions, world = cd.world, me = cd.rank, sub_cap = st->x_sub_cap;
+    // owner of a slot below 2^32: floor(slot / slice) through a reciprocal that never overestimates + a correction
+    // (slices are below 2^32 bits by the host's choice of exchange levels)
+    const uint32_t slice32 = (uint32_t)min(slice_bits, (uint64_t)0xffffffffu);
+    const uint32_t slice_inv = (uint32_t)(0xffffffffull / slice32);
     const bool xsrc = level >= 1;  // exchange levels are a prefix: the predecessor is one, too
     const uint64_t* __restrict__ src = xsrc ? (((level - 1) & 1) ? buf1 : buf0) : user_keys;
     const uint64_t k_dense = st->lv[0].k_loc;
@@ -89,28 +105,27 @@ __global__ void __launch_bounds__(PASS_THREADS, BPHF_PASS_CTAS)
     uint32_t phase = 0;
     uint64_t total = 0;
     bool overflow = false;
-    uint32_t n_o[SHARD_MAX], h_o[SHARD_MAX], pos_o[SHARD_MAX];  // per owner: staged keys, ring head, entries written
 
-    auto slot_of = [&](uint64_t key) -> uint64_t {
-        return c_big ? level_index<true>(kc, c_sp0, key, c_bits) : level_index<false>(kc, c_sp0, key, c_bits);
-    };
     const uint64_t n_gw = (uint64_t)gridDim.x * WP_WARPS;
     for (uint64_t r = (uint64_t)blockIdx.x * WP_WARPS + warp; r < R; r += n_gw) {
-#pragma unroll
-        for (int o = 0; o < SHARD_MAX; o++) n_o[o] = h_o[o] = pos_o[o] = 0;
-        // `cnt` staged keys of owner o -> the block (r, o): key stays here, its offset in o's slice goes to o
-        auto flush = [&](int o, uint32_t& n, uint32_t& h, uint32_t& pos, uint32_t cnt) {
+        if (lane < 3 * SHARD_MAX) ring_st[lane] = 0;
+        __syncwarp();
+        // `cnt` staged pairs of owner o -> block (r, o): the key stays here, its offset in o's slice goes to o
+        auto flush = [&](uint32_t o, uint32_t cnt) {
+            const uint32_t h = r_head[o], pos = r_pos[o];
             if (pos + cnt > sub_cap) {
-                overflow = true;  // more keys for one owner than the block holds (grossly unbalanced hash / shards)
+                overflow = true;  // more keys for one owner than the block holds (grossly unbalanced shards / hash)
             } else if ((uint32_t)lane < cnt) {
-                const uint64_t kk = stg[o * XS_STAGE + ((h + lane) & (XS_STAGE - 1))];
-                const uint64_t loc = slot_of(kk) - (uint64_t)o * slice_bits;
-                dst[((uint64_t)r * world + o) * sub_cap + pos + lane] = kk;
-                cd.xidx[o][((uint64_t)me * R + r) * sub_cap + pos + lane] = (uint32_t)loc;
+                const uint32_t e = o * XS_STAGE + ((h + lane) & (XS_STAGE - 1));
+                dst[((uint64_t)r * world + o) * sub_cap + pos + lane] = stg_key[e];
+                cd.xidx[o][((uint64_t)me * R + r) * sub_cap + pos + lane] = stg_loc[e];
             }
-            pos += cnt;
-            h = (h + cnt) & (XS_STAGE - 1);
-            n -= cnt;
+            __syncwarp();
+            if (lane == 0) {
+                r_head[o] = (h + cnt) & (XS_STAGE - 1);
+                r_cnt[o] -= cnt;
+                r_pos[o] = pos + cnt;
+            }
             __syncwarp();
         };
         const uint32_t n_seg = xsrc ? world : 1u;
@@ -123,7 +138,7 @@ __global__ void __launch_bounds__(PASS_THREADS, BPHF_PASS_CTAS)
             } else {
                 n_rt = r < dense_tiles ? (dense_tiles - r + R - 1) / R : 0;
             }
-            const uint64_t blk = ((uint64_t)r * world + seg) * sub_cap;                  // xsrc: key block
+            const uint64_t blk = ((uint64_t)r * world + seg) * sub_cap;                                // xsrc: key block
             const uint32_t* __restrict__ bits = src_bits + (((uint64_t)seg * R + r) * sub_cap) / 32;  // xsrc: its survivor bits
             auto tile_ptr = [&](uint64_t j) -> const uint64_t* {
                 return xsrc ? src + blk + j * WP_TILE : src + (r + j * R) * WP_TILE;
@@ -145,56 +160,70 @@ __global__ void __launch_bounds__(PASS_THREADS, BPHF_PASS_CTAS)
             for (uint64_t j = 0; j < n_rt; j++) {
                 const int b = (int)(j & 1);
                 const uint32_t valid = tile_valid(j);
-                uint64_t* __restrict__ tile = stage + b * WP_TILE;
+                // Context::filter of the previous level: the owner's answers, one bit per key in arrival order
+                uint32_t bw[PASS_KPT];
+#pragma unroll
+                for (int q = 0; q < PASS_KPT; q++) bw[q] = xsrc ? ld_cg_u32(bits + j * PASS_KPT + q) : 0xffffffffu;
+                uint64_t key[PASS_KPT];
                 if (tile_tma(j)) {
                     mbar_wait(&mbar[b], (phase >> b) & 1u);
                     phase ^= 1u << b;
+#pragma unroll
+                    for (int q = 0; q < PASS_KPT; q++) key[q] = stage[b * WP_TILE + lane + 32 * q];
+                    __syncwarp();
+                    if (lane == 0) fence_proxy_async();
                 } else {
                     const uint64_t* __restrict__ tp = tile_ptr(j);
 #pragma unroll
-                    for (int q = 0; q < PASS_KPT; q++)
-                        if (lane + 32u * q < valid) tile[lane + 32 * q] = ld_stream_u64(tp + lane + 32 * q);
-                    __syncwarp();
+                    for (int q = 0; q < PASS_KPT; q++) key[q] = (lane + 32u * q < valid) ? ld_stream_u64(tp + lane + 32 * q) : 0;
                 }
-#pragma unroll 1
-                for (int q = 0; q < PASS_KPT; q++) {
-                    bool live = lane + 32u * q < valid;
-                    // Context::filter of the previous level: the owner's answer, one bit per key in arrival order
-                    if (xsrc) live = live && ((ld_cg_u32(bits + j * PASS_KPT + q) >> lane) & 1u);
-                    const uint64_t key = tile[lane + 32 * q];
-                    uint32_t own = 0;
-                    if (live) own = (uint32_t)(slot_of(key) / slice_bits);
+                issue(j + 2);  // this tile's buffer is free again
 #pragma unroll
-                    for (int o = 0; o < SHARD_MAX; o++) {
-                        if ((uint32_t)o < world) {
-                            const bool mine = live && own == (uint32_t)o;
-                            const uint32_t mk = __ballot_sync(0xffffffffu, mine);
-                            if (mine) stg[o * XS_STAGE + ((h_o[o] + n_o[o] + __popc(mk & lt_mask)) & (XS_STAGE - 1))] = key;
-                            n_o[o] += __popc(mk);
+                for (int q = 0; q < PASS_KPT; q++) {
+                    const bool live = (lane + 32u * q < valid) && ((bw[q] >> lane) & 1u);
+                    uint32_t own = 0xffu, loc = 0;
+                    if (live) {
+                        if (c_big) {
+                            const uint64_t slot = level_index<true>(kc, c_sp0, key[q], c_bits);
+                            own = (uint32_t)(slot / slice_bits);
+                            loc = (uint32_t)(slot - (uint64_t)own * slice_bits);
+                        } else {
+                            const uint32_t slot = (uint32_t)level_index<false>(kc, c_sp0, key[q], c_bits);
+                            own = __umulhi(slot, slice_inv);
+                            while (slot - own * slice32 >= slice32) own++;  // at most two steps
+                            loc = slot - own * slice32;
                         }
                     }
+                    const uint32_t grp = __match_any_sync(0xffffffffu, own);
+                    if (live) {
+                        const uint32_t e = own * XS_STAGE + ((r_head[own] + r_cnt[own] + __popc(grp & lt_mask)) & (XS_STAGE - 1));
+                        stg_key[e] = key[q];
+                        stg_loc[e] = loc;
+                    }
                     __syncwarp();
-#pragma unroll
-                    for (int o = 0; o < SHARD_MAX; o++)
-                        if ((uint32_t)o < world && n_o[o] >= 32) flush(o, n_o[o], h_o[o], pos_o[o], 32);
+                    if (live && (grp & lt_mask) == 0) r_cnt[own] += __popc(grp);  // the group's first lane
+                    __syncwarp();
+                    uint32_t full = __ballot_sync(0xffffffffu, (uint32_t)lane < world && r_cnt[lane & (SHARD_MAX - 1)] >= 32);
+                    while (full) {
+                        const uint32_t o = __ffs(full) - 1;
+                        full &= full - 1;
+                        flush(o, 32);
+                    }
                 }
-                __syncwarp();
-                if (lane == 0) fence_proxy_async();
-                issue(j + 2);  // this tile's buffer is free again
             }
         }
-        // end of the region: the rest of every owner's staging, then the block counts (here and at the owner)
-#pragma unroll
-        for (int o = 0; o < SHARD_MAX; o++) {
-            if ((uint32_t)o < world) {
-                if (n_o[o]) flush(o, n_o[o], h_o[o], pos_o[o], n_o[o]);
-                if (lane == 0) {
-                    dst_cnt[r * world + o] = overflow ? 0u : pos_o[o];
-                    cd.xcnt[o][(size_t)me * R + r] = overflow ? 0u : pos_o[o];
-                }
-                total += pos_o[o];
+        // end of the region: the rest of every owner's ring, then the block counts (here and at the owner)
+        for (uint32_t o = 0; o < world; o++) {
+            const uint32_t left = r_cnt[o];
+            if (left) flush(o, left);
+            const uint32_t wrote = r_pos[o];
+            if (lane == 0) {
+                dst_cnt[r * world + o] = overflow ? 0u : wrote;
+                cd.xcnt[o][(size_t)me * R + r] = overflow ? 0u : wrote;
             }
+            total += wrote;
         }
+        __syncwarp();
     }
     if (lane == 0) {
         if (overflow) st->status = ST_ERR_LIST_OVERFLOW;

@@ -43,7 +43,7 @@ import pytest  # noqa: E402
 @pytest.mark.gpu
 def test_bench_line_on_the_gpu_has_every_contract_key():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--keys", "4000000", "--steps", "3", "--warmup", "3",
-                          "--cpu-baseline-keys", "4000000"], capture_output=True, text=True, timeout=600)
+                          "--cpu-baseline-keys", "4000000", "--no-extra-configs"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])   # the JSON line is the last line of stdout
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
@@ -54,6 +54,9 @@ def test_bench_line_on_the_gpu_has_every_contract_key():
     assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(line["roofline"])
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["bit_exact_vs_gpu"] is True
     assert line["lookup"]["permutation_ok"] is True
+    la = line["roofline"]["l2_atomic"]   # the L2-atomic ceiling, measured in process
+    assert la["ceilings_measured_Gops"]["atom"] > 1 and la["ops_per_build_per_gpu"]["fetch_or"] > 4000000 and 0 < la["frac_of_ceiling"] < 1.5
+    assert line["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
 
 
 # ---- the warm-up second of a multi-rank run is a collective decision (gloo, world size 2, CPU) -----------------
