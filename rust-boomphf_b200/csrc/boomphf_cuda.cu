@@ -141,7 +141,7 @@ static const DeviceInfo& device_info(int dev) {
                 (const void*)shard_gather_x_kernel<false>, (const void*)shard_gather_x_kernel<true>,
                 (const void*)pass_x_kernel<false>, (const void*)pass_x_kernel<true>,
                 (const void*)xscatter_kernel<false>, (const void*)xscatter_kernel<true>, (const void*)xmark_kernel,
-                (const void*)xfinalize_kernel, (const void*)xbits_kernel, (const void*)xpop_kernel};
+                (const void*)xfinalize_kernel, (const void*)xpush_kernel, (const void*)xbits_kernel, (const void*)xpop_kernel};
             for (const void* k : all_kernels) CK(cudaFuncGetAttributes(&fa, k));
         }
         if (prev != dev) CK(cudaSetDevice(prev));
@@ -261,6 +261,8 @@ struct bphf_comm {
                                  // become resident next to a peer's spinning barrier kernel
     uint64_t epoch = 0;          // barrier counter; advances identically on every shard
     cudaStream_t stream = nullptr;  // the shard's build stream (owned: one hardware queue per live shard)
+    cudaStream_t push_stream = nullptr;  // exchange levels: final a slices go to the peers next to the build stream's work
+    cudaEvent_t push_ev = nullptr;
     void* pinned = nullptr;         // pinned staging for the build state read-back
     CommDev dev;
     // exchange levels (xchg_kernels.cuh): world x x_regions blocks of x_sub_cap entries each way
@@ -514,6 +516,7 @@ struct Builder {
     bphf_comm* comm = nullptr;  // sharded build: the arenas live in the comm's peer-visible allocation
     bool gathered = false;      // sharded build: the remaining keys were collected on every shard; unsharded from here
     uint32_t xchg_levels = 0;   // sharded build: leading levels built by the exchange kernels (same on every shard)
+    uint32_t xchg_launched = 0; // exchange levels enqueued so far
     std::vector<EventPair> events;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
 
@@ -828,8 +831,12 @@ struct Builder {
         CK(cudaGetLastError());
         end_event(ev);
         launches++;
-        // nobody may start the next build (and overwrite its exchange slot) before every shard has read it
-        if (comm) launch_barrier(BAR_PLAIN, 0);
+        // nobody may start the next build (and overwrite its exchange slot) before every shard has read it; the final a
+        // slices of the exchange levels that this shard pushed on the side stream are complete before it signals
+        if (comm) {
+            join_pushes();
+            launch_barrier(BAR_PLAIN, 0);
+        }
     }
     // ---- sharded build: device-side barrier and OR-collide merge over peer memory ---------------------
     void launch_barrier(uint32_t kind, uint32_t level) {
@@ -871,17 +878,33 @@ struct Builder {
         const uint64_t per = (pairs + comm->world - 1) / comm->world;
         const int fgrid = (int)std::min<uint64_t>(std::max<uint64_t>(1, (per + FIN_THREADS - 1) / FIN_THREADS), (uint64_t)info.sm_count * 4);
         xfinalize_kernel<<<fgrid, FIN_THREADS, 0, s>>>(d_state, level, comm->dev);
+        // the final slice goes to the peers on the side stream, next to xbits and everything that follows
+        CK(cudaEventRecord(comm->push_ev, s));
+        CK(cudaStreamWaitEvent(comm->push_stream, comm->push_ev, 0));
+        xpush_kernel<<<std::max(1, fgrid / 2), FIN_THREADS, 0, comm->push_stream>>>(d_state, level, comm->dev);
         xbits_kernel<<<wgrid, PASS_THREADS, 0, s>>>(d_state, level, comm->dev, c32());
         CK(cudaGetLastError());
-        launches += 3;
+        launches += 4;
         end_event(e1);
         const size_t em2 = begin_event(4, level);
         launch_barrier(BAR_XDONE, level);
         end_event(em2);
-        const int pgrid = (int)std::min<uint64_t>(std::max<uint64_t>(1, (pairs + FIN_THREADS - 1) / FIN_THREADS), (uint64_t)info.sm_count * 8);
-        xpop_kernel<<<pgrid, FIN_THREADS, 0, s>>>(d_state, level, d_words, d_blockpop);
-        CK(cudaGetLastError());
-        launches++;
+        xchg_launched = std::max(xchg_launched, level + 1);
+    }
+    // every shard's pushes have to be complete before anybody reads a replica: this shard's join the build stream in front
+    // of the barrier that ends the build; the rank popcounts of the exchange levels follow that barrier
+    void join_pushes() {
+        if (!comm || !xchg_launched) return;
+        CK(cudaEventRecord(comm->push_ev, comm->push_stream));
+        CK(cudaStreamWaitEvent(s, comm->push_ev, 0));
+    }
+    void launch_xpop() {
+        for (uint32_t level = 0; level < xchg_launched; level++) {
+            const int pgrid = info.sm_count * 8;
+            xpop_kernel<<<pgrid, FIN_THREADS, 0, s>>>(d_state, level, d_words, d_blockpop);
+            CK(cudaGetLastError());
+            launches++;
+        }
     }
     // first level after the exchange levels: filter by the owners' survivor bits, then as any merge-mode level
     void launch_pass_x(uint32_t level) {
@@ -1366,6 +1389,7 @@ static int build_once(const uint64_t* keys, uint64_t n, double gamma, int has_se
     m->n_levels = st.n_levels;
     m->words_used = st.words_used;
     m->lv.assign(st.lv, st.lv + st.n_levels);
+    b.launch_xpop();  // exchange levels: rank popcounts of the complete level (after the barrier that ended the build)
     const uint64_t n_blocks = st.words_used / 8;
     handle_alloc(&m->d_ranks, std::max<uint64_t>(n_blocks, 1) * 8, device, s);
     {
@@ -1711,6 +1735,8 @@ BPHF_API int bphf_comm_create(int device, int rank, int world, uint64_t max_keys
     // plain cudaMalloc: exportable with cudaIpcGetMemHandle (pool memory is not)
     CK(cudaMalloc((void**)&c->base, c->bytes));
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->push_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&c->push_ev, cudaEventDisableTiming));
     CK(cudaHostAlloc(&c->pinned, sizeof(BuildState), cudaHostAllocDefault));
     CK(cudaMemset(c->base, 0, c->bytes));
     CK(cudaDeviceSynchronize());
@@ -1787,6 +1813,8 @@ BPHF_API void bphf_comm_destroy(bphf_comm* c) {
             if (c->peer_is_ipc[p] && c->peer_base[p]) cudaIpcCloseMemHandle(c->peer_base[p]);
         if (c->base) cudaFree(c->base);
         if (c->stream) cudaStreamDestroy(c->stream);
+        if (c->push_stream) cudaStreamDestroy(c->push_stream);
+        if (c->push_ev) cudaEventDestroy(c->push_ev);
         if (c->pinned) cudaFreeHost(c->pinned);
     }
     if (prev >= 0) cudaSetDevice(prev);

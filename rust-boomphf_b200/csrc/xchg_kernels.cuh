@@ -294,26 +294,10 @@ __global__ void __launch_bounds__(PASS_THREADS)
 }
 
 // ---------------------------------------------------------------------------------------------
-// xfinalize_kernel: a &= ~collide on the owner's slice, unique count, final a slice -> every shard's arena
+// xfinalize_kernel: a &= ~collide on the owner's slice + unique count (local);
+// xpush_kernel: the final slice of a -> every other shard's arena.  The push runs on a side stream, next to xbits and the
+// levels that follow: nobody needs another owner's slice before the build is over (lookups use the complete replica).
 // ---------------------------------------------------------------------------------------------
-template <int WORLD>
-__device__ __forceinline__ uint64_t xfinalize_slice(const CommDev& cd, uint64_t pair_off, uint64_t p0, uint64_t p1) {
-    uint64_t uniq = 0;
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    const ulonglong2* __restrict__ a2 = reinterpret_cast<const ulonglong2*>(cd.words[cd.rank]);
-    const ulonglong2* __restrict__ c2 = reinterpret_cast<const ulonglong2*>(cd.coll[cd.rank]);
-    for (uint64_t p = p0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < p1; p += stride) {
-        ulonglong2 a = a2[pair_off + p];
-        const ulonglong2 c = c2[pair_off + p];
-        a.x &= ~c.x;
-        a.y &= ~c.y;
-        uniq += __popcll(a.x) + __popcll(a.y);
-#pragma unroll
-        for (int r = 0; r < WORLD; r++) reinterpret_cast<ulonglong2*>(cd.words[r])[pair_off + p] = a;
-    }
-    return uniq;
-}
-
 __global__ void __launch_bounds__(FIN_THREADS)
     xfinalize_kernel(BuildState* __restrict__ st, uint32_t level, CommDev cd) {
     __shared__ uint64_t warp_u[FIN_THREADS / 32];
@@ -325,16 +309,17 @@ __global__ void __launch_bounds__(FIN_THREADS)
     const uint64_t n_pairs = round_up8(cu->n_words) / 2;
     const uint64_t per = slice_bits / 128;
     const uint64_t p0 = min(n_pairs, per * cd.rank), p1 = min(n_pairs, p0 + per);
+    ulonglong2* __restrict__ a2 = reinterpret_cast<ulonglong2*>(cd.words[cd.rank]) + pair_off;
+    const ulonglong2* __restrict__ c2 = reinterpret_cast<const ulonglong2*>(cd.coll[cd.rank]) + pair_off;
     uint64_t u = 0;
-    switch (cd.world) {
-        case 2: u = xfinalize_slice<2>(cd, pair_off, p0, p1); break;
-        case 3: u = xfinalize_slice<3>(cd, pair_off, p0, p1); break;
-        case 4: u = xfinalize_slice<4>(cd, pair_off, p0, p1); break;
-        case 5: u = xfinalize_slice<5>(cd, pair_off, p0, p1); break;
-        case 6: u = xfinalize_slice<6>(cd, pair_off, p0, p1); break;
-        case 7: u = xfinalize_slice<7>(cd, pair_off, p0, p1); break;
-        case 8: u = xfinalize_slice<8>(cd, pair_off, p0, p1); break;
-        default: break;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t p = p0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < p1; p += stride) {
+        ulonglong2 a = a2[p];
+        const ulonglong2 c = c2[p];
+        a.x &= ~c.x;
+        a.y &= ~c.y;
+        u += __popcll(a.x) + __popcll(a.y);
+        a2[p] = a;
     }
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) u += __shfl_xor_sync(0xffffffffu, u, d);
@@ -346,7 +331,26 @@ __global__ void __launch_bounds__(FIN_THREADS)
         for (int w = 0; w < FIN_THREADS / 32; w++) t += warp_u[w];
         if (t) atomicAdd((unsigned long long*)&st->uniq_count, (unsigned long long)t);
     }
-    __threadfence_system();  // the slice must be performed at every shard before the barrier kernel signals
+}
+
+// (runs concurrently with later kernels of the build stream: it only reads level `level`'s descriptor, which is final)
+__global__ void __launch_bounds__(FIN_THREADS)
+    xpush_kernel(const BuildState* __restrict__ st, uint32_t level, CommDev cd) {
+    const LevelDesc* cu = &st->lv[level];
+    const uint64_t slice_bits = cu->x_slice_bits;
+    if (slice_bits == 0 || st->n_levels < level) return;
+    const uint64_t pair_off = cu->word_off / 2;
+    const uint64_t n_pairs = round_up8(cu->n_words) / 2;
+    const uint64_t per = slice_bits / 128;
+    const uint64_t p0 = min(n_pairs, per * cd.rank), p1 = min(n_pairs, p0 + per);
+    const ulonglong2* __restrict__ a2 = reinterpret_cast<const ulonglong2*>(cd.words[cd.rank]) + pair_off;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t p = p0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < p1; p += stride) {
+        const ulonglong2 a = a2[p];
+        for (uint32_t r = 0; r < cd.world; r++)
+            if (r != cd.rank) reinterpret_cast<ulonglong2*>(cd.words[r])[pair_off + p] = a;
+    }
+    __threadfence_system();
 }
 
 // ---------------------------------------------------------------------------------------------
