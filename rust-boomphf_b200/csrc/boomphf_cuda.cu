@@ -879,9 +879,14 @@ struct Builder {
         const int fgrid = (int)std::min<uint64_t>(std::max<uint64_t>(1, (per + FIN_THREADS - 1) / FIN_THREADS), (uint64_t)info.sm_count * 4);
         xfinalize_kernel<<<fgrid, FIN_THREADS, 0, s>>>(d_state, level, comm->dev);
         // the final slice goes to the peers on the side stream, next to xbits and everything that follows
-        CK(cudaEventRecord(comm->push_ev, s));
-        CK(cudaStreamWaitEvent(comm->push_stream, comm->push_ev, 0));
-        xpush_kernel<<<std::max(1, fgrid / 2), FIN_THREADS, 0, comm->push_stream>>>(d_state, level, comm->dev);
+        // (shards that share one GPU -- tests -- keep to their one stream: with more streams than hardware queues a
+        // peer's spinning barrier kernel can sit in front of the very kernel it waits for)
+        cudaStream_t ps = comm->co_located ? s : comm->push_stream;
+        if (ps != s) {
+            CK(cudaEventRecord(comm->push_ev, s));
+            CK(cudaStreamWaitEvent(ps, comm->push_ev, 0));
+        }
+        xpush_kernel<<<std::max(1, fgrid / 2), FIN_THREADS, 0, ps>>>(d_state, level, comm->dev);
         xbits_kernel<<<wgrid, PASS_THREADS, 0, s>>>(d_state, level, comm->dev, c32());
         CK(cudaGetLastError());
         launches += 4;
@@ -894,7 +899,7 @@ struct Builder {
     // every shard's pushes have to be complete before anybody reads a replica: this shard's join the build stream in front
     // of the barrier that ends the build; the rank popcounts of the exchange levels follow that barrier
     void join_pushes() {
-        if (!comm || !xchg_launched) return;
+        if (!comm || !xchg_launched || comm->co_located) return;
         CK(cudaEventRecord(comm->push_ev, comm->push_stream));
         CK(cudaStreamWaitEvent(s, comm->push_ev, 0));
     }
@@ -1732,6 +1737,11 @@ BPHF_API int bphf_comm_create(int device, int rank, int world, uint64_t max_keys
     c->dev.world = (uint32_t)world;
     c->dev.x_sub_cap = c->x_sub_cap;
     c->dev.x_regions = c->x_regions;
+    {
+        const char* e = getenv("BPHF_BARRIER_TIMEOUT_MS");
+        const double ms = e ? atof(e) : 0.0;
+        c->dev.barrier_timeout_ns = ms > 0.0 ? (uint64_t)(ms * 1e6) : BARRIER_TIMEOUT_NS_DEFAULT;
+    }
     // plain cudaMalloc: exportable with cudaIpcGetMemHandle (pool memory is not)
     CK(cudaMalloc((void**)&c->base, c->bytes));
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -1832,7 +1842,11 @@ BPHF_API int bphf_build_sharded_u64(bphf_comm* c, const uint64_t* keys, uint64_t
     if (n_local > n_global) return fail(BPHF_ERR_ARG, "n_local > n_global");
     if (keys_mem != BPHF_MEM_HOST && keys_mem != BPHF_MEM_DEVICE) return fail(BPHF_ERR_ARG, "bad keys_mem");
     if (!(gamma > 1.01)) return fail(BPHF_ERR_GAMMA, "assertion failed: gamma > 1.01");
-    if (c->world == 1) return build_impl(keys, n_local, gamma, has_seed, seed, c->device, keys_mem, nullptr, out);
+    // a one-shard "group" is an ordinary build -- unless BPHF_XCHG_WORLD1 asks for the sharded schedule anyway: the shard
+    // then owns every slot and routes to itself, which is how the exchange kernels are profiled on one GPU (under ncu a
+    // real peer would wait at a device barrier for kernels that the profiler replays one at a time)
+    if (c->world == 1 && !getenv("BPHF_XCHG_WORLD1"))
+        return build_impl(keys, n_local, gamma, has_seed, seed, c->device, keys_mem, nullptr, out);
     // same policy as an unsharded build, on the GLOBAL level sizes (every shard marks full-width levels)
     bool bucket = g_build_mode == 2;
     uint64_t min_keys = g_bucket_min_keys;

@@ -138,6 +138,7 @@ struct CommDev {
     uint32_t* xbits[SHARD_MAX];   // xbits[p]: survivor bits that the owners returned to sender p, [owner o][region r][x_sub_cap / 32]
     uint32_t x_sub_cap;           // entries per (sender, region, owner) block; multiple of 256
     uint32_t x_regions;           // R
+    uint64_t barrier_timeout_ns;  // how long shard_barrier_kernel waits for a peer before it reports ST_ERR_COMM
 };
 
 // ---- bucket geometry --------------------------------------------------------------------------------
@@ -203,7 +204,7 @@ __host__ __device__ inline void make_level(BuildState* st, uint32_t level, uint6
     d.b_range = d.b_count = d.b_cap = 0;
     d.pad_ = 0;
     d.x_slice_bits = 0;
-    if (st->shard_world > 1 && level < st->xchg_levels) {
+    if (level < st->xchg_levels) {  // (0 for unsharded builds)
         const uint64_t slice_words = round_up8((d.n_words + st->shard_world - 1) / st->shard_world);
         d.x_slice_bits = slice_words * 64;  // < 2^32 by the host's choice of xchg_levels: slots travel as 32-bit offsets
     }

@@ -20,7 +20,11 @@
 
 namespace bphf {
 
-constexpr uint64_t BARRIER_TIMEOUT_NS = 4000000000ULL;  // 4 s
+// A shard that never arrives ends the build with ST_ERR_COMM instead of a hang.  The bound has to cover whatever a peer
+// may legitimately still be doing when this shard reaches its first barrier -- the H2D copy of its keys, module load,
+// a late host thread -- so it is generous (30 s; BPHF_BARRIER_TIMEOUT_MS overrides it at bphf_comm_create).  A peer
+// that FAILS does not cost the timeout: it still signals, with its error status.
+constexpr uint64_t BARRIER_TIMEOUT_NS_DEFAULT = 30000000000ULL;
 
 __device__ __forceinline__ uint64_t global_timer_ns() {
     uint64_t t;
@@ -82,7 +86,7 @@ __global__ void __launch_bounds__(32)
         const uint64_t* src = cd.flags[cd.rank] + (size_t)p * FLAG_STRIDE;
         const uint64_t t0 = global_timer_ns();
         while (ld_acquire_sys(src) < epoch) {
-            if (global_timer_ns() - t0 > BARRIER_TIMEOUT_NS) {
+            if (global_timer_ns() - t0 > cd.barrier_timeout_ns) {
                 timeout = true;
                 break;
             }

@@ -290,6 +290,61 @@ def test_baseline_size_100m_properties(pkg, oracle):
     assert st["keys_in"][0] == n and [oracle.level_size(1.7, k) for k in st["keys_in"]] == st["bits"]
 
 
+def test_baseline_size_100m_is_the_oracles_structure_word_for_word(pkg, oracle):
+    """BASELINE configs[1] at full size against the ORACLE (not against itself): 1e8 keys, every level's bits, words and
+    ranks equal what the restated new_parallel builds from the same keys (about 2 s of host time on 16 cores)."""
+    import ctypes as C
+    import torch
+    n = 100_000_000
+    dk = torch.empty(n, dtype=torch.int64, device="cuda")
+    assert pkg.lib().bphf_keygen_u64(C.c_void_p(dk.data_ptr()), 0, n, 1, 0, 0, None) == 0
+    m = pkg.Mphf.new_parallel(1.7, dk, None)
+    keys = oracle.keygen(n, seed=1, kind=0)
+    assert np.array_equal(dk[:1000].cpu().numpy().view(np.uint64), keys[:1000])   # same generator on both sides
+    ref = oracle.OracleMphf.new_parallel(1.7, keys, None, nthreads=len(os.sched_getaffinity(0)))
+    assert_same_levels(m.levels(), ref.levels())
+
+
+def test_natural_policy_buckets_level0_at_3e8_keys_and_matches_the_oracle(pkg, oracle):
+    """3e8 keys: level 0 has 5.1e8 bits > 4.5e8, so the DEFAULT policy builds it with the bucketed (shared-memory)
+    kernels on its own -- no forced mode, no small thresholds -- followed by the plain striped-list levels; all words and
+    ranks against the oracle's new_parallel (about 7 s of host time)."""
+    import ctypes as C
+    import torch
+    n = 300_000_000
+    dk = torch.empty(n, dtype=torch.int64, device="cuda")
+    assert pkg.lib().bphf_keygen_u64(C.c_void_p(dk.data_ptr()), 0, n, 9, 0, 0, None) == 0
+    m = pkg.Mphf.new_parallel(1.7, dk, None)
+    st = m.build_stats()
+    assert st["bucketed_levels"] >= 1 and st["rebuilds"] == 0
+    keys = oracle.keygen(n, seed=9, kind=0)
+    ref = oracle.OracleMphf.new_parallel(1.7, keys, None, nthreads=len(os.sched_getaffinity(0)))
+    assert_same_levels(m.levels(), ref.levels())
+    out = m.hash_batch(dk)
+    bad = C.c_uint64(1)
+    assert pkg.lib().bphf_check_permutation(C.c_void_p(out.data_ptr()), n, 0, C.byref(bad)) == 0 and bad.value == 0
+
+
+def test_level0_beyond_2_pow_32_bits_refuses_buckets_and_matches_the_oracle(pkg, oracle):
+    """gamma * n >= 2^32: level 0 takes the `%` reduction of the full 64-bit hash (src/lib.rs:81) and cannot be bucketed
+    (32-bit slot arithmetic); gamma = 30 keeps the key set small (1.5e8 keys -> 4.5e9 bits) so the oracle finishes in
+    seconds.  Words, ranks and hashes against the oracle."""
+    import ctypes as C
+    import torch
+    n, gamma = 150_000_000, 30.0
+    assert oracle.level_size(gamma, n) >= 2 ** 32
+    dk = torch.empty(n, dtype=torch.int64, device="cuda")
+    assert pkg.lib().bphf_keygen_u64(C.c_void_p(dk.data_ptr()), 0, n, 4, 0, 0, None) == 0
+    m = pkg.Mphf.new_parallel(gamma, dk, None)
+    st = m.build_stats()
+    assert st["bits"][0] >= 2 ** 32 and st["bucketed_levels"] == 0
+    keys = oracle.keygen(n, seed=4, kind=0)
+    ref = oracle.OracleMphf.new_parallel(gamma, keys, None, nthreads=len(os.sched_getaffinity(0)))
+    assert_same_levels(m.levels(), ref.levels())
+    sample = keys[::997]
+    assert np.array_equal(m.hash_batch(sample), ref.hash_batch(sample, nthreads=0))
+
+
 # ---- construction strategies: bucketed shared-memory kernels vs plain L2-atomic kernels -----------------------
 @pytest.fixture
 def small_buckets(pkg):
