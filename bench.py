@@ -25,9 +25,9 @@ sys.path.insert(0, ROOT)
 import __graft_entry__ as ge  # noqa: E402
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
-# (profiles/r02d_summary.md; n = 1e8, gamma = 1.7, one GPU -- only quoted for that workload)
+# (profiles/r02_summary.md; n = 1e8, gamma = 1.7, one GPU -- only quoted for that workload)
 NCU_TRAFFIC_1E8 = {"mark_list_kernel": 0.8472e9 + 9.463e6, "cascade_kernel": 1.450e9 + 641.4e6}
-NCU_TRAFFIC_SOURCE = "ncu --set full, profiles/r02d_summary.md (capture of this code state)"
+NCU_TRAFFIC_SOURCE = "ncu --set full, profiles/r02_summary.md (capture of this code state)"
 
 METRIC = "mphf_build_throughput"
 UNIT = "Mkeys/s"

@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(PASS_THREADS)
 // first source per region x 256 can never overflow, and whoever filters region r appends to it with a private cursor.
 // Why: with one dense list every 256 survivors cost a reservation on ONE global cursor -- 174 k same-address atomics
 // for level 1 of a 1e8-key build -- and those alone held the pass at 0.94 ms against 0.69 ms without them
-// (tools/microbench_pass.cu, profiles/r02a_summary.md); ordering does not matter (only the redo SET feeds the next
+// (tools/microbench_pass.cu, profiles/r02_summary.md); ordering does not matter (only the redo SET feeds the next
 // level).  Lists that other kernels produce stay dense (the input, scatter_kernel's output after the
 // bucketed levels, the collected list of a sharded build): list_is_striped() tells which kind level l has.
 //

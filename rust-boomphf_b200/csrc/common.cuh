@@ -58,7 +58,7 @@ enum BuildStatus : uint32_t {
 // Layout: the words that thousands of warps update or poll at the same time sit in 128-byte lines of their own.  They
 // used to share the first line of the struct: the CTAs waiting at the cascade's grid barrier poll bar_gen, and every
 // update of the append cursor by the CTAs still working queued behind those polls in the same L2 slice
-// (profiles/r02a_summary.md).
+// (profiles/r02_summary.md).
 struct alignas(128) BuildState {
     uint32_t status;
     uint32_t n_levels;    // levels completed so far

@@ -313,7 +313,7 @@ def test_sharded_exchange_wrong_global_count_is_an_error_not_a_hang(pkg, oracle,
 
 def test_exchange_schedule_with_a_single_shard_matches_the_oracle(pkg, oracle, small_xchg, monkeypatch):
     # BPHF_XCHG_WORLD1: the one shard owns every slot and routes to itself -- the configuration the exchange kernels are
-    # profiled in (profiles/r02d_summary.md); same structure as any other build
+    # profiled in (profiles/r02_summary.md); same structure as any other build
     monkeypatch.setenv("BPHF_XCHG_WORLD1", "1")
     ms = _run(pkg, oracle, oracle.keygen(1_000_003, seed=12, kind=0), 1)
     assert _xchg_levels(ms[0]) >= 2
