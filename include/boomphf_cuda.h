@@ -251,6 +251,20 @@ BPHF_API int bphf_set_ingest_mode(int mode, uint64_t ring_keys);
 /* lookup strategy (measurement only; identical results): 0 (default) = level-synchronous kernel over the packed
  * lookup structure, 1 = one thread per key over the same structure */
 BPHF_API int bphf_set_query_mode(int mode);
+/* Lookups against structures larger than the L2 (BASELINE configs[3]; Mphf::hash, src/lib.rs:324-335, over a batch):
+ * the queries are grouped by the slice of level 0 (then level 1, ...) their slot falls in, every slice is probed while
+ * it is L2 resident, and the ranks are put back in the caller's order -- identical results, no random DRAM probe.
+ * mode 0 (default) = used for device-resident batches >= 32 Mi keys against >= 96 MB of lookup structure, 1 = never, 2 = whenever the
+ * structure has a packed form and more than one level (tests).  The other arguments tune it, 0 = default:
+ * slice_shift = log2 of the bits of a level per slice (28), walk_bytes = the trailing levels that fit this many bytes are
+ * walked unpartitioned (40 MiB), batch_keys = queries per pass (2^27; scratch is ~55 B per key and stage),
+ * cap_scale = slice list capacity relative to its plan (1.0; below 1 forces the overflow path: the batch is then redone
+ * by the plain kernel, on the device, without a host round trip). */
+BPHF_API int bphf_set_query_partition(int mode, uint32_t slice_shift, uint64_t walk_bytes, uint64_t batch_keys,
+                                      double cap_scale);
+/* counters of the partitioned lookup: batches launched by this process, batches redone by the plain kernel on `device`
+ * (synchronises the device), stages of the last plan.  Any pointer may be null. */
+BPHF_API int bphf_query_partition_stats(int device, uint64_t *batches, uint64_t *fallbacks, uint32_t *stages);
 
 /* ---- utilities used by tests and bench (device side) ------------------------------------ */
 /* distinct-by-construction synthetic keys: kind 0 = splitmix64 finaliser of

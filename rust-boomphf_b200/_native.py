@@ -33,7 +33,8 @@ SYMBOLS = [
     "bphf_abi_version", "bphf_last_error", "bphf_device_count", "bphf_wy_swap_8byte_tail",
     "bphf_build_u64", "bphf_num_levels", "bphf_level_dims", "bphf_level_export", "bphf_export_all",
     "bphf_total_dims", "bphf_from_levels", "bphf_free", "bphf_hash_batch_u64", "bphf_map_permute_u64",
-    "bphf_map_get_batch_u64", "bphf_get_build_stats", "bphf_set_profile", "bphf_set_build_mode", "bphf_set_query_mode", "bphf_keygen_u64",
+    "bphf_map_get_batch_u64", "bphf_get_build_stats", "bphf_set_profile", "bphf_set_build_mode", "bphf_set_query_mode", "bphf_set_query_partition",
+    "bphf_query_partition_stats", "bphf_keygen_u64",
     "bphf_check_permutation", "bphf_checksum_u64", "bphf_host_alloc", "bphf_host_free",
     "bphf_comm_create", "bphf_comm_ipc_handle", "bphf_comm_connect_ipc", "bphf_comm_connect_local",
     "bphf_comm_destroy", "bphf_build_sharded_u64", "bphf_build_chunked_u64",
@@ -143,6 +144,10 @@ def lib():
     L.bphf_set_profile.argtypes = [i32]
     L.bphf_set_query_mode.restype = i32
     L.bphf_set_query_mode.argtypes = [i32]
+    L.bphf_set_query_partition.restype = i32
+    L.bphf_set_query_partition.argtypes = [i32, u32, u64, u64, dbl]
+    L.bphf_query_partition_stats.restype = i32
+    L.bphf_query_partition_stats.argtypes = [i32, pu64, pu64, pu32]
     L.bphf_set_build_mode.restype = i32
     L.bphf_set_build_mode.argtypes = [i32, u64]
     L.bphf_keygen_u64.restype = i32

@@ -18,6 +18,7 @@
 #include "build_kernels.cuh"
 #include "bucket_kernels.cuh"
 #include "query_kernels.cuh"
+#include "qpart_kernels.cuh"
 #include "shard_kernels.cuh"
 #include "xchg_kernels.cuh"
 
@@ -70,6 +71,24 @@ static DeviceInfo g_dev[MAX_DEVICES];
 static std::mutex g_dev_mutex;
 static int g_profile = 0;
 static int g_query_mode = 0;  // 0: level-synchronous packed kernel, 1: thread-per-key packed kernel (measurement)
+
+// partitioned lookup (qpart_kernels.cuh): structures larger than the L2
+struct QPartCfg {
+    int mode = 0;                      // 0 automatic, 1 never, 2 whenever the structure allows it (tests)
+    uint32_t slice_shift = 28;         // bits of a level per bucket: 2^28 bits = 45 MB of granules
+    uint64_t walk_bytes = 40ull << 20; // the levels left to the walk stage fit this many bytes of granules
+    uint64_t batch_keys = 1ull << 27;  // queries per pass (scratch: ~55 B per key and stage)
+    double cap_scale = 1.0;            // bucket list capacity relative to the planned one (tests: force overflows)
+    // automatic mode: a slice only pays off when it takes many more probes than it has sectors (all of level 0: 9e6
+    // sectors at 1e9 keys), so smaller batches go to the plain kernel ...
+    uint64_t min_keys = 1ull << 25;
+    uint64_t min_struct_bytes = 96ull << 20;  // ... and so do structures that the L2 holds anyway
+};
+static QPartCfg g_qpart;
+static std::mutex g_qpart_mutex;
+__device__ unsigned long long g_qp_fallbacks;  // batches redone by qfallback_kernel on this device
+static std::atomic<uint64_t> g_qp_batches{0};
+static std::atomic<uint32_t> g_qp_last_stages{0};
 
 static const DeviceInfo& device_info(int dev) {
     if (dev < 0 || dev >= MAX_DEVICES) throw CudaFailure{BPHF_ERR_ARG, "device ordinal out of range"};
@@ -134,6 +153,8 @@ static const DeviceInfo& device_info(int dev) {
                 (const void*)query_kernel<false>, (const void*)query_kernel<true>, (const void*)map_permute_kernel<false>,
                 (const void*)map_get_kernel<false>, (const void*)map_scatter_kernel, (const void*)map_gather_kernel,
                 (const void*)pack_query_kernel, (const void*)set_base_rank_kernel, (const void*)query_sync_kernel,
+                (const void*)qfirst_kernel, (const void*)qprobe_kernel, (const void*)qwalk_kernel,
+                (const void*)qrestore_kernel<true>, (const void*)qrestore_kernel<false>, (const void*)qfallback_kernel,
                 (const void*)key_words_kernel, (const void*)l2_probe_kernel, (const void*)keygen_kernel, (const void*)check_perm_kernel, (const void*)checksum_kernel,
                 (const void*)shard_barrier_kernel, (const void*)or_collide_merge_kernel, (const void*)tail_gather_kernel,
                 (const void*)shard_gather_kernel<false>, (const void*)shard_gather_kernel<true>,
@@ -1615,6 +1636,34 @@ BPHF_API int bphf_set_query_mode(int mode) {
     return BPHF_OK;
 }
 
+BPHF_API int bphf_set_query_partition(int mode, uint32_t slice_shift, uint64_t walk_bytes, uint64_t batch_keys, double cap_scale) {
+    if (mode < 0 || mode > 2) return fail(BPHF_ERR_ARG, "partition mode is 0 (automatic), 1 (never) or 2 (whenever possible)");
+    if (slice_shift > 31) return fail(BPHF_ERR_ARG, "slice_shift is at most 31 (levels of the packed structure have < 2^32 bits)");
+    std::lock_guard<std::mutex> lock(g_qpart_mutex);
+    const QPartCfg def;
+    g_qpart.mode = mode;
+    g_qpart.slice_shift = slice_shift ? slice_shift : def.slice_shift;
+    g_qpart.walk_bytes = walk_bytes ? walk_bytes : def.walk_bytes;
+    g_qpart.batch_keys = batch_keys ? batch_keys : def.batch_keys;
+    g_qpart.cap_scale = cap_scale > 0.0 ? std::min(cap_scale, 1.5) : def.cap_scale;
+    return BPHF_OK;
+}
+
+BPHF_API int bphf_query_partition_stats(int device, uint64_t* batches, uint64_t* fallbacks, uint32_t* stages) {
+    API_BEGIN
+    DeviceGuard guard(device);
+    if (batches) *batches = g_qp_batches.load();
+    if (stages) *stages = g_qp_last_stages.load();
+    if (fallbacks) {
+        unsigned long long f = 0;
+        CK(cudaDeviceSynchronize());
+        CK(cudaMemcpyFromSymbol(&f, g_qp_fallbacks, sizeof f));
+        *fallbacks = f;
+    }
+    return BPHF_OK;
+    API_END
+}
+
 BPHF_API int bphf_set_profile(int level) {
     g_profile = level < 0 ? 0 : (level > 2 ? 2 : level);
     return BPHF_OK;
@@ -2170,6 +2219,147 @@ static int query_grid(const DeviceInfo& info, uint64_t n) {
     return (int)std::max<uint64_t>(1, std::min<uint64_t>(blocks, (uint64_t)info.sm_count * 16));
 }
 
+// ---- partitioned lookup (qpart_kernels.cuh): structures larger than the L2 ---------------------------------------
+struct QPartPlan {
+    int n_stages = 0;                  // partitioned stages (levels 0..n_stages-1); the walk stage starts at level n_stages
+    uint32_t shift[QP_MAX_STAGES] = {}, n_buckets[QP_MAX_STAGES] = {};
+};
+static QPartPlan qpart_plan(const bphf_mphf* m, const QPartCfg& cfg, uint64_t n) {
+    QPartPlan p;
+    if (cfg.mode == 1 || !m->d_lvp || m->kc.kind == BPHF_KIND_STREAM || g_query_mode != 0) return p;
+    if (m->n_keys >= 0xfffffffeULL || m->n_levels < 2) return p;  // ranks travel as 32-bit values, 0xffffffff = None
+    if (cfg.mode == 0 && (n < cfg.min_keys || m->total_gran * 16 < cfg.min_struct_bytes)) return p;
+    uint64_t rest = m->total_gran * 16;  // bytes of granules of the levels not yet assigned to a stage
+    for (uint32_t l = 0; l + 1 < m->n_levels && p.n_stages < QP_MAX_STAGES; l++) {
+        if (rest <= cfg.walk_bytes) break;
+        const uint64_t bits = m->lv[l].bits;
+        uint32_t shift = std::max<uint32_t>(cfg.slice_shift, 5);
+        while (((bits + (1ull << shift) - 1) >> shift) > QP_MAX_BUCKETS) shift++;
+        const uint32_t nb = (uint32_t)((bits + (1ull << shift) - 1) >> shift);
+        if (nb < 2) break;  // the level is one slice: nothing to group
+        p.shift[p.n_stages] = shift;
+        p.n_buckets[p.n_stages] = nb;
+        p.n_stages++;
+        rest -= (bits + GRAN_BITS - 1) / GRAN_BITS * 16;
+    }
+    return p;
+}
+
+static int qp_grid(const DeviceInfo& info, const void* fn, int threads) {
+    static std::mutex mu;
+    static std::vector<std::pair<const void*, int>> cache;
+    std::lock_guard<std::mutex> lock(mu);
+    for (auto& e : cache)
+        if (e.first == fn) return info.sm_count * e.second;
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
+    cache.emplace_back(fn, per_sm);
+    return info.sm_count * per_sm;
+}
+
+static void launch_query_partitioned(const bphf_mphf* m, const DeviceInfo& info, const QPartCfg& cfg, const QPartPlan& plan,
+                                     const uint64_t* keys, uint64_t n, uint64_t* out, cudaStream_t s) {
+    const QView v = query_view(m);
+    const int S = plan.n_stages;
+    // (at most 2^29 keys per pass: the slots of a stage, ~1.1-2 per key, are 32-bit numbers)
+    const uint64_t B = std::min<uint64_t>(n, std::min<uint64_t>(std::max<uint64_t>(cfg.batch_keys, QP_UNIT), 1ull << 29));
+    auto round_unit = [](uint64_t x) { return (x + QP_UNIT - 1) / QP_UNIT * QP_UNIT; };
+    // st[0] = the caller's keys, st[1..S] = partitioned stages (levels 0..S-1), st[S+1] = walk stage
+    std::vector<QPStage> st(S + 2);
+    Staged scratch(s);
+    const size_t ctl_stage = (size_t)QP_MAX_LISTS * QP_CURSOR_STRIDE;
+    const size_t ctl_words = (size_t)(S + 2) * ctl_stage + 32;
+    uint32_t* d_ctl = scratch.scratch<uint32_t>(ctl_words);
+    uint32_t* d_overflow = d_ctl + (size_t)(S + 2) * ctl_stage;
+    for (int i = 0; i <= S + 1; i++) {
+        QPStage& q = st[i];
+        memset(&q, 0, sizeof q);
+        q.cursor = d_ctl + (size_t)i * ctl_stage;
+        if (i == 0) {
+            q.n_buckets = 1;
+            q.cap = (uint32_t)round_unit(B);
+            q.res = scratch.scratch<uint32_t>(q.cap);  // the slot of stage 1 every key went to
+            continue;
+        }
+        const bool walk = i == S + 1;
+        q.level = (uint32_t)(i - 1);
+        q.n_buckets = walk ? 1 : plan.n_buckets[i - 1];
+        q.shift = walk ? 0 : plan.shift[i - 1];
+        // a list receives B * (its bucket's share of the level's bits) / QP_SUBS keys at most when the queries hash
+        // uniformly (every key of the batch may reach the stage: absent keys miss everywhere)
+        const double share = walk ? 1.0 : std::min(1.0, (double)(1ull << q.shift) / (double)m->lv[q.level].bits);
+        const double mean = (double)B * share / QP_SUBS;
+        const uint64_t cap = (uint64_t)((mean * 1.03 + 6.0 * std::sqrt(mean) + QP_UNIT) * cfg.cap_scale);
+        q.cap = (uint32_t)round_unit(std::max<uint64_t>(cap, 1));
+        const uint64_t slots = (uint64_t)q.cap * q.n_buckets * QP_SUBS;  // < 2^32: slots travel as 32-bit words
+        q.keys = scratch.scratch<uint64_t>(slots);
+        q.res = scratch.scratch<uint32_t>(slots);
+        if (!walk) q.went = scratch.scratch<uint32_t>(slots / 32);
+    }
+    const int g_split0 = qp_grid(info, (const void*)qfirst_kernel, QP_THREADS);
+    const int g_split = qp_grid(info, (const void*)qprobe_kernel, QP_THREADS);
+    const int g_rest0 = qp_grid(info, (const void*)qrestore_kernel<true>, QP_THREADS);
+    const int g_rest = qp_grid(info, (const void*)qrestore_kernel<false>, QP_THREADS);
+    const int g_walk = qp_grid(info, (const void*)qwalk_kernel, QS_THREADS);
+    const int g_fall = qp_grid(info, (const void*)qfallback_kernel, QS_THREADS);
+    unsigned long long* d_fallbacks = nullptr;
+    CK(cudaGetSymbolAddress((void**)&d_fallbacks, g_qp_fallbacks));
+    // BPHF_Q_PROFILE=1 (measurement aid): CUDA events around every kernel of the first batch, printed to stderr
+    static const bool q_profile = getenv("BPHF_Q_PROFILE") != nullptr;
+    std::vector<cudaEvent_t> ev;
+    std::vector<std::string> ev_name;
+    auto mark = [&](const char* name) {
+        if (!q_profile) return;
+        cudaEvent_t e;
+        CK(cudaEventCreate(&e));
+        CK(cudaEventRecord(e, s));
+        ev.push_back(e);
+        ev_name.push_back(name);
+    };
+    for (uint64_t lo = 0; lo < n; lo += B) {
+        const uint64_t cnt = std::min(B, n - lo);
+        const bool prof = q_profile && lo == 0;
+        CK(cudaMemsetAsync(d_ctl, 0, ctl_words * 4, s));
+        QPStage first = st[0];
+        first.keys = const_cast<uint64_t*>(keys + lo);
+        if (prof) mark("begin");
+        qfirst_kernel<<<g_split0, QP_THREADS, 0, s>>>(v, first, st[1], cnt, d_overflow);
+        if (prof) mark("split first");
+        for (int i = 1; i <= S; i++) {
+            qprobe_kernel<<<g_split, QP_THREADS, 0, s>>>(v, st[i], st[i + 1], d_overflow);
+            if (prof) mark("split stage");
+        }
+        qwalk_kernel<<<g_walk, QS_THREADS, 0, s>>>(v, st[S + 1]);
+        if (prof) mark("walk");
+        for (int i = S; i >= 1; i--) {
+            qrestore_kernel<false><<<g_rest, QP_THREADS, 0, s>>>(st[i], st[i + 1], 0, nullptr);
+            if (prof) mark("restore stage");
+        }
+        qrestore_kernel<true><<<g_rest0, QP_THREADS, 0, s>>>(first, st[1], cnt, out + lo);
+        if (prof) mark("restore first");
+        qfallback_kernel<<<g_fall, QS_THREADS, 0, s>>>(v, keys + lo, cnt, out + lo, d_overflow, d_fallbacks);
+        if (prof) mark("fallback check");
+        CK(cudaGetLastError());
+        g_qp_batches++;
+    }
+    if (!ev.empty()) {
+        CK(cudaStreamSynchronize(s));
+        std::string line = "[bphf q-profile] stages " + std::to_string(S) + ", batch " + std::to_string(std::min(B, n)) + " keys:";
+        float total = 0;
+        for (size_t i = 1; i < ev.size(); i++) {
+            float ms = 0;
+            CK(cudaEventElapsedTime(&ms, ev[i - 1], ev[i]));
+            total += ms;
+            char buf[96];
+            snprintf(buf, sizeof buf, " %s %.3f", ev_name[i].c_str(), ms);
+            line += buf;
+        }
+        fprintf(stderr, "%s | total %.3f ms\n", line.c_str(), total);
+        for (cudaEvent_t e : ev) cudaEventDestroy(e);
+    }
+    g_qp_last_stages = (uint32_t)S;
+}
+
 // stream_kc: segment tables of the query batch for a BPHF_KIND_STREAM handle (keys == nullptr: key i is index i)
 static void launch_query(const bphf_mphf* m, const DeviceInfo& info, const uint64_t* keys, uint64_t n, uint64_t* out, cudaStream_t s,
                          const KeyCfg* stream_kc = nullptr) {
@@ -2183,6 +2373,16 @@ static void launch_query(const bphf_mphf* m, const DeviceInfo& info, const uint6
         return;
     }
     if (v.lvp && g_query_mode == 0) {
+        QPartCfg cfg;
+        {
+            std::lock_guard<std::mutex> lock(g_qpart_mutex);
+            cfg = g_qpart;
+        }
+        const QPartPlan plan = qpart_plan(m, cfg, n);
+        if (plan.n_stages > 0) {
+            launch_query_partitioned(m, info, cfg, plan, keys, n, out, s);
+            return;
+        }
         const uint64_t tiles = (n + (uint64_t)QS_WTILE * QS_WARPS - 1) / ((uint64_t)QS_WTILE * QS_WARPS);
         // persistent CTAs: exactly one wave of resident CTAs, each walks tiles blockIdx, +gridDim, ...
         static int per_sm = 0;

@@ -219,8 +219,22 @@ __device__ __forceinline__ uint32_t wqueue_append(bool miss, uint32_t i, uint16_
     return count + __popc(m);
 }
 
-__global__ void __launch_bounds__(QS_THREADS, 8)
-    query_sync_kernel(QView v, const uint64_t* __restrict__ keys, uint64_t n, uint64_t* __restrict__ out) {
+// the 256-key tiles of a dense key array
+struct QSDenseTiles {
+    uint64_t n;
+    __device__ __forceinline__ uint64_t count() const { return (n + QS_WTILE - 1) / QS_WTILE; }
+    __device__ __forceinline__ void locate(uint64_t tile, uint64_t* base, uint32_t* t_n) const {
+        *base = tile * QS_WTILE;
+        *t_n = (uint32_t)min((uint64_t)QS_WTILE, n - *base);
+    }
+};
+// SUB = false: Mphf::hash of the keys from level 0, ranks (u64, BPHF_NONE) to out.
+// SUB = true: the last stage of the partitioned lookup (qpart_kernels.cuh): the keys reached level `level0` unresolved,
+// the walk starts there and the ranks go to out32 (0xffffffff = None: the caller made sure every rank is smaller).
+// Tiles: where tile t of the key list starts (the same offset applies to the output) and how many keys it holds.
+template <bool SUB, class Tiles>
+__device__ __forceinline__ void query_sync_body(const QView& v, const Tiles& tiles, const uint64_t* __restrict__ keys,
+                                                uint64_t* __restrict__ out, uint32_t* __restrict__ out32, uint32_t level0) {
     __shared__ QLevelP lv[BPHF_MAX_LEVELS + 1];
     __shared__ uint64_t res_all[QS_WARPS][QS_WTILE];      // key while unresolved, rank (or NONE) once resolved
     __shared__ uint16_t queue_all[QS_WARPS][2][QS_WTILE];
@@ -231,11 +245,13 @@ __global__ void __launch_bounds__(QS_THREADS, 8)
     const uint4* __restrict__ q = v.packed;
     const KeyCfg kc = v.kc;
     const uint32_t n_levels = v.n_levels;
-    const uint64_t n_tiles = (n + QS_WTILE - 1) / QS_WTILE;
+    const uint32_t l0 = SUB ? level0 : 0u;  // first level of the walk
+    const uint64_t n_tiles = tiles.count();
     const uint64_t w_stride = (uint64_t)gridDim.x * QS_WARPS;
     for (uint64_t tile = (uint64_t)blockIdx.x * QS_WARPS + warp; tile < n_tiles; tile += w_stride) {
-        const uint64_t base = tile * QS_WTILE;
-        const uint32_t t_n = (uint32_t)min((uint64_t)QS_WTILE, n - base);
+        uint64_t base;
+        uint32_t t_n;
+        tiles.locate(tile, &base, &t_n);
         uint32_t n_q = 0;
         // ---- round 0: every key of the tile against level 0 (batches of 4 independent probes per lane)
 #pragma unroll
@@ -250,24 +266,24 @@ __global__ void __launch_bounds__(QS_THREADS, 8)
             }
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                pp[j] = packed_slot(kc, lv[0], key[j]);
-                g[j] = __ldg(q + lv[0].gran_off + pp[j].g);
+                pp[j] = packed_slot(kc, lv[l0], key[j]);
+                g[j] = __ldg(q + lv[l0].gran_off + pp[j].g);
             }
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 const uint32_t i = (h + j) * 32 + lane;
                 uint64_t rank;
-                const bool hit = packed_hit(lv[0], g[j], pp[j].bit, &rank);
+                const bool hit = packed_hit(lv[l0], g[j], pp[j].bit, &rank);
                 res[i] = hit ? rank : key[j];
                 n_q = wqueue_append(!hit && i < t_n, i, queue_all[warp][1], n_q);
             }
         }
         __syncwarp();
         // ---- round r: the queue against level r, two entries per lane in flight
-        uint32_t r = 1;
+        uint32_t r = l0 + 1;
         for (; r < n_levels && n_q > QS_STRAGGLERS; r++) {
-            const uint16_t* __restrict__ qin = queue_all[warp][r & 1];
-            uint16_t* __restrict__ qout = queue_all[warp][(r + 1) & 1];
+            const uint16_t* __restrict__ qin = queue_all[warp][(r - l0) & 1];  // (round 0 filled queue 1)
+            uint16_t* __restrict__ qout = queue_all[warp][(r - l0 + 1) & 1];
             const QLevelP L = lv[r];
             uint32_t n_out = 0;
             for (uint32_t t0 = 0; t0 < n_q; t0 += 64) {
@@ -304,7 +320,7 @@ __global__ void __launch_bounds__(QS_THREADS, 8)
         // The round loop also ends when the levels run out (r == n_levels) with ANY number of keys still queued
         // (absent keys against a shallow MPHF): every queued entry is drained, not just the first 32.
         for (uint32_t t = lane; t < n_q; t += 32) {
-            const uint32_t i = queue_all[warp][r & 1][t];
+            const uint32_t i = queue_all[warp][(r - l0) & 1][t];
             const uint64_t key = res[i];
             uint64_t rank = BPHF_NONE;
             for (uint32_t l = r; l < n_levels; l++) {
@@ -322,10 +338,18 @@ __global__ void __launch_bounds__(QS_THREADS, 8)
 #pragma unroll
         for (int j = 0; j < QS_KPL; j++) {
             const uint32_t i = j * 32 + lane;
-            if (i < t_n) out[base + i] = res[i];
+            if (i < t_n) {
+                if (SUB) __stcs(out32 + base + i, (uint32_t)res[i]);  // BPHF_NONE truncates to 0xffffffff
+                else out[base + i] = res[i];
+            }
         }
         __syncwarp();
     }
+}
+
+__global__ void __launch_bounds__(QS_THREADS, 8)
+    query_sync_kernel(QView v, const uint64_t* __restrict__ keys, uint64_t n, uint64_t* __restrict__ out) {
+    query_sync_body<false>(v, QSDenseTiles{n}, keys, out, nullptr, 0);
 }
 
 // create_map as an out-of-place scatter: keys_out[hash(k)] = k, values_out[hash(k)] = v.
