@@ -257,6 +257,8 @@ def extra_configs(pkg, L, device, stream, orc):
         res0[name] = e
         del keys, res, m
     out["configs0_new_1M"] = res0
+    # ---- configs[3]: Mphf::hash (src/lib.rs:324-335) of 1e9 in-set keys against the 435 MB structure of 1e9 keys
+    out["configs3_lookup_1e9"] = config3_lookup(pkg, L, device, stream, orc)
     # ---- configs[4]
     n5 = 500_000_000
     free_b, _ = torch.cuda.mem_get_info(device)
@@ -310,6 +312,62 @@ def extra_configs(pkg, L, device, stream, orc):
                                       "single-threaded in the reference, src/hashmap.rs:27-66)"}
     out["configs4_boomhashmap_5e8"] = res5
     return out
+
+
+def config3_lookup(pkg, L, device, stream, orc, n=1_000_000_000):
+    """BASELINE configs[3] on one GPU: n = 1e9 keys built once, then all n looked up, keys and ranks device resident.  Timed
+    with CUDA events on `stream` for the plain kernel (every probe of the big levels is a random DRAM sector) and for the
+    partitioned kernels (csrc/qpart_kernels.cuh, what the library picks on its own for this size); both outputs must be
+    the same permutation of 0..n-1.  CPU: the oracle's hash over a bounded sample against a 1e8-key structure."""
+    import torch
+    free_b, _ = torch.cuda.mem_get_info(device)
+    if free_b < 60e9:
+        return {"skipped": "needs ~45 GB of free device memory, %.0f GB free" % (free_b / 1e9)}
+    dev = "cuda:%d" % device
+    keys = torch.empty(n, dtype=torch.int64, device=dev)
+    assert L.bphf_keygen_u64(C.c_void_p(keys.data_ptr()), 0, n, 1, 0, device, None) == 0
+    m = pkg.Mphf.new_parallel(GAMMA, keys, None)
+    tw, tr, _ = m.total_dims()
+    res = torch.empty_like(keys)
+    peak, _ = measured_peaks()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    r = {"n_keys": n, "levels": m.num_levels, "structure_bytes": 8 * (tw + tr)}
+    sums = []
+    for label, mode in (("plain_kernel", 1), ("partitioned", 0)):
+        assert L.bphf_set_query_partition(mode, 0, 0, 0, 0.0) == 0
+        m.hash_batch(keys, out=res, stream=stream)
+        reps = 3
+        e0.record(stream)
+        for _ in range(reps):
+            m.hash_batch(keys, out=res, stream=stream)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        bad, sm, xr = C.c_uint64(1), C.c_uint64(), C.c_uint64()
+        assert L.bphf_check_permutation(C.c_void_p(res.data_ptr()), n, device, C.byref(bad)) == 0
+        assert L.bphf_checksum_u64(C.c_void_p(res.data_ptr()), n, device, C.byref(sm), C.byref(xr)) == 0
+        sums.append((sm.value, xr.value))
+        r[label] = {"ms": ms, "Mkeys_s": n / ms / 1e3, "permutation_ok": bad.value == 0,
+                    "frac_of_hbm": (16.0 * n + 8.0 * (tw + tr)) / (ms * 1e-3) / 1e9 / peak}
+    assert L.bphf_set_query_partition(0, 0, 0, 0, 0.0) == 0
+    b, f, st = C.c_uint64(0), C.c_uint64(0), C.c_uint32(0)
+    assert L.bphf_query_partition_stats(device, C.byref(b), C.byref(f), C.byref(st)) == 0
+    r["partitioned"].update({"stages": st.value, "batches_redone_by_the_plain_kernel": f.value,
+                             "same_ranks_as_the_plain_kernel": sums[0] == sums[1]})
+    r["frac_of_hbm_counts"] = "8 B key in + 8 B rank out per lookup + the structure once, over the measured copy bandwidth"
+    del keys, res, m
+    if orc is not None:
+        nb, nq = 100_000_000, 20_000_000
+        threads = host_threads()
+        hk = orc.keygen(nb, seed=1, kind=0)
+        ref = orc.OracleMphf.new_parallel(GAMMA, hk, None, nthreads=threads)
+        t1, _ = _timed(lambda: ref.hash_batch(hk[:nq], nthreads=1), 1, lambda: None)
+        tt, _ = _timed(lambda: ref.hash_batch(hk[:nq], nthreads=threads), 1, lambda: None)
+        r["cpu_sample"] = {"structure_keys": nb, "lookups": nq, "Mkeys_s_1core": nq / t1 / 1e6, "Mkeys_s_all_cores": nq / tt / 1e6,
+                           "cores": threads, "what": "oracle Mphf::hash over a bounded sample (the reference's hash is a "
+                                                     "single-threaded call; all cores = one batch split over the host threads)"}
+        del ref, hk
+    return r
 
 
 def north_star_1e9(pkg, L, local_rank, rank, world, dev, stream, peak):

@@ -2294,7 +2294,7 @@ static void launch_query_partitioned(const bphf_mphf* m, const DeviceInfo& info,
         const uint64_t slots = (uint64_t)q.cap * q.n_buckets * QP_SUBS;  // < 2^32: slots travel as 32-bit words
         q.keys = scratch.scratch<uint64_t>(slots);
         q.res = scratch.scratch<uint32_t>(slots);
-        if (!walk) q.went = scratch.scratch<uint32_t>(slots / 32);
+        if (!walk) q.went = scratch.scratch<uint8_t>(slots / 8);
     }
     const int g_split0 = qp_grid(info, (const void*)qfirst_kernel, QP_THREADS);
     const int g_split = qp_grid(info, (const void*)qprobe_kernel, QP_THREADS);

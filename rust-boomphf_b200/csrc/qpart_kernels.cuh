@@ -46,7 +46,7 @@ constexpr uint32_t QP_NONE32 = 0xffffffffu;      // rank of "no level claims the
 constexpr uint32_t QP_CURSOR_STRIDE = 32;        // u32 per cursor: one 128-byte line each
 constexpr int QP_MAX_STAGES = 4;
 #ifndef QP_SPLIT_CTAS
-#define QP_SPLIT_CTAS 3   // CTAs per SM of the probing kernel: 80 registers; at 4 (64 registers) it spills and runs 30 % slower
+#define QP_SPLIT_CTAS 3   // CTAs per SM of the probing kernel: 80 registers; at 4 (64 registers, spills) it measured 30 % slower
 #endif
 #ifndef QP_PROBE_BATCH
 #define QP_PROBE_BATCH 4  // granule loads of a lane in flight together (8 at 2 CTAs per SM measured no faster)
@@ -57,7 +57,7 @@ constexpr int QP_MAX_STAGES = 4;
 struct QPStage {
     uint64_t* keys;
     uint32_t* res;     // per entry: its rank (or QP_NONE32), or -- while its `went` bit is set -- its slot in the next stage
-    uint32_t* went;    // [slot / 32]  word (unit, iteration): bit `lane` = the entry went on to the next stage
+    uint8_t* went;     // [slot / 8]  byte (unit, lane): bit `it` = the lane's entry `it` went on to the next stage
     uint32_t* cursor;  // [list * QP_CURSOR_STRIDE]  fill of each list
     uint32_t n_buckets, shift, cap, level;  // cap: entries per list, a multiple of QP_UNIT
 };
@@ -93,32 +93,33 @@ struct QPLoc {
     uint64_t slot;  // first entry of the unit in the stage's arrays (multiple of QP_UNIT)
     uint32_t n;     // entries of the unit that exist
 };
-__device__ __forceinline__ QPLoc qp_locate(const QPStage& st, const uint32_t* pre, const uint32_t* fill, uint32_t item) {
-    uint32_t lo = 0, hi = st.n_buckets * QP_SUBS;  // largest l with pre[l] <= item (item < pre[hi])
-    while (hi - lo > 1) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (pre[mid] <= item) lo = mid;
-        else hi = mid;
+// A warp visits its units in increasing order: the list of the next one is found by walking on from the last one's
+// (lists hold ~2000 units of a 2^27-key batch, a persistent grid's stride is ~3500: one or two steps).
+struct QPWalker {
+    uint32_t lo = 0;  // list of the last unit located
+    __device__ __forceinline__ QPLoc locate(const QPStage& st, const uint32_t* pre, const uint32_t* fill, uint32_t item) {
+        while (pre[lo + 1] <= item) lo++;  // (item < pre[n_lists]: stops at the list that holds it, empty lists are skipped)
+        const uint32_t unit = item - pre[lo];
+        QPLoc r;
+        r.slot = (uint64_t)lo * st.cap + (uint64_t)unit * QP_UNIT;
+        r.n = min((uint32_t)QP_UNIT, fill[lo] - unit * QP_UNIT);
+        return r;
     }
-    const uint32_t unit = item - pre[lo];
-    QPLoc r;
-    r.slot = (uint64_t)lo * st.cap + (uint64_t)unit * QP_UNIT;
-    r.n = min((uint32_t)QP_UNIT, fill[lo] - unit * QP_UNIT);
-    return r;
-}
+};
 
-// Positions for the entries of a unit that go on: lane's entry `it` goes to bucket c[it] (or nowhere: go bit clear).
-// On return slot[it] = the entry's slot in stage nxt, or QP_NONE32 when the list was full (overflow raised).
-// cnt: the warp's 16 counters in shared memory.
-__device__ __forceinline__ void qp_place(const uint32_t (&c)[QP_KPL], uint32_t go, const QPStage& nxt, uint32_t sub,
-                                         uint32_t* __restrict__ cnt, uint32_t* __restrict__ overflow,
-                                         uint32_t (&slot)[QP_KPL]) {
+// Positions for the entries of a unit that go on: the lane's entry `it` goes to bucket (cpack >> 4 it) & 15 when bit it
+// of `go` is set.  On return word[it] of such an entry = its slot in stage nxt, or QP_NONE32 (and its go bit cleared)
+// when the list was full (overflow raised); the other words are left alone.  cnt: the warp's 16 counters in shared
+// memory.  (Buckets packed four bits each and one in/out array: the probing kernel has 80 registers to live in.)
+__device__ __forceinline__ uint32_t qp_place(uint32_t cpack, uint32_t go, const QPStage& nxt, uint32_t sub,
+                                             uint32_t* __restrict__ cnt, uint32_t* __restrict__ overflow,
+                                             uint32_t (&word)[QP_KPL]) {
     const uint32_t lane = threadIdx.x & 31;
     if (lane < 16) cnt[lane] = 0;
     __syncwarp();
 #pragma unroll
-    for (int it = 0; it < QP_KPL; it++)
-        slot[it] = ((go >> it) & 1u) ? atomicAdd(cnt + c[it], 1u) : 0u;  // position within the unit's run of the bucket
+    for (int it = 0; it < QP_KPL; it++)  // position within the unit's run of the bucket
+        if ((go >> it) & 1u) word[it] = atomicAdd(cnt + ((cpack >> (4 * it)) & 15u), 1u);
     __syncwarp();
     if (lane < nxt.n_buckets) {
         const uint32_t run = cnt[lane];
@@ -132,10 +133,19 @@ __device__ __forceinline__ void qp_place(const uint32_t (&c)[QP_KPL], uint32_t g
     __syncwarp();
 #pragma unroll
     for (int it = 0; it < QP_KPL; it++) {
-        const uint32_t pos = cnt[c[it]] + slot[it];
-        slot[it] = (((go >> it) & 1u) && pos < nxt.cap) ? (c[it] * QP_SUBS + sub) * nxt.cap + pos : QP_NONE32;
+        if ((go >> it) & 1u) {
+            const uint32_t c = (cpack >> (4 * it)) & 15u;
+            const uint32_t pos = cnt[c] + word[it];
+            if (pos < nxt.cap) {
+                word[it] = (c * QP_SUBS + sub) * nxt.cap + pos;
+            } else {
+                word[it] = QP_NONE32;
+                go &= ~(1u << it);
+            }
+        }
     }
     __syncwarp();  // cnt is reused by the warp's next unit
+    return go;
 }
 
 // The caller's keys (n_first of them) are split by their level nxt.level slot; first.res takes the slot of every key.
@@ -156,20 +166,22 @@ __global__ void __launch_bounds__(QP_THREADS, 4)
         const uint64_t slot0 = (uint64_t)item * QP_UNIT;
         const uint32_t n = (uint32_t)min((uint64_t)QP_UNIT, n_first - slot0);
         uint64_t key[QP_KPL];
-        uint32_t c[QP_KPL], slot[QP_KPL];
-        uint32_t go = 0;  // bit it: the lane's entry `it` exists
+        uint32_t slot[QP_KPL];
+        uint32_t go = 0;     // bit it: the lane's entry `it` exists
+        uint32_t cpack = 0;  // four bits per entry: its bucket
 #pragma unroll
         for (int it = 0; it < QP_KPL; it++) {
             const uint32_t e = it * 32 + lane;
             key[it] = e < n ? __ldcs(reinterpret_cast<const unsigned long long*>(first.keys) + slot0 + e) : 0ULL;
             go |= (e < n ? 1u : 0u) << it;
+            slot[it] = QP_NONE32;
         }
 #pragma unroll
-        for (int it = 0; it < QP_KPL; it++) c[it] = hashmod_small(kc, lv.sp0, key[it], lv.bits) >> nxt.shift;
-        qp_place(c, go, nxt, item & (QP_SUBS - 1), cnt, overflow, slot);
+        for (int it = 0; it < QP_KPL; it++) cpack |= (hashmod_small(kc, lv.sp0, key[it], lv.bits) >> nxt.shift) << (4 * it);
+        const uint32_t went = qp_place(cpack, go, nxt, item & (QP_SUBS - 1), cnt, overflow, slot);
 #pragma unroll
         for (int it = 0; it < QP_KPL; it++) {
-            if (slot[it] != QP_NONE32) nxt.keys[slot[it]] = key[it];
+            if ((went >> it) & 1u) nxt.keys[slot[it]] = key[it];
             const uint32_t e = it * 32 + lane;
             if (e < n) __stcs(first.res + slot0 + e, slot[it]);
         }
@@ -209,11 +221,14 @@ __global__ void __launch_bounds__(QP_THREADS, QP_SPLIT_CTAS)
     const uint32_t w_stride = gridDim.x * QP_WARPS;
     const uint32_t item0 = blockIdx.x * QP_WARPS + warp;
     const uint32_t n_mine = item0 < total ? (total - item0 + w_stride - 1) / w_stride : 0u;
+    QPWalker ahead, here;
     auto issue = [&](uint32_t j) {  // unit j of this warp -> ring stage j & 1 (whole units: the arrays are padded)
-        if (j < n_mine && lane == 0) {
-            const QPLoc u = qp_locate(cur, pre, fill, item0 + j * w_stride);
-            mbar_expect_tx(&mbar[j & 1], QP_UNIT * 8);
-            bulk_load(ring_all[warp][j & 1], cur.keys + u.slot, QP_UNIT * 8, &mbar[j & 1]);
+        if (j < n_mine) {
+            const QPLoc u = ahead.locate(cur, pre, fill, item0 + j * w_stride);
+            if (lane == 0) {
+                mbar_expect_tx(&mbar[j & 1], QP_UNIT * 8);
+                bulk_load(ring_all[warp][j & 1], cur.keys + u.slot, QP_UNIT * 8, &mbar[j & 1]);
+            }
         }
     };
     issue(0);
@@ -221,7 +236,7 @@ __global__ void __launch_bounds__(QP_THREADS, QP_SPLIT_CTAS)
     uint32_t phase = 0;  // bit b: parity of mbar[b]'s next completion
     for (uint32_t j = 0; j < n_mine; j++) {
         const uint32_t item = item0 + j * w_stride;
-        const QPLoc u = qp_locate(cur, pre, fill, item);
+        const QPLoc u = here.locate(cur, pre, fill, item);
         const uint32_t b = j & 1;
         mbar_wait(&mbar[b], (phase >> b) & 1u);
         phase ^= 1u << b;
@@ -253,37 +268,28 @@ __global__ void __launch_bounds__(QP_THREADS, QP_SPLIT_CTAS)
         }
         // bucket of the next stage: hashed for every entry, needed or not (a branch per entry costs more than the hash
         // of the entries that were found: some lane of the warp misses in every iteration anyway)
-        uint32_t c[QP_KPL], slot[QP_KPL];
+        uint32_t cpack = 0;
+        if (!one_bucket) {
 #pragma unroll
-        for (int jj = 0; jj < 4; jj++) {
-            if (one_bucket) {
-                c[2 * jj] = c[2 * jj + 1] = 0u;
-            } else {
+            for (int jj = 0; jj < 4; jj++) {
                 const ulonglong2 k2 = kq[jj * 32 + lane];
-                c[2 * jj] = hashmod_small(kc, lv[1].sp0, k2.x, lv[1].bits) >> nxt.shift;
-                c[2 * jj + 1] = hashmod_small(kc, lv[1].sp0, k2.y, lv[1].bits) >> nxt.shift;
+                cpack |= (hashmod_small(kc, lv[1].sp0, k2.x, lv[1].bits) >> nxt.shift) << (8 * jj);
+                cpack |= (hashmod_small(kc, lv[1].sp0, k2.y, lv[1].bits) >> nxt.shift) << (8 * jj + 4);
             }
         }
-        qp_place(c, go, nxt, item & (QP_SUBS - 1), cnt, overflow, slot);
+        const uint32_t went = qp_place(cpack, go, nxt, item & (QP_SUBS - 1), cnt, overflow, word);
 #pragma unroll
         for (int jj = 0; jj < 4; jj++) {
             const ulonglong2 k2 = kq[jj * 32 + lane];
-            if (slot[2 * jj] != QP_NONE32) nxt.keys[slot[2 * jj]] = k2.x;
-            if (slot[2 * jj + 1] != QP_NONE32) nxt.keys[slot[2 * jj + 1]] = k2.y;
+            if ((went >> (2 * jj)) & 1u) nxt.keys[word[2 * jj]] = k2.x;
+            if ((went >> (2 * jj + 1)) & 1u) nxt.keys[word[2 * jj + 1]] = k2.y;
         }
         __syncwarp();  // every lane is done with the ring stage
         if (lane == 0) fence_proxy_async();
         issue(j + 2);
+        // (an entry dropped at a full list has QP_NONE32 as its rank: the batch is redone anyway)
         uint2* __restrict__ res = reinterpret_cast<uint2*>(cur.res + u.slot);
-        uint32_t mine = 0;  // lane it < 8: who went on in iteration it
-#pragma unroll
-        for (int it = 0; it < QP_KPL; it++) {
-            const bool went = slot[it] != QP_NONE32;  // (an entry dropped at a full list keeps QP_NONE32: the batch is redone)
-            const uint32_t m = __ballot_sync(0xffffffffu, went);
-            if (lane == (uint32_t)it) mine = m;
-            if ((go >> it) & 1u) word[it] = slot[it];
-        }
-        if (lane < QP_KPL) __stcs(cur.went + (u.slot >> 5) + lane, mine);
+        __stcs(cur.went + (u.slot >> 3) + lane, (uint8_t)went);
 #pragma unroll
         for (int jj = 0; jj < 4; jj++) __stcs(res + jj * 32 + lane, make_uint2(word[2 * jj], word[2 * jj + 1]));
     }
@@ -299,9 +305,10 @@ struct QPListTiles {
     const QPStage& st;
     const uint32_t* pre;
     const uint32_t* fill;
+    QPWalker w;
     __device__ __forceinline__ uint64_t count() const { return pre[st.n_buckets * QP_SUBS]; }
-    __device__ __forceinline__ void locate(uint64_t tile, uint64_t* base, uint32_t* t_n) const {
-        const QPLoc u = qp_locate(st, pre, fill, (uint32_t)tile);
+    __device__ __forceinline__ void locate(uint64_t tile, uint64_t* base, uint32_t* t_n) {
+        const QPLoc u = w.locate(st, pre, fill, (uint32_t)tile);
         *base = u.slot;
         *t_n = u.n;
     }
@@ -310,7 +317,8 @@ struct QPListTiles {
 __global__ void __launch_bounds__(QS_THREADS, 8) qwalk_kernel(QView v, QPStage st) {
     __shared__ uint32_t pre[QP_SUBS + 1], fill[QP_SUBS];
     qp_prefix(st, pre, fill);
-    query_sync_body<true>(v, QPListTiles{st, pre, fill}, st.keys, nullptr, st.res, st.level);
+    QPListTiles tiles{st, pre, fill, QPWalker()};
+    query_sync_body<true>(v, tiles, st.keys, nullptr, st.res, st.level);
 }
 
 // cur.res (FIRST: out, 64-bit, in the caller's order) <- ranks of the entries that went on to stage nxt
@@ -327,6 +335,7 @@ __global__ void __launch_bounds__(QP_THREADS, 8)
         total = pre[cur.n_buckets * QP_SUBS];
     }
     const uint32_t* __restrict__ below = nxt.res;
+    QPWalker walker;
     const uint32_t w_stride = gridDim.x * QP_WARPS;
     for (uint32_t item = blockIdx.x * QP_WARPS + (threadIdx.x >> 5); item < total; item += w_stride) {
         if (FIRST) {
@@ -349,17 +358,16 @@ __global__ void __launch_bounds__(QP_THREADS, 8)
                            w[it] == QP_NONE32 ? (unsigned long long)BPHF_NONE : (unsigned long long)w[it]);
             }
         } else {
-            const QPLoc u = qp_locate(cur, pre, fill, item);
+            const QPLoc u = walker.locate(cur, pre, fill, item);
             uint2* __restrict__ res = reinterpret_cast<uint2*>(cur.res + u.slot);
-            const uint32_t mine = lane < QP_KPL ? __ldcs(cur.went + (u.slot >> 5) + lane) : 0u;
+            const uint32_t went = __ldcs(cur.went + (u.slot >> 3) + lane);
             uint2 w[4];
 #pragma unroll
             for (int j = 0; j < 4; j++) w[j] = __ldcs(res + j * 32 + lane);
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                const uint32_t m0 = __shfl_sync(0xffffffffu, mine, 2 * j), m1 = __shfl_sync(0xffffffffu, mine, 2 * j + 1);
-                if ((m0 >> lane) & 1u) w[j].x = __ldg(below + w[j].x);
-                if ((m1 >> lane) & 1u) w[j].y = __ldg(below + w[j].y);
+                if ((went >> (2 * j)) & 1u) w[j].x = __ldg(below + w[j].x);
+                if ((went >> (2 * j + 1)) & 1u) w[j].y = __ldg(below + w[j].y);
             }
 #pragma unroll
             for (int j = 0; j < 4; j++) __stcs(res + j * 32 + lane, w[j]);

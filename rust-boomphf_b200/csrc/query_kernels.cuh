@@ -233,7 +233,7 @@ struct QSDenseTiles {
 // the walk starts there and the ranks go to out32 (0xffffffff = None: the caller made sure every rank is smaller).
 // Tiles: where tile t of the key list starts (the same offset applies to the output) and how many keys it holds.
 template <bool SUB, class Tiles>
-__device__ __forceinline__ void query_sync_body(const QView& v, const Tiles& tiles, const uint64_t* __restrict__ keys,
+__device__ __forceinline__ void query_sync_body(const QView& v, Tiles tiles, const uint64_t* __restrict__ keys,
                                                 uint64_t* __restrict__ out, uint32_t* __restrict__ out32, uint32_t level0) {
     __shared__ QLevelP lv[BPHF_MAX_LEVELS + 1];
     __shared__ uint64_t res_all[QS_WARPS][QS_WTILE];      // key while unresolved, rank (or NONE) once resolved

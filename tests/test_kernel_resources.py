@@ -40,6 +40,10 @@ def _one(usage, *parts):
     (("cascade_kernelILb0E",), 128),
     (("query_sync_kernel",), 64),                  # 8 CTAs of 128 threads per SM
     (("tail_kernel", "KeyCfg"), 64),
+    (("qprobe_kernel",), 80),                      # partitioned lookup: 3 CTAs of 256 threads per SM, no spills
+    (("qfirst_kernel",), 64),
+    (("qrestore_kernelILb0E",), 32),               # a pure gather: 8 CTAs per SM
+    (("qwalk_kernel",), 64),
 ])
 def test_hot_kernels_keep_their_registers_and_do_not_spill(usage, parts, max_reg):
     reg, stack, _ = _one(usage, *parts)
@@ -82,3 +86,6 @@ def test_level_kernels_use_the_bulk_copy_engine_and_fire_and_forget_reductions(p
     assert mark.count("ATOMG.E.OR") >= 8 and mark.count("REDG.E.OR") >= 8     # 8 keys per thread, issued back to back
     look = _sass(pkg, usage, "query_sync_kernel")
     assert "LDG.E.128" in look                                                # one 16-byte granule per probe
+    probe = _sass(pkg, usage, "qprobe_kernel")                                # partitioned lookup: units arrive by TMA
+    for mnemonic in ("UBLKCP", "SYNCS.PHASECHK", "LDG.E.128", "ATOMS.ADD"):
+        assert mnemonic in probe, mnemonic

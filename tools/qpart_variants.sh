@@ -1,6 +1,4 @@
 # times the partitioned lookup kernels of library variants (BPHF_LIB_VARIANT tags given as arguments; "" = the product)
 for tag in "$@"; do
-  for sh in 28 27; do
-    echo "== variant '$tag' slice_shift $sh"; BPHF_Q_PROFILE=1 BPHF_LIB_VARIANT=$tag python tools/prof_qpart.py 1e9 134217728 2 $sh 2>&1 | grep -a "q-profile" | tail -1
-  done
+  echo "== variant '$tag'"; BPHF_Q_PROFILE=1 BPHF_LIB_VARIANT=$tag python tools/prof_qpart.py 1e9 134217728 2 2>&1 | grep -a "q-profile" | tail -1
 done
