@@ -41,7 +41,7 @@ def _one(usage, *parts):
     (("query_sync_kernel",), 64),                  # 8 CTAs of 128 threads per SM
     (("tail_kernel", "KeyCfg"), 64),
     (("qprobe_kernel",), 80),                      # partitioned lookup: 3 CTAs of 256 threads per SM, no spills
-    (("qfirst_kernel",), 64),
+    (("qfirst_kernel",), 48),                      # 5 CTAs per SM
     (("qrestore_kernelILb0E",), 32),               # a pure gather: 8 CTAs per SM
     (("qwalk_kernel",), 64),
 ])
