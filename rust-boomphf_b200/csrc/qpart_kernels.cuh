@@ -246,18 +246,30 @@ __global__ void __launch_bounds__(QP_THREADS, QP_SPLIT_CTAS)
         const ulonglong2* __restrict__ kq = reinterpret_cast<const ulonglong2*>(ring_all[warp][b]);
         uint32_t word[QP_KPL];  // rank of a hit
         uint32_t go = 0;        // bit it: the lane's entry `it` goes on to the next stage
-        // probe level cur.level, QP_PROBE_BATCH granules of the lane in flight at a time
+        // probe level cur.level, QP_PROBE_BATCH granules of the lane in flight at a time.  While they are in flight the
+        // same entries are hashed for the next level -- for every entry, needed or not: some lane of the warp misses in
+        // every iteration anyway, a branch per entry costs more than the hash of the entries that were found, and the
+        // arithmetic fills the wait for the granules
+        uint32_t cpack = 0;  // four bits per entry: its bucket in the next stage
 #pragma unroll
         for (int h = 0; h < QP_KPL; h += QP_PROBE_BATCH) {
             PackedProbe pp[QP_PROBE_BATCH];
             uint4 g[QP_PROBE_BATCH];
+            ulonglong2 k2[QP_PROBE_BATCH / 2];
 #pragma unroll
             for (int jj = 0; jj < QP_PROBE_BATCH; jj += 2) {
-                const ulonglong2 k2 = kq[((h + jj) >> 1) * 32 + lane];
-                pp[jj] = packed_slot(kc, lv[0], k2.x);
+                k2[jj >> 1] = kq[((h + jj) >> 1) * 32 + lane];
+                pp[jj] = packed_slot(kc, lv[0], k2[jj >> 1].x);
                 g[jj] = __ldg(q + lv[0].gran_off + pp[jj].g);
-                pp[jj + 1] = packed_slot(kc, lv[0], k2.y);
+                pp[jj + 1] = packed_slot(kc, lv[0], k2[jj >> 1].y);
                 g[jj + 1] = __ldg(q + lv[0].gran_off + pp[jj + 1].g);
+            }
+            if (!one_bucket) {
+#pragma unroll
+                for (int jj = 0; jj < QP_PROBE_BATCH; jj += 2) {
+                    cpack |= (hashmod_small(kc, lv[1].sp0, k2[jj >> 1].x, lv[1].bits) >> nxt.shift) << (4 * (h + jj));
+                    cpack |= (hashmod_small(kc, lv[1].sp0, k2[jj >> 1].y, lv[1].bits) >> nxt.shift) << (4 * (h + jj + 1));
+                }
             }
 #pragma unroll
             for (int jj = 0; jj < QP_PROBE_BATCH; jj++) {
@@ -267,17 +279,6 @@ __global__ void __launch_bounds__(QP_THREADS, QP_SPLIT_CTAS)
                 const bool hit = packed_hit(lv[0], g[jj], pp[jj].bit, &rk);
                 word[it] = (uint32_t)rk;
                 go |= ((!hit && e < u.n) ? 1u : 0u) << it;
-            }
-        }
-        // bucket of the next stage: hashed for every entry, needed or not (a branch per entry costs more than the hash
-        // of the entries that were found: some lane of the warp misses in every iteration anyway)
-        uint32_t cpack = 0;
-        if (!one_bucket) {
-#pragma unroll
-            for (int jj = 0; jj < 4; jj++) {
-                const ulonglong2 k2 = kq[jj * 32 + lane];
-                cpack |= (hashmod_small(kc, lv[1].sp0, k2.x, lv[1].bits) >> nxt.shift) << (8 * jj);
-                cpack |= (hashmod_small(kc, lv[1].sp0, k2.y, lv[1].bits) >> nxt.shift) << (8 * jj + 4);
             }
         }
         const uint32_t went = qp_place(cpack, go, nxt, item & (QP_SUBS - 1), cnt, overflow, word);
