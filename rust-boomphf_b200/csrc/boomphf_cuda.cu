@@ -2379,9 +2379,17 @@ static void launch_query(const bphf_mphf* m, const DeviceInfo& info, const uint6
             cfg = g_qpart;
         }
         const QPartPlan plan = qpart_plan(m, cfg, n);
-        if (plan.n_stages > 0) {
-            launch_query_partitioned(m, info, cfg, plan, keys, n, out, s);
-            return;
+        // (in place -- out == keys -- stays with the plain kernel: the fallback of a batch re-reads its keys)
+        if (plan.n_stages > 0 && (const void*)keys != (const void*)out) {
+            try {
+                launch_query_partitioned(m, info, cfg, plan, keys, n, out, s);
+                return;
+            } catch (const CudaFailure& f) {
+                // no room for the slice lists (~55 B per key and stage): the plain kernel needs no scratch.  Nothing
+                // of a batch is visible before its last kernel, and batches already done are simply redone.
+                if (f.code != BPHF_ERR_NOMEM) throw;
+                (void)cudaGetLastError();
+            }
         }
         const uint64_t tiles = (n + (uint64_t)QS_WTILE * QS_WARPS - 1) / ((uint64_t)QS_WTILE * QS_WARPS);
         // persistent CTAs: exactly one wave of resident CTAs, each walks tiles blockIdx, +gridDim, ...

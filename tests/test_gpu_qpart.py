@@ -165,3 +165,19 @@ def test_automatic_mode_takes_the_partitioned_path_beyond_the_l2_and_agrees_with
     assert b1 == b0 + 1 and f1 == f0 and stages >= 1, (b0, b1, f0, f1, stages, m.total_dims())
     assert torch.equal(got, plain)
     assert int((got == -1).sum()) > 1000  # (most absent keys land on a set bit of some level)
+
+
+def test_in_place_lookup_keeps_to_the_plain_kernel_and_is_right(pkg, oracle, part):
+    import torch
+    keys = oracle.keygen(300_000, seed=41, kind=0)
+    m = pkg.Mphf.new_parallel(1.7, keys, None)
+    ref = oracle.OracleMphf.new_parallel(1.7, keys)
+    q = _queries(oracle, keys, 20_000, seed=6)
+    buf = torch.from_numpy(q.view(np.int64).copy()).cuda()
+    part(2, 15, 4096, 0)
+    b0, _, _ = _stats(pkg)
+    m.hash_batch(buf, out=buf)          # out == keys
+    torch.cuda.synchronize()
+    b1, _, _ = _stats(pkg)
+    assert b1 == b0, "an in-place batch must not go through the partitioned kernels (their fallback re-reads the keys)"
+    assert np.array_equal(buf.cpu().numpy().view(np.uint64), ref.hash_batch(q, nthreads=0))
