@@ -28,6 +28,12 @@ import __graft_entry__ as ge  # noqa: E402
 # (profiles/r02_summary.md; n = 1e8, gamma = 1.7, one GPU -- only quoted for that workload)
 NCU_TRAFFIC_1E8 = {"mark_list_kernel": 0.8472e9 + 9.463e6, "cascade_kernel": 1.450e9 + 641.4e6}
 NCU_TRAFFIC_SOURCE = "ncu --set full, profiles/r02_summary.md (capture of this code state)"
+# the exchange-level kernels of a sharded build, per GPU at 1e8 keys per GPU: captured in one-shard mode
+# (BPHF_XCHG_WORLD1: the same per-GPU work, stores local instead of NVLink), profiles/r02d_ncu_xchg_table.md
+NCU_TRAFFIC_XCHG_1E8 = {"xscatter_kernel": 0.800e9 + 1.149e9,
+                        "xmark + xfinalize + xbits": (442.8e6 + 4.1e6) + 42.5e6 + (421.3e6 + 15.9e6)}
+NCU_TRAFFIC_XCHG_SOURCE = ("ncu --set full in one-shard exchange mode (same per-GPU work, local stores instead of NVLink), "
+                           "profiles/r02d_ncu_xchg_table.md")
 
 METRIC = "mphf_build_throughput"
 UNIT = "Mkeys/s"
@@ -702,9 +708,10 @@ def main():
     roofline = {
         "bound": "hbm", "kernel": k_name,
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-        "traffic": next((v for k, v in NCU_TRAFFIC_1E8.items() if k_name.startswith(k)), None)
-        if (world == 1 and n == 100_000_000) else None,
-        "traffic_source": NCU_TRAFFIC_SOURCE,
+        "traffic": (next((v for k, v in NCU_TRAFFIC_1E8.items() if k_name.startswith(k)), None)
+                    if world == 1 else next((v for k, v in NCU_TRAFFIC_XCHG_1E8.items() if k_name.startswith(k)), None))
+        if n == 100_000_000 else None,
+        "traffic_source": NCU_TRAFFIC_SOURCE if world == 1 else NCU_TRAFFIC_XCHG_SOURCE,
         "peak_source": peak_src, "kernel_ms": k_ms, "algorithmic_bytes_per_launch": k_bytes,
         "kernels": [{"kernel": c[0], "ms": c[1], "algorithmic_bytes": c[2],
                      "achieved": (c[2] / (c[1] * 1e-3) / 1e9) if c[1] > 0 else None} for c in cands],
