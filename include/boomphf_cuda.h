@@ -254,7 +254,8 @@ BPHF_API int bphf_set_query_mode(int mode);
 /* Lookups against structures larger than the L2 (BASELINE configs[3]; Mphf::hash, src/lib.rs:324-335, over a batch):
  * the queries are grouped by the slice of level 0 (then level 1, ...) their slot falls in, every slice is probed while
  * it is L2 resident, and the ranks are put back in the caller's order -- identical results, no random DRAM probe.
- * mode 0 (default) = used for device-resident batches >= 32 Mi keys against >= 96 MB of lookup structure, 1 = never, 2 = whenever the
+ * mode 0 (default) = used for device-resident batches >= 32 Mi keys against >= 200 MB of packed lookup structure
+ * (~3.5e8 keys at gamma 1.7: below that the L2 still serves the plain kernel better), 1 = never, 2 = whenever the
  * structure has a packed form and more than one level (tests).  The other arguments tune it, 0 = default:
  * slice_shift = log2 of the bits of a level per slice (28), walk_bytes = the trailing levels that fit this many bytes are
  * walked unpartitioned (40 MiB), batch_keys = queries per pass (2^27; scratch is ~55 B per key and stage),

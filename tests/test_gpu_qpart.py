@@ -140,10 +140,12 @@ def test_gamma_and_seed_do_not_matter_to_the_partition(pkg, oracle, part):
 
 
 def test_automatic_mode_takes_the_partitioned_path_beyond_the_l2_and_agrees_with_the_plain_kernel(pkg, part):
-    """natural scale: 2.6e8 keys -> 113 MB of lookup structure, 2^26 device-resident queries (in-set and absent); the
-    policy picks the partitioned kernels on its own and the ranks equal the plain kernel's, value for value"""
+    """natural scale: 4e8 keys -> 230 MB of packed lookup structure (the policy's threshold is 200 MB: below it the L2
+    still serves the plain kernel better), 2^26 device-resident queries (in-set and absent); the policy picks the
+    partitioned kernels on its own and the ranks equal the plain kernel's, value for value.  A 2e8-key structure
+    (115 MB) must stay with the plain kernel."""
     import torch
-    n, nq = 260_000_000, 1 << 26
+    n, nq = 400_000_000, 1 << 26
     L = pkg.lib()
     keys = torch.empty(n, dtype=torch.int64, device="cuda")
     assert L.bphf_keygen_u64(C.c_void_p(keys.data_ptr()), 0, n, 1, 0, 0, None) == 0
@@ -165,6 +167,15 @@ def test_automatic_mode_takes_the_partitioned_path_beyond_the_l2_and_agrees_with
     assert b1 == b0 + 1 and f1 == f0 and stages >= 1, (b0, b1, f0, f1, stages, m.total_dims())
     assert torch.equal(got, plain)
     assert int((got == -1).sum()) > 1000  # (most absent keys land on a set bit of some level)
+    del m, got, plain
+    small_keys = torch.empty(200_000_000, dtype=torch.int64, device="cuda")
+    assert L.bphf_keygen_u64(C.c_void_p(small_keys.data_ptr()), 0, 200_000_000, 1, 0, 0, None) == 0
+    small = pkg.Mphf.new_parallel(1.7, small_keys, None)
+    del small_keys
+    b2, _, _ = _stats(pkg)
+    small.hash_batch(q)
+    torch.cuda.synchronize()
+    assert _stats(pkg)[0] == b2, "a structure the L2 serves must stay with the plain kernel"
 
 
 def test_in_place_lookup_keeps_to_the_plain_kernel_and_is_right(pkg, oracle, part):
