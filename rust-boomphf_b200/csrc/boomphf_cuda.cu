@@ -135,6 +135,8 @@ static const DeviceInfo& device_info(int dev) {
                 CK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 60));
             }
         }
+        if (const char* e = getenv("BPHF_QP_CARVEOUT"))  // measurement aid: shared-memory carve-out of the probing lookup kernel
+            CK(cudaFuncSetAttribute(qprobe_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));
         CK(cudaFuncSetAttribute(scatter0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CK(cudaFuncSetAttribute(scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CK(cudaFuncSetAttribute(bucket_mark_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

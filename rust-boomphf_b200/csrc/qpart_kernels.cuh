@@ -48,6 +48,14 @@ constexpr int QP_MAX_STAGES = 4;
 #ifndef QP_SPLIT_CTAS
 #define QP_SPLIT_CTAS 3   // CTAs per SM of the probing kernel: 80 registers; at 4 (64 registers, spills) it measured 30 % slower
 #endif
+#ifndef QP_RING
+#define QP_RING 1         // 1: the units of the probing kernel arrive through a TMA ring in shared memory; 0: read in place + L1 prefetch (5 % slower)
+#endif
+#if QP_RING
+#define QP_KEY2(p) (*(p))
+#else
+#define QP_KEY2(p) __ldg(p)
+#endif
 #ifndef QP_PROBE_BATCH
 #define QP_PROBE_BATCH 4  // granule loads of a lane in flight together (8 at 2 CTAs per SM measured no faster)
 #endif
@@ -198,24 +206,28 @@ __global__ void __launch_bounds__(QP_THREADS, QP_FIRST_CTAS)
 // Entry e of a unit sits with lane (e % 64) / 2 at iteration 2 * (e / 64) + e % 2 (16-byte shared loads, 8-byte stores).
 __global__ void __launch_bounds__(QP_THREADS, QP_SPLIT_CTAS)
     qprobe_kernel(QView v, QPStage cur, QPStage nxt, uint32_t* __restrict__ overflow) {
+#if QP_RING
     __shared__ __align__(128) uint64_t ring_all[QP_WARPS][2][QP_UNIT];
     __shared__ __align__(8) uint64_t mbar_all[QP_WARPS][2];
+#endif
     __shared__ QLevelP lv[2];
     __shared__ uint32_t pre[QP_MAX_LISTS + 1], fill[QP_MAX_LISTS];
     __shared__ uint32_t cnt_all[QP_WARPS][16];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t* __restrict__ cnt = cnt_all[warp];
-    uint64_t* __restrict__ mbar = mbar_all[warp];
     if (threadIdx.x == 0) {
         lv[0] = v.lvp[cur.level];
         lv[1] = v.lvp[nxt.level];
     }
+#if QP_RING
+    uint64_t* __restrict__ mbar = mbar_all[warp];
     if (lane == 0) {
         mbar_init(&mbar[0], 1);
         mbar_init(&mbar[1], 1);
         fence_mbar_init();
         fence_proxy_async();
     }
+#endif
     qp_prefix(cur, pre, fill);
     const uint32_t total = pre[cur.n_buckets * QP_SUBS];
     const KeyCfg kc = v.kc;
@@ -225,6 +237,7 @@ __global__ void __launch_bounds__(QP_THREADS, QP_SPLIT_CTAS)
     const uint32_t item0 = blockIdx.x * QP_WARPS + warp;
     const uint32_t n_mine = item0 < total ? (total - item0 + w_stride - 1) / w_stride : 0u;
     QPWalker ahead, here;
+#if QP_RING
     auto issue = [&](uint32_t j) {  // unit j of this warp -> ring stage j & 1 (whole units: the arrays are padded)
         if (j < n_mine) {
             const QPLoc u = ahead.locate(cur, pre, fill, item0 + j * w_stride);
@@ -237,13 +250,30 @@ __global__ void __launch_bounds__(QP_THREADS, QP_SPLIT_CTAS)
     issue(0);
     issue(1);
     uint32_t phase = 0;  // bit b: parity of mbar[b]'s next completion
+#else
+    // no ring: the unit is read from global memory at each use (2 KB per warp: the later reads hit the L1) and the
+    // next unit is prefetched into the L1 one unit ahead -- the shared memory a ring takes (32 KB per CTA) is worth more
+    // as L1, where the random granule loads wait
+    auto issue = [&](uint32_t j) {
+        if (j < n_mine) {
+            const QPLoc u = ahead.locate(cur, pre, fill, item0 + j * w_stride);
+            if (lane < QP_UNIT * 8 / 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(cur.keys + u.slot + lane * 16));
+        }
+    };
+    issue(0);
+#endif
     for (uint32_t j = 0; j < n_mine; j++) {
         const uint32_t item = item0 + j * w_stride;
         const QPLoc u = here.locate(cur, pre, fill, item);
+#if QP_RING
         const uint32_t b = j & 1;
         mbar_wait(&mbar[b], (phase >> b) & 1u);
         phase ^= 1u << b;
         const ulonglong2* __restrict__ kq = reinterpret_cast<const ulonglong2*>(ring_all[warp][b]);
+#else
+        issue(j + 1);
+        const ulonglong2* __restrict__ kq = reinterpret_cast<const ulonglong2*>(cur.keys + u.slot);
+#endif
         uint32_t word[QP_KPL];  // rank of a hit
         uint32_t go = 0;        // bit it: the lane's entry `it` goes on to the next stage
         // probe level cur.level, QP_PROBE_BATCH granules of the lane in flight at a time.  While they are in flight the
@@ -258,7 +288,7 @@ __global__ void __launch_bounds__(QP_THREADS, QP_SPLIT_CTAS)
             ulonglong2 k2[QP_PROBE_BATCH / 2];
 #pragma unroll
             for (int jj = 0; jj < QP_PROBE_BATCH; jj += 2) {
-                k2[jj >> 1] = kq[((h + jj) >> 1) * 32 + lane];
+                k2[jj >> 1] = QP_KEY2(kq + ((h + jj) >> 1) * 32 + lane);
                 pp[jj] = packed_slot(kc, lv[0], k2[jj >> 1].x);
                 g[jj] = __ldg(q + lv[0].gran_off + pp[jj].g);
                 pp[jj + 1] = packed_slot(kc, lv[0], k2[jj >> 1].y);
@@ -284,24 +314,28 @@ __global__ void __launch_bounds__(QP_THREADS, QP_SPLIT_CTAS)
         const uint32_t went = qp_place(cpack, go, nxt, item & (QP_SUBS - 1), cnt, overflow, word);
 #pragma unroll
         for (int jj = 0; jj < 4; jj++) {
-            const ulonglong2 k2 = kq[jj * 32 + lane];
+            const ulonglong2 k2 = QP_KEY2(kq + jj * 32 + lane);
             if ((went >> (2 * jj)) & 1u) nxt.keys[word[2 * jj]] = k2.x;
             if ((went >> (2 * jj + 1)) & 1u) nxt.keys[word[2 * jj + 1]] = k2.y;
         }
+#if QP_RING
         __syncwarp();  // every lane is done with the ring stage
         if (lane == 0) fence_proxy_async();
         issue(j + 2);
+#endif
         // (an entry dropped at a full list has QP_NONE32 as its rank: the batch is redone anyway)
         uint2* __restrict__ res = reinterpret_cast<uint2*>(cur.res + u.slot);
         __stcs(cur.went + (u.slot >> 3) + lane, (uint8_t)went);
 #pragma unroll
         for (int jj = 0; jj < 4; jj++) __stcs(res + jj * 32 + lane, make_uint2(word[2 * jj], word[2 * jj + 1]));
     }
+#if QP_RING
     __syncwarp();
     if (lane == 0) {
         mbar_inval(&mbar[0]);
         mbar_inval(&mbar[1]);
     }
+#endif
 }
 
 // the units of the walk stage's lists as tiles of query_sync_body
